@@ -1,0 +1,300 @@
+// crt_device.cuh -- device-side data layout and the exact-arithmetic building blocks of the wavefront pipeline.
+//
+// Every floating-point expression on the result path is written with the explicit round-to-nearest intrinsics
+// (__fmul_rn / __fadd_rn / __fsub_rn / __fdiv_rn / __fsqrt_rn), which are never contracted into FMAs and are
+// IEEE-754 correctly rounded independent of -fmad / -prec-div / -prec-sqrt.  The library is additionally built with
+// --fmad=false.  The operand ORDER of each expression follows the reference, because the parity
+// bar is bit-exact hit ids and bit-identical float RGB.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace crtd {
+
+// ------------------------------------------------------------------------------------------------------------
+// HBM layout (all arrays immutable after upload, 16-byte aligned records)
+//
+//  nodes     2 x float4 per KD node, ALL trees in one array (mesh trees first, then the top-level tree).  Inside a
+//            tree the nodes are stored in the reference's VISITING order (child[1] subtree before child[0] subtree,
+//            KDTree.cpp:65-72 pushes 0 then 1 on a LIFO stack) so the fixed-order DFS needs no stack at all:
+//              lo = {min.x, min.y, min.z, a}   hi = {max.x, max.y, max.z, b}
+//              inner node : a = index of the next node when the slab test fails ("skip", end of its subtree)
+//              leaf node  : a = 0x80000000 | reference count, b = first reference; next node is always index + 1
+//            Passing nodes continue at index + 1.  A 32-byte node is exactly one DRAM/L2 sector.
+//  leaf_refs u32 GLOBAL triangle ids of the mesh trees' leaves, in the reference's stored order.
+//  top_refs  u32 mesh ids of the top-level tree's leaves.
+//  tri_geom  3 x float4 per triangle: {v0, n.x} {v1, n.y} {v2, n.z}  (48 B: everything Ray::intersectWithTriangle reads)
+//  tri_shade uint4 per triangle: {i0, i1, i2, mesh}  -- only touched once per ray, at shading time
+// ------------------------------------------------------------------------------------------------------------
+struct DMesh {
+  uint32_t node_begin, node_end;  // [begin, end) in `nodes`
+  uint32_t material;
+  uint32_t first_triangle;
+};
+struct DMaterial {
+  uint32_t type, smooth, texture;
+  float ior;
+  float albedo[3];
+  float pad;
+};
+struct DTexture {
+  uint32_t kind;
+  float color_a[3];
+  float color_b[3];
+  float scalar;
+  uint32_t width, height;
+  unsigned long long texel_offset;
+};
+struct DLight {
+  float pos[3];
+  float intensity;  // static_cast<float>(light.intentsity), exact for the u32 -> f32 conversion of the reference
+};
+
+struct DScene {
+  const float4 *nodes;
+  const uint32_t *leaf_refs;
+  const uint32_t *top_refs;
+  const float4 *tri_geom;
+  const uint4 *tri_shade;
+  const float4 *vtx_normal;
+  const float2 *vtx_uv;
+  const DMesh *meshes;
+  const DMaterial *materials;
+  const DTexture *textures;
+  const float *texels;
+  const DLight *lights;
+  uint32_t n_lights;
+  uint32_t top_begin, top_end;
+  uint32_t width, height;
+  float bg[3];
+};
+
+struct DCamera {
+  float pos[3];
+  float rot[9];
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// exact float helpers
+// ------------------------------------------------------------------------------------------------------------
+#define CRT_DI __device__ __forceinline__
+
+CRT_DI float fmul(float a, float b) { return __fmul_rn(a, b); }
+CRT_DI float fadd(float a, float b) { return __fadd_rn(a, b); }
+CRT_DI float fsub(float a, float b) { return __fsub_rn(a, b); }
+CRT_DI float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+CRT_DI float fsqrt(float a) { return __fsqrt_rn(a); }
+
+struct V3 {
+  float x, y, z;
+};
+CRT_DI V3 mk(float x, float y, float z) {
+  V3 r;
+  r.x = x;
+  r.y = y;
+  r.z = z;
+  return r;
+}
+CRT_DI V3 vsub(V3 a, V3 b) { return mk(fsub(a.x, b.x), fsub(a.y, b.y), fsub(a.z, b.z)); }
+CRT_DI V3 vadd(V3 a, V3 b) { return mk(fadd(a.x, b.x), fadd(a.y, b.y), fadd(a.z, b.z)); }
+// (a0*b0 + a1*b1) + a2*b2                                                         Vector.cpp:57-59
+CRT_DI float vdot(V3 a, V3 b) { return fadd(fadd(fmul(a.x, b.x), fmul(a.y, b.y)), fmul(a.z, b.z)); }
+// Vector.cpp:61-65
+CRT_DI V3 vcross(V3 a, V3 b) {
+  return mk(fsub(fmul(a.y, b.z), fmul(a.z, b.y)), fsub(fmul(a.z, b.x), fmul(a.x, b.z)),
+            fsub(fmul(a.x, b.y), fmul(a.y, b.x)));
+}
+CRT_DI V3 vscale(V3 a, float s) { return mk(fmul(a.x, s), fmul(a.y, s), fmul(a.z, s)); }  // Vector * float
+CRT_DI V3 sscale(float s, V3 a) { return mk(fmul(s, a.x), fmul(s, a.y), fmul(s, a.z)); }  // float * Vector
+CRT_DI float vlen(V3 a) { return fsqrt(fadd(fadd(fmul(a.x, a.x), fmul(a.y, a.y)), fmul(a.z, a.z))); }
+// Vector::normalize                                                             Vector.cpp:97-106
+CRT_DI V3 vnorm(V3 a) {
+  float l = vlen(a);
+  if (l == 0.0f) return a;
+  l = fdiv(1.0f, l);
+  return mk(fmul(a.x, l), fmul(a.y, l), fmul(a.z, l));
+}
+// Vector::reflect: *this - (2 * dot) * normal                                   Vector.cpp:119-122
+CRT_DI V3 vreflect(V3 d, V3 n) { return vsub(d, sscale(fmul(2.0f, vdot(d, n)), n)); }
+// std::max(a,b) = (a<b)?b:a, std::min(a,b) = (b<a)?b:a -- written as selects so NaN operands behave like libstdc++
+CRT_DI float stdmax(float a, float b) { return (a < b) ? b : a; }
+CRT_DI float stdmin(float a, float b) { return (b < a) ? b : a; }
+
+#define CRT_FLT_EPSILON 1.1920928955078125e-7f
+#define CRT_FLT_MAX 3.402823466e+38f
+#define CRT_INVALID 0xFFFFFFFFu
+#define CRT_LEAF_FLAG 0x80000000u
+
+// ------------------------------------------------------------------------------------------------------------
+// rays
+// ------------------------------------------------------------------------------------------------------------
+struct Ray {
+  V3 o, d;
+  V3 inv;         // 1.0f / d per axis (BoundingBox.h:95), hoisted: depends on the ray only
+  uint32_t flags; // bit i: |d_i| < FLT_EPSILON (BoundingBox.h:90); bit 3: primary ray (back-face cull, Ray.cpp:13)
+};
+
+CRT_DI void ray_prepare(Ray &r, bool primary) {
+  r.flags = primary ? 8u : 0u;
+  if (fabsf(r.d.x) < CRT_FLT_EPSILON) r.flags |= 1u;
+  if (fabsf(r.d.y) < CRT_FLT_EPSILON) r.flags |= 2u;
+  if (fabsf(r.d.z) < CRT_FLT_EPSILON) r.flags |= 4u;
+  r.inv.x = fdiv(1.0f, r.d.x);
+  r.inv.y = fdiv(1.0f, r.d.y);
+  r.inv.z = fdiv(1.0f, r.d.z);
+}
+
+// RayTracer::getRay + the second normalisation of shootRay                      RayTracer.cpp:61-80, 420
+CRT_DI void primary_ray(const DCamera &cam, uint32_t W, uint32_t H, uint32_t row, uint32_t col, V3 &o, V3 &d) {
+  float x = fadd((float)col, 0.5f);
+  float y = fadd((float)row, 0.5f);
+  x = fdiv(x, (float)W);
+  y = fdiv(y, (float)H);
+  x = fsub(fmul(2.0f, x), 1.0f);
+  y = fsub(1.0f, fmul(2.0f, y));
+  x = fmul(x, fdiv((float)W, (float)H));
+  const float z = -1.0f;
+  // Vector * Matrix<3>                                                          Matrix.h:137-142
+  V3 dr = mk(fadd(fadd(fmul(x, cam.rot[0]), fmul(y, cam.rot[3])), fmul(z, cam.rot[6])),
+             fadd(fadd(fmul(x, cam.rot[1]), fmul(y, cam.rot[4])), fmul(z, cam.rot[7])),
+             fadd(fadd(fmul(x, cam.rot[2]), fmul(y, cam.rot[5])), fmul(z, cam.rot[8])));
+  d = vnorm(vnorm(dr));
+  o = mk(cam.pos[0], cam.pos[1], cam.pos[2]);
+}
+
+// BoundingBox::hasIntersection                                                  BoundingBox.h:85-108
+// (no t1 >= 0 test: boxes behind the origin pass; NaN bounds never reject -- both as in the reference)
+CRT_DI bool slab_test(const float4 lo, const float4 hi, const Ray &r) {
+  float t0 = -CRT_FLT_MAX, t1 = CRT_FLT_MAX;
+#define CRT_SLAB_AXIS(bit, O, I, MN, MX)                     \
+  if (r.flags & bit) {                                       \
+    if (O < MN || O > MX) return false;                      \
+  } else {                                                   \
+    float tn = fmul(fsub(MN, O), I);                         \
+    float tf = fmul(fsub(MX, O), I);                         \
+    if (tn > tf) {                                           \
+      float tmp = tn;                                        \
+      tn = tf;                                               \
+      tf = tmp;                                              \
+    }                                                        \
+    t0 = stdmax(t0, tn);                                     \
+    t1 = stdmin(t1, tf);                                     \
+    if (t0 > t1) return false;                               \
+  }
+  CRT_SLAB_AXIS(1u, r.o.x, r.inv.x, lo.x, hi.x)
+  CRT_SLAB_AXIS(2u, r.o.y, r.inv.y, lo.y, hi.y)
+  CRT_SLAB_AXIS(4u, r.o.z, r.inv.z, lo.z, hi.z)
+#undef CRT_SLAB_AXIS
+  return true;
+}
+
+// Ray::intersectWithTriangle + Triangle::pointIsInTriangle                       Ray.cpp:9-31, Triangle.cpp:37-57
+// Returns true for a candidate; t may be NaN / inf exactly like the reference.
+CRT_DI bool triangle_test(const float4 g0, const float4 g1, const float4 g2, const Ray &r, float &t_out, V3 &p_out) {
+  const V3 n = mk(g0.w, g1.w, g2.w);
+  const V3 v0 = mk(g0.x, g0.y, g0.z);
+  const float nd = vdot(r.d, n);
+  if ((r.flags & 8u) && nd >= 0.0f) return false;
+  const float dist = -vdot(v0, n);
+  const float t = fdiv(-fadd(vdot(n, r.o), dist), nd);
+  if (t < 0.0f) return false;
+  const V3 p = vadd(r.o, vscale(r.d, t));
+  const V3 v1 = mk(g1.x, g1.y, g1.z);
+  const V3 v2 = mk(g2.x, g2.y, g2.z);
+  if (vdot(n, vcross(vsub(v1, v0), vsub(p, v0))) < -CRT_FLT_EPSILON) return false;
+  if (vdot(n, vcross(vsub(v2, v1), vsub(p, v1))) < -CRT_FLT_EPSILON) return false;
+  if (vdot(n, vcross(vsub(v0, v2), vsub(p, v2))) < -CRT_FLT_EPSILON) return false;
+  t_out = t;
+  p_out = p;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Stack-free two-level traversal state (one per lane, registers only).
+//   top        cursor in the top-level tree          [top_begin, top_end)
+//   mref/mend  cursor in the current top-level leaf's mesh list
+//   cur/cend   cursor in the current mesh tree
+//   tref/tend  cursor in the current mesh leaf's triangle list
+// Order of events = the reference's: KDTree.cpp:127-166 (top level) around KDTree.cpp:48-87 (per mesh).
+// ------------------------------------------------------------------------------------------------------------
+struct Trav {
+  uint32_t top, mref, mend, cur, cend, tref, tend;
+};
+CRT_DI void trav_begin(Trav &s, const DScene &sc) {
+  s.top = sc.top_begin;
+  s.mref = s.mend = 0;
+  s.cur = s.cend = 0;
+  s.tref = s.tend = 0;
+}
+
+// Advances until a triangle list is pending (returns true) or the traversal is complete (returns false).
+// SKIP_REFRACTIVE: shadow rays ignore refractive meshes (AccelerationStructure.cpp:67-71).
+template <bool SKIP_REFRACTIVE, bool COUNT>
+CRT_DI bool trav_to_leaf(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests) {
+  for (;;) {
+    if (s.cur != s.cend) {
+      const float4 lo = __ldg(&sc.nodes[2 * (size_t)s.cur]);
+      const float4 hi = __ldg(&sc.nodes[2 * (size_t)s.cur + 1]);
+      const uint32_t a = __float_as_uint(lo.w);
+      if (COUNT) node_tests++;
+      if (slab_test(lo, hi, r)) {
+        s.cur += 1;
+        if (a & CRT_LEAF_FLAG) {
+          s.tref = __float_as_uint(hi.w);
+          s.tend = s.tref + (a & ~CRT_LEAF_FLAG);
+          return true;
+        }
+      } else {
+        s.cur = (a & CRT_LEAF_FLAG) ? s.cur + 1 : a;
+      }
+    } else if (s.mref != s.mend) {
+      const uint32_t m = __ldg(&sc.top_refs[s.mref++]);
+      const DMesh me = sc.meshes[m];
+      if (SKIP_REFRACTIVE && sc.materials[me.material].type == 3u) continue;
+      s.cur = me.node_begin;
+      s.cend = me.node_end;
+    } else if (s.top != sc.top_end) {
+      const float4 lo = __ldg(&sc.nodes[2 * (size_t)s.top]);
+      const float4 hi = __ldg(&sc.nodes[2 * (size_t)s.top + 1]);
+      const uint32_t a = __float_as_uint(lo.w);
+      if (COUNT) node_tests++;
+      if (slab_test(lo, hi, r)) {
+        s.top += 1;
+        if (a & CRT_LEAF_FLAG) {
+          s.mref = __float_as_uint(hi.w);
+          s.mend = s.mref + (a & ~CRT_LEAF_FLAG);
+        }
+      } else {
+        s.top = (a & CRT_LEAF_FLAG) ? s.top + 1 : a;
+      }
+    } else {
+      return false;
+    }
+  }
+}
+
+// Closest-hit bookkeeping = "closest = intersections[0]; min = inf; for c: if (c.t < min) ..." (KDTree.cpp:75-86,
+// 156-166) folded into a stream: the first candidate is kept unless a later one has t < min (strict).  Folding the
+// per-mesh and the across-mesh scans into one stream is exact.
+struct Closest {
+  float min_t, best_t;
+  uint32_t best_tri;  // CRT_INVALID = no candidate yet
+};
+CRT_DI void closest_begin(Closest &c) {
+  c.min_t = __int_as_float(0x7f800000);
+  c.best_t = 0.0f;
+  c.best_tri = CRT_INVALID;
+}
+CRT_DI void closest_offer(Closest &c, uint32_t tri, float t) {
+  if (c.best_tri == CRT_INVALID) {
+    c.best_tri = tri;
+    c.best_t = t;
+  }
+  if (t < c.min_t) {
+    c.min_t = t;
+    c.best_t = t;
+    c.best_tri = tri;
+  }
+}
+
+}  // namespace crtd

@@ -1,0 +1,685 @@
+// crt_kernels.cuh -- the wavefront pipeline kernels (sm_100a).
+//
+//   K1  primary-ray generation      fused into k_closest<PRIMARY> / k_shade (level 0) + standalone k_generate_rays
+//   K2  k_closest                   persistent closest-hit traversal, one ray per lane, stack-free two-level KD walk
+//   K4/K5 k_shade                   per-hit: barycentrics, smooth normal, texture sample, material switch,
+//                                   reflect / refract + Fresnel, compaction of children into the next level's queue
+//   K3  k_shadow_accumulate         persistent any-hit traversal per (diffuse hit, light) + in-order light sum
+//   K6  k_resolve                   bottom-up combine of the ray tree in the reference's expression order
+//   K7  k_store                     level-0 colours -> framebuffer (f32 + PPMColor u8)
+//
+// Reference functions replaced are cited at each kernel.  No tensor cores: the path is pointer-chasing + scalar
+// binary32 arithmetic; the B200-specific choices are the 32-byte-sector node records, L2-resident working set,
+// persistent grids sized to 148 SMs x resident CTAs, warp-aggregated queue compaction (ballot / shuffle).
+#pragma once
+#include "crt_device.cuh"
+
+namespace crtd {
+
+#define CRT_FULL_MASK 0xFFFFFFFFu
+#define CRT_MAX_LEVELS 34
+
+struct Frame {
+  DCamera cam;
+  uint32_t tiles_x, n_tiles;          // 8x4-pixel tiles over the whole image
+  uint32_t shard_index, shard_count;  // tile t belongs to shard t % shard_count
+  const uint8_t *mask;                // optional per-pixel coverage (rectangles that do not tile the image)
+  uint32_t item_begin;                // first level-0 work item of this chunk (shard-local numbering)
+  uint32_t n_items0;                  // level-0 work items in this chunk
+  uint32_t max_depth;
+  float shadow_bias, reflection_bias, refraction_bias;
+};
+
+struct Levels {
+  float4 *ray_o;      // xyz origin, w = parent node (unused)      -- indexed by node id - offset[1]
+  float4 *ray_d;      // xyz direction (normalised twice), w = ray type
+  uint32_t *hit_tri;  // per node: global triangle id or CRT_INVALID
+  float *hit_t;
+  float4 *color;      // per node: resolved colour
+  uint4 *comb;        // per node: {kind, childA, childB / material, bits(F)}
+  float4 *dq;         // diffuse queue, 3 x float4 per item: {P, bits(node)} {N, base.r} {base.g, base.b, -, -}
+  uint32_t *counts;   // [CRT_MAX_LEVELS] rays per level; [CRT_MAX_LEVELS] = diffuse queue length
+  unsigned long long *stats;  // [0..3] rays by type, [4] node tests, [5] triangle tests
+  uint32_t offset[CRT_MAX_LEVELS + 1];
+};
+
+enum { COMB_FINAL = 0, COMB_REFLECT = 1, COMB_FRESNEL = 2, COMB_COPY = 3 };
+
+CRT_DI uint32_t lane_id() { return threadIdx.x & 31u; }
+CRT_DI uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// Warp-aggregated allocation: every lane of the (fully converged) warp asks for n slots; one atomic per warp.
+CRT_DI uint32_t warp_alloc(uint32_t *counter, uint32_t n) {
+  uint32_t incl = n;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t v = __shfl_up_sync(CRT_FULL_MASK, incl, d);
+    if (lane_id() >= (uint32_t)d) incl += v;
+  }
+  uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
+  uint32_t base = 0;
+  if (lane_id() == 31 && total) base = atomicAdd(counter, total);
+  base = __shfl_sync(CRT_FULL_MASK, base, 31);
+  return base + incl - n;
+}
+
+// level-0 work item -> pixel.  Items are numbered tile-major (8x4 tiles) so a warp starts on one coherent tile.
+CRT_DI bool item_pixel(const Frame &fr, const DScene &sc, uint32_t item, uint32_t &row, uint32_t &col) {
+  const uint32_t local_tile = item >> 5, l = item & 31u;
+  const unsigned long long gt = (unsigned long long)local_tile * fr.shard_count + fr.shard_index;
+  if (gt >= fr.n_tiles) return false;
+  const uint32_t ty = (uint32_t)gt / fr.tiles_x, tx = (uint32_t)gt % fr.tiles_x;
+  col = tx * 8u + (l & 7u);
+  row = ty * 4u + (l >> 3);
+  if (col >= sc.width || row >= sc.height) return false;
+  if (fr.mask && !fr.mask[(size_t)row * sc.width + col]) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2: closest hit.  Replaces RayTracer::trace -> KDTree<ObjectKDTreeSubTree>::intersect -> KDTree<Triangle>::intersect
+// (RayTracer.cpp:453-458, KDTree.cpp:127-166, 48-87).  Persistent: lanes pull rays from a global cursor with one
+// atomic per refill; a warp regroups (refills idle lanes) when fewer than REGROUP lanes are still traversing.
+// ------------------------------------------------------------------------------------------------------------
+template <bool PRIMARY, bool COUNT, int REGROUP>
+__global__ void __launch_bounds__(256) k_closest(const DScene sc, const Frame fr, const Levels lv, const uint32_t level,
+                                                uint32_t *__restrict__ work_counter) {
+  const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
+  const uint32_t node_base = lv.offset[level];
+  const uint32_t lane = lane_id();
+  bool active = false, exhausted = false;
+  uint32_t node = 0, n_nodes = 0, n_tris = 0;
+  Ray ray;
+  Trav tv;
+  Closest cl;
+  tv.tref = tv.tend = 0;
+  for (;;) {
+    const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !active);
+    if (!exhausted && idle) {
+      const uint32_t want = __popc(idle);
+      uint32_t start = 0;
+      if (lane == 0) start = atomicAdd(work_counter, want);
+      start = __shfl_sync(CRT_FULL_MASK, start, 0);
+      if (start + want >= total) exhausted = true;
+      if (!active) {
+        const uint32_t i = start + __popc(idle & lanemask_lt());
+        if (i < total) {
+          bool valid = true;
+          if (PRIMARY) {
+            uint32_t row, col;
+            valid = item_pixel(fr, sc, fr.item_begin + i, row, col);
+            if (valid) primary_ray(fr.cam, sc.width, sc.height, row, col, ray.o, ray.d);
+          } else {
+            const float4 o = lv.ray_o[node_base - lv.offset[1] + i];
+            const float4 d = lv.ray_d[node_base - lv.offset[1] + i];
+            ray.o = mk(o.x, o.y, o.z);
+            ray.d = mk(d.x, d.y, d.z);
+          }
+          if (valid) {
+            ray_prepare(ray, PRIMARY);
+            trav_begin(tv, sc);
+            closest_begin(cl);
+            node = node_base + i;
+            active = true;
+          }
+        }
+      }
+    }
+    if (__ballot_sync(CRT_FULL_MASK, active) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    while (active) {
+      if (tv.tref == tv.tend && !trav_to_leaf<false, COUNT>(tv, sc, ray, n_nodes)) {
+        lv.hit_tri[node] = cl.best_tri;
+        lv.hit_t[node] = cl.best_t;
+        active = false;
+        break;
+      }
+      while (tv.tref != tv.tend) {
+        const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
+        const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
+        const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
+        const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+        float t;
+        V3 p;
+        if (COUNT) n_tris++;
+        if (triangle_test(g0, g1, g2, ray, t, p)) closest_offer(cl, tri, t);
+      }
+      if (REGROUP > 0 && !exhausted && __popc(__activemask()) < REGROUP) break;
+    }
+  }
+  if (COUNT) {
+    unsigned long long a = n_nodes, b = n_tris;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      a += __shfl_xor_sync(CRT_FULL_MASK, a, d);
+      b += __shfl_xor_sync(CRT_FULL_MASK, b, d);
+    }
+    if (lane == 0) {
+      atomicAdd(&lv.stats[4], a);
+      atomicAdd(&lv.stats[5], b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Texture::getColor x4                                                          Texture.cpp:14-72
+// ------------------------------------------------------------------------------------------------------------
+CRT_DI V3 texture_color(const DScene &sc, const DTexture &t, const uint4 sh, float b0, float b1, float b2) {
+  if (t.kind == 0u) return mk(t.color_a[0], t.color_a[1], t.color_a[2]);
+  if (t.kind == 1u) {
+    if (b0 < t.scalar || b1 < t.scalar || b2 < t.scalar) return mk(t.color_b[0], t.color_b[1], t.color_b[2]);
+    return mk(t.color_a[0], t.color_a[1], t.color_a[2]);
+  }
+  float2 uv0 = make_float2(0.f, 0.f), uv1 = uv0, uv2 = uv0;
+  if (sc.vtx_uv) {
+    uv0 = sc.vtx_uv[sh.x];
+    uv1 = sc.vtx_uv[sh.y];
+    uv2 = sc.vtx_uv[sh.z];
+  }
+  // b0 * UV1 + b1 * UV2 + (b2 * UV0)                                            Texture.cpp:34-36, 63-65
+  const float u = fadd(fadd(fmul(b0, uv1.x), fmul(b1, uv2.x)), fmul(b2, uv0.x));
+  const float v = fadd(fadd(fmul(b0, uv1.y), fmul(b1, uv2.y)), fmul(b2, uv0.y));
+  if (t.kind == 2u) {
+    // static_cast<unsigned int>(uv / squareSize): x86 cvttss2si (64-bit) truncation; inputs are kept in range by the
+    // scene contract, where CUDA's saturating cvt.rzi.u32 agrees.
+    const unsigned x = (unsigned)fdiv(u, t.scalar);
+    const unsigned y = (unsigned)fdiv(v, t.scalar);
+    if ((x & 1u) == (y & 1u)) return mk(t.color_a[0], t.color_a[1], t.color_a[2]);
+    return mk(t.color_b[0], t.color_b[1], t.color_b[2]);
+  }
+  const int w = (int)t.width, h = (int)t.height;
+  int x = (int)fmul(u, (float)w);
+  int y = (int)fmul(fsub(1.0f, v), (float)h);
+  x = x < 0 ? 0 : (x > w - 1 ? w - 1 : x);
+  y = y < 0 ? 0 : (y > h - 1 ? h - 1 : y);
+  const float *px = sc.texels + 3ull * (t.texel_offset + (unsigned long long)y * w + x);
+  return mk(px[0], px[1], px[2]);
+}
+
+// (1 - x)^5 as the reference's std::powf(1.0f - cosineAlpha, 5) (RayTracer.cpp:407): glibc's powf evaluates in
+// binary64 and rounds once; x^5 by binary64 multiplies rounded once agrees except in ~0.07 % of inputs (1 ulp),
+// SURVEY.md section 7.  See DESIGN.md section 3.5.
+CRT_DI float pow5_like_glibc(float x) {
+  const double d = (double)x;
+  const double d2 = __dmul_rn(d, d);
+  const double d4 = __dmul_rn(d2, d2);
+  return __double2float_rn(__dmul_rn(d4, d));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K4/K5: shade + spawn for one level.  Replaces the body of RayTracer::shootRay after trace() (RayTracer.cpp:430-450),
+// the hit post-processing of KDTree<ObjectKDTreeSubTree>::intersect (KDTree.cpp:167-190), Triangle::
+// getBarycentricCoordinates (Triangle.cpp:63-73), the set-up halves of calculateReflection / calculateRefraction
+// (RayTracer.cpp:358-417) and Texture::getColor.  Children are compacted into level+1 with one atomic per warp.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_shade(const DScene sc, const Frame fr, const Levels lv, const uint32_t level) {
+  const uint32_t total = (level == 0) ? fr.n_items0 : lv.counts[level];
+  const uint32_t node_base = lv.offset[level];
+  const uint32_t rounded = (total + 31u) & ~31u;
+  uint32_t n_refl = 0, n_refr = 0, n_prim = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+    bool valid = i < total;
+    const uint32_t node = node_base + i;
+    V3 o = mk(0, 0, 0), d = mk(0, 0, 0);
+    if (valid) {
+      if (level == 0) {
+        uint32_t row, col;
+        valid = item_pixel(fr, sc, fr.item_begin + i, row, col);
+        if (valid) {
+          primary_ray(fr.cam, sc.width, sc.height, row, col, o, d);
+          n_prim++;
+        }
+      } else {
+        const float4 ro = lv.ray_o[node - lv.offset[1]];
+        const float4 rd = lv.ray_d[node - lv.offset[1]];
+        o = mk(ro.x, ro.y, ro.z);
+        d = mk(rd.x, rd.y, rd.z);
+      }
+    }
+    uint32_t want_children = 0, want_diffuse = 0;
+    uint32_t kind = COMB_FINAL, mat_index = 0;
+    V3 P = mk(0, 0, 0), N = mk(0, 0, 0), base = mk(0, 0, 0), out = mk(sc.bg[0], sc.bg[1], sc.bg[2]);
+    V3 c0o = P, c0d = P, c1o = P, c1d = P;
+    float fresnel = 0.0f;
+    const V3 bg = mk(sc.bg[0], sc.bg[1], sc.bg[2]);
+    const uint32_t tri = valid ? lv.hit_tri[node] : CRT_INVALID;
+    if (valid && tri != CRT_INVALID) {
+      const float t = lv.hit_t[node];
+      const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
+      const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
+      const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+      const uint4 sh = __ldg(&sc.tri_shade[tri]);
+      const DMesh me = sc.meshes[sh.w];
+      mat_index = me.material;
+      const DMaterial mat = sc.materials[mat_index];
+      P = vadd(o, vscale(d, t));  // Ray.cpp:22
+      N = mk(g0.w, g1.w, g2.w);   // Ray.cpp:28
+      float u = 0.0f, v = 0.0f;
+      if (mat.smooth || mat.texture != CRT_INVALID) {
+        // Triangle::getBarycentricCoordinates                                  Triangle.cpp:63-73
+        const V3 v0 = mk(g0.x, g0.y, g0.z), v1 = mk(g1.x, g1.y, g1.z), v2 = mk(g2.x, g2.y, g2.z);
+        const V3 v0p = vsub(P, v0), v0v1 = vsub(v1, v0), v0v2 = vsub(v2, v0);
+        const float area = vlen(vcross(v0v1, v0v2));
+        u = fdiv(vlen(vcross(v0p, v0v2)), area);
+        v = fdiv(vlen(vcross(v0v1, v0p)), area);
+        if (mat.smooth) {  // KDTree.cpp:180-185
+          const float4 n0 = __ldg(&sc.vtx_normal[sh.x]), n1 = __ldg(&sc.vtx_normal[sh.y]), n2 = __ldg(&sc.vtx_normal[sh.z]);
+          const float w = fsub(fsub(1.0f, u), v);
+          N = vnorm(vadd(vadd(vscale(mk(n1.x, n1.y, n1.z), u), vscale(mk(n2.x, n2.y, n2.z), v)),
+                         vscale(mk(n0.x, n0.y, n0.z), w)));
+        }
+      }
+      const bool child_traced = level + 1 <= fr.max_depth;  // RayTracer.cpp:427-429
+      if (mat.type == 0u) {                                 // Diffuse: calculateDiffusion
+        want_diffuse = 1;
+        base = (mat.texture != CRT_INVALID)
+                   ? texture_color(sc, sc.textures[mat.texture], sh, u, v, fsub(fsub(1.0f, u), v))
+                   : mk(mat.albedo[0], mat.albedo[1], mat.albedo[2]);
+      } else if (mat.type == 1u) {  // Reflective: calculateReflection            RayTracer.cpp:366-373
+        c0o = vadd(P, vscale(N, fr.reflection_bias));
+        c0d = vnorm(vnorm(vreflect(d, N)));  // getNormalized() then shootRay's normalize
+        if (child_traced) {
+          want_children = 1;
+          kind = COMB_REFLECT;
+        } else {
+          out = vadd(mk(0, 0, 0), mk(fmul(mat.albedo[0], bg.x), fmul(mat.albedo[1], bg.y), fmul(mat.albedo[2], bg.z)));
+        }
+      } else if (mat.type == 3u) {  // Refractive: calculateRefraction           RayTracer.cpp:381-416
+        float eta1 = 1.0f, eta2 = mat.ior;
+        V3 n = N;
+        float idn = vdot(d, n);
+        if (idn > 0.0f) {
+          const float tmp = eta1;
+          eta1 = eta2;
+          eta2 = tmp;
+          n = sscale(-1.0f, n);
+          idn = -idn;
+        }
+        const float cos_a = -idn;
+        const float sin_a = fsqrt(stdmax(0.0f, fsub(1.0f, fmul(cos_a, cos_a))));
+        c0o = vadd(P, vscale(n, fr.reflection_bias));
+        c0d = vnorm(vnorm(vreflect(d, n)));
+        const float eta = fdiv(eta1, eta2);
+        const float sin_b = fmul(eta, sin_a);
+        if (sin_b < 1.0f) {
+          const float r = fdiv(fsub(eta1, eta2), fadd(eta1, eta2));
+          const float r0 = fmul(r, r);  // powf(r, 2) == r*r bit for bit
+          fresnel = fadd(r0, fmul(fsub(1.0f, r0), pow5_like_glibc(fsub(1.0f, cos_a))));
+          const float cos_b = fsqrt(stdmax(0.0f, fsub(1.0f, fmul(sin_b, sin_b))));
+          const V3 dir = vsub(sscale(eta, vadd(d, sscale(cos_a, n))), sscale(cos_b, n));
+          c1o = vsub(P, vscale(n, fr.refraction_bias));
+          c1d = vnorm(vnorm(dir));
+          if (child_traced) {
+            want_children = 2;
+            kind = COMB_FRESNEL;
+          } else {
+            out = vadd(sscale(fresnel, bg), sscale(fsub(1.0f, fresnel), bg));
+          }
+        } else {
+          if (child_traced) {
+            want_children = 1;
+            kind = COMB_COPY;
+          } else {
+            out = bg;
+          }
+        }
+      }  // Constant / default: background                                       RayTracer.cpp:443-446
+    }
+    // ---- queue compaction: one atomic per warp per queue ----
+    const uint32_t child = warp_alloc(&lv.counts[level + 1], want_children);
+    const uint32_t dslot = warp_alloc(&lv.counts[CRT_MAX_LEVELS], want_diffuse);
+    if (!valid) continue;
+    if (want_children) {
+      const uint32_t cbase = lv.offset[level + 1] + child;
+      const uint32_t q = cbase - lv.offset[1];
+      lv.ray_o[q] = make_float4(c0o.x, c0o.y, c0o.z, __uint_as_float(node));
+      lv.ray_d[q] = make_float4(c0d.x, c0d.y, c0d.z, __uint_as_float(2u));
+      n_refl++;
+      if (want_children == 2) {
+        lv.ray_o[q + 1] = make_float4(c1o.x, c1o.y, c1o.z, __uint_as_float(node));
+        lv.ray_d[q + 1] = make_float4(c1d.x, c1d.y, c1d.z, __uint_as_float(3u));
+        n_refr++;
+      }
+      lv.comb[node] = make_uint4(kind, cbase, kind == COMB_REFLECT ? mat_index : cbase + 1, __float_as_uint(fresnel));
+    } else {
+      lv.comb[node] = make_uint4(COMB_FINAL, 0, 0, 0);
+      if (want_diffuse) {
+        float4 *q = lv.dq + 3 * (size_t)dslot;
+        q[0] = make_float4(P.x, P.y, P.z, __uint_as_float(node));
+        q[1] = make_float4(N.x, N.y, N.z, base.x);
+        q[2] = make_float4(base.y, base.z, 0.f, 0.f);
+      } else {
+        lv.color[node] = make_float4(out.x, out.y, out.z, 0.f);
+      }
+    }
+  }
+  // ray statistics (traced rays only)
+  unsigned long long a = n_prim, b = n_refl, c = n_refr;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    a += __shfl_xor_sync(CRT_FULL_MASK, a, s);
+    b += __shfl_xor_sync(CRT_FULL_MASK, b, s);
+    c += __shfl_xor_sync(CRT_FULL_MASK, c, s);
+  }
+  if (lane_id() == 0) {
+    if (a) atomicAdd(&lv.stats[0], a);
+    if (b) atomicAdd(&lv.stats[2], b);
+    if (c) atomicAdd(&lv.stats[3], c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3: shadow any-hit + diffuse accumulation.  Replaces the light loop of RayTracer::calculateDiffusion
+// (RayTracer.cpp:308-330) and RayTracer::hasIntersection -> ObjectKDTree::checkForIntersection
+// (RayTracer.cpp:507-518, AccelerationStructure.cpp:56-94).  The reference runs a full closest-hit per mesh and
+// accepts iff |P - o| <= distanceToLight; because that length is monotone in t, "closest passes" == "some candidate
+// passes", so terminating on the first passing candidate is exact.  One lane owns one diffuse hit
+// and walks the lights in order so the sum is formed in the reference's order.
+// ------------------------------------------------------------------------------------------------------------
+template <bool COUNT, int REGROUP>
+__global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, const Frame fr, const Levels lv,
+                                                          uint32_t *__restrict__ work_counter) {
+  const uint32_t total = lv.counts[CRT_MAX_LEVELS];
+  const uint32_t lane = lane_id();
+  const float PI = 3.14159274101257324219f;  // M_PIf                            RayTracer.cpp:27
+  bool active = false, exhausted = false, need_ray = false, occluded = false;
+  uint32_t node = 0, light = 0, n_nodes = 0, n_tris = 0;
+  V3 P = mk(0, 0, 0), N = P, base = P, acc = P;
+  float contrib = 0.0f, dist = 0.0f;
+  Ray ray;
+  Trav tv;
+  tv.tref = tv.tend = 0;
+  for (;;) {
+    const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !active);
+    if (!exhausted && idle) {
+      const uint32_t want = __popc(idle);
+      uint32_t start = 0;
+      if (lane == 0) start = atomicAdd(work_counter, want);
+      start = __shfl_sync(CRT_FULL_MASK, start, 0);
+      if (start + want >= total) exhausted = true;
+      if (!active) {
+        const uint32_t i = start + __popc(idle & lanemask_lt());
+        if (i < total) {
+          const float4 q0 = lv.dq[3 * (size_t)i], q1 = lv.dq[3 * (size_t)i + 1], q2 = lv.dq[3 * (size_t)i + 2];
+          P = mk(q0.x, q0.y, q0.z);
+          node = __float_as_uint(q0.w);
+          N = mk(q1.x, q1.y, q1.z);
+          base = mk(q1.w, q2.x, q2.y);
+          acc = mk(0, 0, 0);
+          light = 0;
+          active = true;
+          need_ray = true;
+        }
+      }
+    }
+    if (__ballot_sync(CRT_FULL_MASK, active) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    while (active) {
+      if (need_ray) {
+        if (light == sc.n_lights) {
+          lv.color[node] = make_float4(acc.x, acc.y, acc.z, 0.f);
+          active = false;
+          break;
+        }
+        const DLight L = sc.lights[light];
+        V3 ld = vsub(mk(L.pos[0], L.pos[1], L.pos[2]), P);
+        dist = vlen(ld);
+        const float area = fmul(fmul(fmul(4.0f, dist), dist), PI);  // 4 * r * r * PI
+        ld = vnorm(ld);
+        const float angle = stdmax(0.0f, vdot(ld, N));
+        contrib = fmul(fdiv(L.intensity, area), angle);  // (float(I) / area * angle)
+        ray.o = vadd(P, vscale(N, fr.shadow_bias));
+        ray.d = ld;
+        ray_prepare(ray, false);
+        trav_begin(tv, sc);
+        occluded = false;
+        need_ray = false;
+      }
+      if (tv.tref == tv.tend && !trav_to_leaf<true, COUNT>(tv, sc, ray, n_nodes)) {
+        // shadow ray finished without an accepted hit
+        acc = vadd(acc, sscale(contrib, base));  // finalColor += direct * albedo   RayTracer.cpp:321-327
+        light++;
+        need_ray = true;
+        continue;
+      }
+      while (tv.tref != tv.tend) {
+        const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
+        const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
+        const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
+        const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+        float t;
+        V3 p;
+        if (COUNT) n_tris++;
+        if (triangle_test(g0, g1, g2, ray, t, p)) {
+          // (hitPoint - ray.origin).length() <= distanceToLight               AccelerationStructure.cpp:73-74
+          if (vlen(vsub(p, ray.o)) <= dist) {
+            occluded = true;
+            break;
+          }
+        }
+      }
+      if (occluded) {
+        tv.tref = tv.tend = 0;
+        light++;
+        need_ray = true;
+        occluded = false;
+        continue;
+      }
+      if (REGROUP > 0 && !exhausted && __popc(__activemask()) < REGROUP) break;
+    }
+  }
+  if (COUNT) {
+    unsigned long long a = n_nodes, b = n_tris;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      a += __shfl_xor_sync(CRT_FULL_MASK, a, d);
+      b += __shfl_xor_sync(CRT_FULL_MASK, b, d);
+    }
+    if (lane == 0) {
+      atomicAdd(&lv.stats[4], a);
+      atomicAdd(&lv.stats[5], b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K6: resolve one level bottom-up.  The return path of the recursion, in the reference's expression order:
+//   reflective : Color(0,0,0) += albedo (*) R                                    RayTracer.cpp:369-373
+//   refractive : F * R + (1 - F) * T   |   R on total internal reflection       RayTracer.cpp:414, 416
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resolve(const DScene sc, const Frame fr, const Levels lv, const uint32_t level) {
+  const uint32_t total = (level == 0) ? fr.n_items0 : lv.counts[level];
+  const uint32_t node_base = lv.offset[level];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t node = node_base + i;
+    if (level == 0) {
+      uint32_t row, col;
+      if (!item_pixel(fr, sc, fr.item_begin + i, row, col)) continue;
+    }
+    const uint4 cb = lv.comb[node];
+    if (cb.x == COMB_FINAL) continue;
+    const float4 A = lv.color[cb.y];
+    V3 out;
+    if (cb.x == COMB_REFLECT) {
+      const DMaterial mat = sc.materials[cb.z];
+      out = vadd(mk(0, 0, 0), mk(fmul(mat.albedo[0], A.x), fmul(mat.albedo[1], A.y), fmul(mat.albedo[2], A.z)));
+    } else if (cb.x == COMB_FRESNEL) {
+      const float4 B = lv.color[cb.z];
+      const float F = __uint_as_float(cb.w);
+      out = vadd(sscale(F, mk(A.x, A.y, A.z)), sscale(fsub(1.0f, F), mk(B.x, B.y, B.z)));
+    } else {
+      out = mk(A.x, A.y, A.z);
+    }
+    lv.color[node] = make_float4(out.x, out.y, out.z, 0.f);
+  }
+}
+
+// PPMColor: static_cast<unsigned short>(std::clamp(c, 0.0f, 1.0f) * 255)       Color.cpp:12-16
+CRT_DI uint8_t quantize(float c) {
+  c = (c < 0.0f) ? 0.0f : ((1.0f < c) ? 1.0f : c);
+  const float s = fmul(c, 255.0f);
+  return (uint8_t)(unsigned short)__float2uint_rz(s);  // NaN -> 0 like x86 cvttss2si's low 16 bits
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K7: store.  colorBuffer[row][col] = color (RayTracer.cpp:106) + optional PPMColor bytes + optional hit records.
+// With tile sharding and slab != nullptr the shard's pixels are ALSO written compactly (item order) for the gather.
+// ------------------------------------------------------------------------------------------------------------
+struct HitRec {
+  int mesh, tri;
+  float t;
+};
+__global__ void __launch_bounds__(256) k_store(const DScene sc, const Frame fr, const Levels lv, float *__restrict__ rgb,
+                                              uint8_t *__restrict__ rgb8, HitRec *__restrict__ hits,
+                                              float *__restrict__ slab) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fr.n_items0; i += gridDim.x * blockDim.x) {
+    uint32_t row, col;
+    const bool valid = item_pixel(fr, sc, fr.item_begin + i, row, col);
+    const float4 c = valid ? lv.color[lv.offset[0] + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (slab) {
+      float *s = slab + 3 * (size_t)(fr.item_begin + i);
+      s[0] = c.x;
+      s[1] = c.y;
+      s[2] = c.z;
+    }
+    if (!valid) continue;
+    const size_t pix = (size_t)row * sc.width + col;
+    if (rgb) {
+      rgb[3 * pix + 0] = c.x;
+      rgb[3 * pix + 1] = c.y;
+      rgb[3 * pix + 2] = c.z;
+    }
+    if (rgb8) {
+      rgb8[3 * pix + 0] = quantize(c.x);
+      rgb8[3 * pix + 1] = quantize(c.y);
+      rgb8[3 * pix + 2] = quantize(c.z);
+    }
+    if (hits) {
+      const uint32_t tri = lv.hit_tri[lv.offset[0] + i];
+      HitRec h;
+      if (tri == CRT_INVALID) {
+        h.mesh = -1;
+        h.tri = -1;
+        h.t = 0.0f;
+      } else {
+        const uint32_t m = sc.tri_shade[tri].w;
+        h.mesh = (int)m;
+        h.tri = (int)(tri - sc.meshes[m].first_triangle);
+        h.t = lv.hit_t[lv.offset[0] + i];
+      }
+      hits[pix] = h;
+    }
+  }
+}
+
+// Scatter gathered shard slabs (shard-major, item order) into a full frame: the rank-0 side of the NCCL gather.
+__global__ void __launch_bounds__(256) k_assemble(const DScene sc, Frame fr, const float *__restrict__ slabs,
+                                                 uint32_t items_per_shard, uint32_t shard_count,
+                                                 float *__restrict__ rgb, uint8_t *__restrict__ rgb8) {
+  const unsigned long long total = (unsigned long long)items_per_shard * shard_count;
+  for (unsigned long long g = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; g < total;
+       g += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t shard = (uint32_t)(g / items_per_shard), i = (uint32_t)(g % items_per_shard);
+    fr.shard_index = shard;
+    fr.shard_count = shard_count;
+    uint32_t row, col;
+    if (!item_pixel(fr, sc, i, row, col)) continue;
+    const float *s = slabs + 3 * g;
+    const size_t pix = (size_t)row * sc.width + col;
+    if (rgb) {
+      rgb[3 * pix + 0] = s[0];
+      rgb[3 * pix + 1] = s[1];
+      rgb[3 * pix + 2] = s[2];
+    }
+    if (rgb8) {
+      rgb8[3 * pix + 0] = quantize(s[0]);
+      rgb8[3 * pix + 1] = quantize(s[1]);
+      rgb8[3 * pix + 2] = quantize(s[2]);
+    }
+  }
+}
+
+// K1 standalone: RayTracer::getRay + shootRay's re-normalisation, for the ray parity test.
+__global__ void __launch_bounds__(256) k_generate_rays(const DScene sc, const DCamera cam, float *__restrict__ rays) {
+  const uint32_t n = sc.width * sc.height;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    V3 o, d;
+    primary_ray(cam, sc.width, sc.height, i / sc.width, i % sc.width, o, d);
+    float *r = rays + 6 * (size_t)i;
+    r[0] = o.x;
+    r[1] = o.y;
+    r[2] = o.z;
+    r[3] = d.x;
+    r[4] = d.y;
+    r[5] = d.z;
+  }
+}
+
+// Caller-supplied rays: RayTracer::trace / RayTracer::hasIntersection as plain queries (one ray per thread).
+__global__ void __launch_bounds__(256) k_query(const DScene sc, const float *__restrict__ rays, uint32_t n,
+                                              uint32_t ray_type, const float *__restrict__ max_distance,
+                                              HitRec *__restrict__ hits, uint8_t *__restrict__ occluded) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Ray ray;
+    ray.o = mk(rays[6 * (size_t)i], rays[6 * (size_t)i + 1], rays[6 * (size_t)i + 2]);
+    ray.d = mk(rays[6 * (size_t)i + 3], rays[6 * (size_t)i + 4], rays[6 * (size_t)i + 5]);
+    ray_prepare(ray, ray_type == 0u);
+    Trav tv;
+    trav_begin(tv, sc);
+    uint32_t dummy = 0;
+    if (ray_type == 1u) {
+      const float dist = max_distance[i];
+      bool occ = false;
+      while (!occ && trav_to_leaf<true, false>(tv, sc, ray, dummy)) {
+        while (tv.tref != tv.tend) {
+          const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
+          float t;
+          V3 p;
+          if (triangle_test(__ldg(&sc.tri_geom[3 * (size_t)tri]), __ldg(&sc.tri_geom[3 * (size_t)tri + 1]),
+                            __ldg(&sc.tri_geom[3 * (size_t)tri + 2]), ray, t, p)) {
+            if (vlen(vsub(p, ray.o)) <= dist) {
+              occ = true;
+              break;
+            }
+          }
+        }
+      }
+      occluded[i] = occ ? 1 : 0;
+    } else {
+      Closest cl;
+      closest_begin(cl);
+      while (trav_to_leaf<false, false>(tv, sc, ray, dummy)) {
+        while (tv.tref != tv.tend) {
+          const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
+          float t;
+          V3 p;
+          if (triangle_test(__ldg(&sc.tri_geom[3 * (size_t)tri]), __ldg(&sc.tri_geom[3 * (size_t)tri + 1]),
+                            __ldg(&sc.tri_geom[3 * (size_t)tri + 2]), ray, t, p))
+            closest_offer(cl, tri, t);
+        }
+      }
+      HitRec h;
+      if (cl.best_tri == CRT_INVALID) {
+        h.mesh = -1;
+        h.tri = -1;
+        h.t = 0.0f;
+      } else {
+        const uint32_t m = sc.tri_shade[cl.best_tri].w;
+        h.mesh = (int)m;
+        h.tri = (int)(cl.best_tri - sc.meshes[m].first_triangle);
+        h.t = cl.best_t;
+      }
+      hits[i] = h;
+    }
+  }
+}
+
+}  // namespace crtd

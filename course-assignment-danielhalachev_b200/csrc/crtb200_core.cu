@@ -1,0 +1,770 @@
+// crtb200_core.cu -- C ABI (include/crtb200.h) of the B200-native renderer core: host flattener H1 (reference trees ->
+// stack-free visiting-order layout), device memory management, and the per-frame launch sequence of the wavefront
+// kernels in crt_kernels.cuh.  No CPU rendering path exists in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/crtb200.h"
+#include "crt_kernels.cuh"
+
+using namespace crtd;
+
+static thread_local std::string g_error;
+static int fail(int code, const std::string &msg) {
+  g_error = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                       \
+  do {                                                                                                       \
+    cudaError_t e_ = (expr);                                                                                 \
+    if (e_ != cudaSuccess)                                                                                   \
+      return fail(CRTB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorName(e_) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T> &v) {
+    cudaError_t e = ensure(std::max<size_t>(v.size(), 1));
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct crtb200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool have_scene = false;
+  uint64_t queue_budget = 16ull << 30;
+
+  // scene
+  DScene sc{};
+  DevBuf<float4> nodes, tri_geom, vtx_normal;
+  DevBuf<uint32_t> leaf_refs, top_refs;
+  DevBuf<uint4> tri_shade;
+  DevBuf<float2> vtx_uv;
+  DevBuf<DMesh> meshes;
+  DevBuf<DMaterial> materials;
+  DevBuf<DTexture> textures;
+  DevBuf<float> texels;
+  DevBuf<DLight> lights;
+  bool has_reflective = false, has_refractive = false;
+  uint64_t scene_bytes = 0;
+
+  // frame
+  DevBuf<float> frame;   // persistent colour buffer (RayTracer::colorBuffer, RayTracer.h:69)
+  DevBuf<uint8_t> frame8;
+  DevBuf<HitRec> hits;
+  DevBuf<uint8_t> mask;
+  std::vector<crtb200_rect> mask_rects;
+  bool mask_valid = false, mask_needed = false;
+
+  // queues
+  Levels lv{};
+  DevBuf<float4> ray_o, ray_d, color, dq;
+  DevBuf<uint32_t> hit_tri, counts, work;
+  DevBuf<float> hit_t;
+  DevBuf<uint4> comb;
+  DevBuf<unsigned long long> stats_dev;
+  uint32_t cap_items = 0;
+  uint32_t cap_depth = 0xFFFFFFFFu;
+
+  int blocks_closest = 0, blocks_shadow = 0;
+  crtb200_stats last{};
+  bool last_pending = false;
+};
+
+extern "C" {
+
+uint32_t crtb200_abi_version(void) { return CRTB200_ABI_VERSION; }
+const char *crtb200_last_error(void) { return g_error.c_str(); }
+
+int crtb200_device_count(int *count) {
+  if (!count) return fail(CRTB200_ERR_ARG, "count is null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(CRTB200_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *count = n;
+  return CRTB200_OK;
+}
+
+int crtb200_create(int device, crtb200_ctx **out) {
+  if (!out) return fail(CRTB200_ERR_ARG, "out is null");
+  *out = nullptr;
+  int n = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return fail(CRTB200_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(CRTB200_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100-class; libcrtb200 is built for sm_100a only");
+  crtb200_ctx *c = new crtb200_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return fail(CRTB200_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  for (auto &e : c->ev) cudaEventCreate(&e);
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, 20>, 256, 0);
+  c->blocks_closest = std::max(1, occ) * c->sm_count;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<false, 20>, 256, 0);
+  c->blocks_shadow = std::max(1, occ) * c->sm_count;
+  *out = c;
+  return CRTB200_OK;
+}
+
+int crtb200_destroy(crtb200_ctx *c) {
+  if (!c) return CRTB200_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->nodes.release(); c->tri_geom.release(); c->vtx_normal.release(); c->leaf_refs.release(); c->top_refs.release();
+  c->tri_shade.release(); c->vtx_uv.release(); c->meshes.release(); c->materials.release(); c->textures.release();
+  c->texels.release(); c->lights.release(); c->frame.release(); c->frame8.release(); c->hits.release();
+  c->mask.release(); c->ray_o.release(); c->ray_d.release(); c->color.release(); c->dq.release();
+  c->hit_tri.release(); c->counts.release(); c->work.release(); c->hit_t.release(); c->comb.release();
+  c->stats_dev.release();
+  for (auto &e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return CRTB200_OK;
+}
+
+int crtb200_set_queue_budget(crtb200_ctx *c, uint64_t bytes) {
+  if (!c) return fail(CRTB200_ERR_ARG, "ctx is null");
+  if (bytes < (64ull << 20)) return fail(CRTB200_ERR_ARG, "queue budget must be at least 64 MiB");
+  c->queue_budget = bytes;
+  c->cap_items = 0;
+  return CRTB200_OK;
+}
+
+// ---- host flattener H1: reference-numbered tree -> visiting-order, skip-linked nodes -------------------------
+// The reference pops child[1] before child[0] (it pushes 0 then 1 on a std::stack, KDTree.cpp:65-72), visits every
+// node whose box passes, and never reorders.  So the visiting order is a fixed total order of the nodes and a failed
+// slab test simply jumps over the node's subtree.
+static bool relayout_tree(const crtb200_kdnode *nodes, uint32_t n, uint32_t out_base, uint32_t ref_base,
+                          uint32_t ref_count, std::vector<float4> &out, std::string &err) {
+  if (n == 0) return true;
+  std::vector<uint32_t> order;
+  order.reserve(n);
+  std::vector<uint32_t> stack;
+  std::vector<uint8_t> seen(n, 0);
+  stack.push_back(0);
+  while (!stack.empty()) {
+    uint32_t i = stack.back();
+    stack.pop_back();
+    if (i >= n) {
+      err = "kd node child index out of range";
+      return false;
+    }
+    if (seen[i]) {
+      err = "kd tree is not a tree (node reachable twice)";
+      return false;
+    }
+    seen[i] = 1;
+    order.push_back(i);
+    const crtb200_kdnode &nd = nodes[i];
+    if (nd.leaf_count == 0) {
+      if (nd.child[0] != CRTB200_INVALID) stack.push_back(nd.child[0]);
+      if (nd.child[1] != CRTB200_INVALID) stack.push_back(nd.child[1]);
+    } else if ((uint64_t)nd.leaf_start + nd.leaf_count > ref_count) {
+      err = "kd leaf reference range out of bounds";
+      return false;
+    }
+  }
+  const uint32_t m = (uint32_t)order.size();
+  std::vector<uint32_t> newidx(n, 0), size(n, 1);
+  for (uint32_t k = 0; k < m; k++) newidx[order[k]] = k;
+  for (uint32_t k = m; k-- > 0;) {
+    const crtb200_kdnode &nd = nodes[order[k]];
+    uint32_t s = 1;
+    if (nd.leaf_count == 0) {
+      if (nd.child[0] != CRTB200_INVALID) s += size[nd.child[0]];
+      if (nd.child[1] != CRTB200_INVALID) s += size[nd.child[1]];
+    }
+    size[order[k]] = s;
+  }
+  out.resize(2 * (size_t)(out_base + m));
+  for (uint32_t k = 0; k < m; k++) {
+    const crtb200_kdnode &nd = nodes[order[k]];
+    uint32_t a, b;
+    if (nd.leaf_count) {
+      a = CRT_LEAF_FLAG | nd.leaf_count;
+      b = ref_base + nd.leaf_start;
+    } else {
+      a = out_base + k + size[order[k]];
+      b = CRT_INVALID;
+    }
+    float4 lo = make_float4(nd.box_min[0], nd.box_min[1], nd.box_min[2], 0.f);
+    float4 hi = make_float4(nd.box_max[0], nd.box_max[1], nd.box_max[2], 0.f);
+    std::memcpy(&lo.w, &a, 4);
+    std::memcpy(&hi.w, &b, 4);
+    out[2 * (size_t)(out_base + k)] = lo;
+    out[2 * (size_t)(out_base + k) + 1] = hi;
+  }
+  return true;
+}
+
+int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
+  if (!c || !s) return fail(CRTB200_ERR_ARG, "null argument");
+  if (s->abi_version != CRTB200_ABI_VERSION) return fail(CRTB200_ERR_ARG, "crtb200_scene.abi_version mismatch");
+  if (s->width == 0 || s->height == 0) return fail(CRTB200_ERR_SCENE, "image size is zero");
+  if ((uint64_t)s->width * s->height > 0x7FFFFFFFull / 4) return fail(CRTB200_ERR_SCENE, "image too large");
+  if ((s->n_vertices && (!s->vertex_position || !s->vertex_normal)) || (s->n_triangles && (!s->triangle_vertex || !s->triangle_normal)) ||
+      (s->n_meshes && !s->meshes) || (s->n_materials && !s->materials) || (s->n_lights && !s->lights) ||
+      (s->n_textures && !s->textures) || (s->n_mesh_nodes && !s->mesh_nodes) || (s->n_top_nodes && !s->top_nodes) ||
+      (s->n_mesh_leaf_refs && !s->mesh_leaf_refs) || (s->n_top_leaf_refs && !s->top_leaf_refs))
+    return fail(CRTB200_ERR_SCENE, "a non-empty scene array is null");
+  if (s->n_triangles >= 0x7FFFFFFFu || s->n_mesh_nodes >= 0x7FFFFFF0u) return fail(CRTB200_ERR_SCENE, "scene too large for 31-bit indices");
+  CUDA_TRY(cudaSetDevice(c->device));
+  c->have_scene = false;
+
+  // triangles
+  std::vector<float4> geom(3 * (size_t)s->n_triangles);
+  std::vector<uint4> shade(s->n_triangles);
+  std::vector<uint32_t> tri_mesh(s->n_triangles, CRTB200_INVALID);
+  for (uint32_t m = 0; m < s->n_meshes; m++) {
+    const crtb200_mesh &me = s->meshes[m];
+    if ((uint64_t)me.first_triangle + me.n_triangles > s->n_triangles) return fail(CRTB200_ERR_SCENE, "mesh triangle range out of bounds");
+    if (me.material >= s->n_materials) return fail(CRTB200_ERR_SCENE, "mesh material index out of range");
+    if ((uint64_t)me.first_node + me.n_nodes > s->n_mesh_nodes) return fail(CRTB200_ERR_SCENE, "mesh node range out of bounds");
+    if ((uint64_t)me.first_leaf_ref + me.n_leaf_refs > s->n_mesh_leaf_refs) return fail(CRTB200_ERR_SCENE, "mesh leaf-ref range out of bounds");
+    for (uint32_t t = 0; t < me.n_triangles; t++) tri_mesh[me.first_triangle + t] = m;
+  }
+  for (uint32_t t = 0; t < s->n_triangles; t++) {
+    const uint32_t *iv = s->triangle_vertex + 3 * (size_t)t;
+    if (iv[0] >= s->n_vertices || iv[1] >= s->n_vertices || iv[2] >= s->n_vertices) return fail(CRTB200_ERR_SCENE, "triangle vertex index out of range");
+    if (tri_mesh[t] == CRTB200_INVALID) return fail(CRTB200_ERR_SCENE, "triangle not owned by any mesh");
+    const float *n = s->triangle_normal + 3 * (size_t)t;
+    for (int k = 0; k < 3; k++) {
+      const float *p = s->vertex_position + 3 * (size_t)iv[k];
+      geom[3 * (size_t)t + k] = make_float4(p[0], p[1], p[2], n[k]);
+    }
+    shade[t] = make_uint4(iv[0], iv[1], iv[2], tri_mesh[t]);
+  }
+  // trees: mesh trees first, top-level tree last, one node array
+  std::vector<float4> nodes;
+  std::vector<uint32_t> refs(s->n_mesh_leaf_refs);
+  std::vector<DMesh> meshes(s->n_meshes);
+  uint32_t node_cursor = 0;
+  std::string err;
+  for (uint32_t m = 0; m < s->n_meshes; m++) {
+    const crtb200_mesh &me = s->meshes[m];
+    for (uint32_t k = 0; k < me.n_leaf_refs; k++) {
+      uint32_t local = s->mesh_leaf_refs[me.first_leaf_ref + k];
+      if (local >= me.n_triangles) return fail(CRTB200_ERR_SCENE, "mesh leaf reference out of range");
+      refs[me.first_leaf_ref + k] = me.first_triangle + local;
+    }
+    const size_t before = nodes.size() / 2;
+    if (!relayout_tree(s->mesh_nodes + me.first_node, me.n_nodes, node_cursor, me.first_leaf_ref, me.n_leaf_refs, nodes, err))
+      return fail(CRTB200_ERR_SCENE, err);
+    const uint32_t placed = (uint32_t)(nodes.size() / 2 - before);
+    meshes[m].node_begin = node_cursor;
+    meshes[m].node_end = node_cursor + placed;
+    meshes[m].material = me.material;
+    meshes[m].first_triangle = me.first_triangle;
+    node_cursor += placed;
+  }
+  for (uint32_t k = 0; k < s->n_top_leaf_refs; k++)
+    if (s->top_leaf_refs[k] >= s->n_meshes) return fail(CRTB200_ERR_SCENE, "top-level leaf reference out of range");
+  const uint32_t top_begin = node_cursor;
+  {
+    const size_t before = nodes.size() / 2;
+    if (!relayout_tree(s->top_nodes, s->n_top_nodes, node_cursor, 0, s->n_top_leaf_refs, nodes, err)) return fail(CRTB200_ERR_SCENE, err);
+    node_cursor += (uint32_t)(nodes.size() / 2 - before);
+  }
+  const uint32_t top_end = node_cursor;
+
+  std::vector<float4> vn(s->n_vertices);
+  for (uint32_t v = 0; v < s->n_vertices; v++)
+    vn[v] = make_float4(s->vertex_normal[3 * (size_t)v], s->vertex_normal[3 * (size_t)v + 1], s->vertex_normal[3 * (size_t)v + 2], 0.f);
+  std::vector<float2> uv;
+  if (s->vertex_uv) {
+    uv.resize(s->n_vertices);
+    for (uint32_t v = 0; v < s->n_vertices; v++) uv[v] = make_float2(s->vertex_uv[3 * (size_t)v], s->vertex_uv[3 * (size_t)v + 1]);
+  }
+  std::vector<DMaterial> mats(s->n_materials);
+  c->has_reflective = c->has_refractive = false;
+  for (uint32_t m = 0; m < s->n_materials; m++) {
+    const crtb200_material &mm = s->materials[m];
+    if (mm.texture != CRTB200_INVALID && mm.texture >= s->n_textures) return fail(CRTB200_ERR_SCENE, "material texture index out of range");
+    mats[m].type = mm.type;
+    mats[m].smooth = mm.smooth_shading;
+    mats[m].texture = mm.texture;
+    mats[m].ior = mm.ior;
+    for (int k = 0; k < 3; k++) mats[m].albedo[k] = mm.albedo[k];
+    mats[m].pad = 0.f;
+  }
+  for (uint32_t m = 0; m < s->n_meshes; m++) {
+    const uint32_t type = s->materials[s->meshes[m].material].type;
+    if (type == CRTB200_MAT_REFLECTIVE) c->has_reflective = true;
+    if (type == CRTB200_MAT_REFRACTIVE) c->has_refractive = true;
+  }
+  std::vector<DTexture> texs(s->n_textures);
+  for (uint32_t t = 0; t < s->n_textures; t++) {
+    const crtb200_texture &tt = s->textures[t];
+    texs[t].kind = tt.kind;
+    for (int k = 0; k < 3; k++) {
+      texs[t].color_a[k] = tt.color_a[k];
+      texs[t].color_b[k] = tt.color_b[k];
+    }
+    texs[t].scalar = tt.scalar;
+    texs[t].width = tt.width;
+    texs[t].height = tt.height;
+    texs[t].texel_offset = tt.texel_offset;
+    if (tt.kind == CRTB200_TEX_BITMAP) {
+      if (tt.width == 0 || tt.height == 0 || tt.texel_offset + (uint64_t)tt.width * tt.height > s->n_texels || !s->texels)
+        return fail(CRTB200_ERR_SCENE, "bitmap texture texel range out of bounds");
+    }
+  }
+  std::vector<float> texels(s->texels ? s->texels : nullptr, s->texels ? s->texels + 3 * s->n_texels : nullptr);
+  std::vector<DLight> lights(s->n_lights);
+  for (uint32_t l = 0; l < s->n_lights; l++) {
+    for (int k = 0; k < 3; k++) lights[l].pos[k] = s->lights[l].position[k];
+    lights[l].intensity = static_cast<float>(s->lights[l].intensity);  // RayTracer.cpp:320
+  }
+  std::vector<uint32_t> top_refs(s->top_leaf_refs, s->top_leaf_refs + s->n_top_leaf_refs);
+
+  CUDA_TRY(c->nodes.upload(nodes));
+  CUDA_TRY(c->leaf_refs.upload(refs));
+  CUDA_TRY(c->top_refs.upload(top_refs));
+  CUDA_TRY(c->tri_geom.upload(geom));
+  CUDA_TRY(c->tri_shade.upload(shade));
+  CUDA_TRY(c->vtx_normal.upload(vn));
+  if (!uv.empty()) CUDA_TRY(c->vtx_uv.upload(uv));
+  CUDA_TRY(c->meshes.upload(meshes));
+  CUDA_TRY(c->materials.upload(mats));
+  CUDA_TRY(c->textures.upload(texs));
+  CUDA_TRY(c->texels.upload(texels));
+  CUDA_TRY(c->lights.upload(lights));
+  c->scene_bytes = nodes.size() * 16 + refs.size() * 4 + geom.size() * 16 + shade.size() * 16 + vn.size() * 16;
+
+  DScene &d = c->sc;
+  d.nodes = c->nodes.p;
+  d.leaf_refs = c->leaf_refs.p;
+  d.top_refs = c->top_refs.p;
+  d.tri_geom = c->tri_geom.p;
+  d.tri_shade = c->tri_shade.p;
+  d.vtx_normal = c->vtx_normal.p;
+  d.vtx_uv = uv.empty() ? nullptr : c->vtx_uv.p;
+  d.meshes = c->meshes.p;
+  d.materials = c->materials.p;
+  d.textures = c->textures.p;
+  d.texels = c->texels.p;
+  d.lights = c->lights.p;
+  d.n_lights = s->n_lights;
+  d.top_begin = top_begin;
+  d.top_end = top_end;
+  d.width = s->width;
+  d.height = s->height;
+  for (int k = 0; k < 3; k++) d.bg[k] = s->background[k];
+
+  const size_t px = (size_t)s->width * s->height;
+  CUDA_TRY(c->frame.ensure(px * 3));
+  CUDA_TRY(cudaMemset(c->frame.p, 0, px * 3 * sizeof(float)));  // colorBuffer starts at (0,0,0), RayTracer.cpp:47-50
+  CUDA_TRY(c->frame8.ensure(px * 3));
+  CUDA_TRY(cudaMemset(c->frame8.p, 0, px * 3));
+  CUDA_TRY(c->counts.ensure(CRT_MAX_LEVELS + 1));
+  CUDA_TRY(c->work.ensure(CRT_MAX_LEVELS + 2));
+  CUDA_TRY(c->stats_dev.ensure(8));
+  c->mask_valid = false;
+  c->cap_items = 0;
+  c->have_scene = true;
+  return CRTB200_OK;
+}
+
+}  // extern "C"
+
+// ---- frame planning ------------------------------------------------------------------------------------------
+static uint32_t branching_sum(const crtb200_ctx *c, uint32_t max_depth, uint64_t *per_level) {
+  // worst-case rays per level-0 item at each level (refractive hits spawn two children, RayTracer.cpp:398-412)
+  uint64_t sum = 0;
+  for (uint32_t l = 0; l <= max_depth; l++) {
+    uint64_t b = 1;
+    if (l > 0) {
+      if (c->has_refractive)
+        b = 1ull << std::min<uint32_t>(l, 40);
+      else if (c->has_reflective)
+        b = 1;
+      else
+        b = 0;
+    }
+    per_level[l] = b;
+    sum += b;
+  }
+  return (uint32_t)std::min<uint64_t>(sum, 0xFFFFFFFFull);
+}
+
+static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth) {
+  uint64_t per_level[CRT_MAX_LEVELS] = {0};
+  branching_sum(c, max_depth, per_level);
+  uint64_t sum = 0;
+  for (uint32_t l = 0; l <= max_depth; l++) sum += per_level[l];
+  const uint64_t bytes_per_node = 32 + 8 + 16 + 16 + 48;  // ray + hit + colour + comb + diffuse item
+  uint64_t items = c->queue_budget / (bytes_per_node * sum);
+  items &= ~31ull;
+  if (items < 32 * 64) return fail(CRTB200_ERR_MEMORY, "queue budget too small for one chunk at this ray depth");
+  items = std::min<uint64_t>(items, (shard_items + 31u) & ~31u);
+  if (items * sum >= 0x7FFFFFFFull) items = ((0x7FFFFFFFull / sum) - 32) & ~31ull;
+  if (c->cap_items == items && c->cap_depth == max_depth) return CRTB200_OK;
+  uint64_t total = 0;
+  for (uint32_t l = 0; l <= max_depth; l++) {
+    c->lv.offset[l] = (uint32_t)total;
+    total += per_level[l] * items;
+  }
+  for (uint32_t l = max_depth + 1; l <= CRT_MAX_LEVELS; l++) c->lv.offset[l] = (uint32_t)total;
+  const uint64_t secondary = total - items;
+  CUDA_TRY(c->ray_o.ensure(std::max<uint64_t>(secondary, 1)));
+  CUDA_TRY(c->ray_d.ensure(std::max<uint64_t>(secondary, 1)));
+  CUDA_TRY(c->hit_tri.ensure(total));
+  CUDA_TRY(c->hit_t.ensure(total));
+  CUDA_TRY(c->color.ensure(total));
+  CUDA_TRY(c->comb.ensure(total));
+  CUDA_TRY(c->dq.ensure(3 * total));
+  c->lv.ray_o = c->ray_o.p;
+  c->lv.ray_d = c->ray_d.p;
+  c->lv.hit_tri = c->hit_tri.p;
+  c->lv.hit_t = c->hit_t.p;
+  c->lv.color = c->color.p;
+  c->lv.comb = c->comb.p;
+  c->lv.dq = c->dq.p;
+  c->lv.counts = c->counts.p;
+  c->lv.stats = c->stats_dev.p;
+  c->cap_items = (uint32_t)items;
+  c->cap_depth = max_depth;
+  return CRTB200_OK;
+}
+
+// Pixel coverage of the rectangle list; the mask is only needed when the rectangles do not tile the image exactly
+// (the reference then leaves pixels unrendered).
+static int plan_mask(crtb200_ctx *c, const crtb200_options *o) {
+  const uint32_t W = c->sc.width, H = c->sc.height;
+  std::vector<crtb200_rect> rects(o->rects, o->rects + o->n_rects);
+  if (c->mask_valid && rects.size() == c->mask_rects.size() &&
+      (rects.empty() || !std::memcmp(rects.data(), c->mask_rects.data(), rects.size() * sizeof(crtb200_rect))))
+    return CRTB200_OK;
+  c->mask_rects = rects;
+  c->mask_needed = false;
+  if (!rects.empty()) {
+    std::vector<uint8_t> m((size_t)W * H, 0);
+    for (const auto &r : rects) {
+      const uint32_t r1 = std::min<uint64_t>(H, (uint64_t)r.row + r.height), c1 = std::min<uint64_t>(W, (uint64_t)r.col + r.width);
+      for (uint32_t y = r.row; y < r1; y++) std::memset(&m[(size_t)y * W + r.col], 1, r.col < c1 ? c1 - r.col : 0);
+    }
+    size_t covered = 0;
+    for (uint8_t v : m) covered += v;
+    if (covered != m.size()) {
+      c->mask_needed = true;
+      CUDA_TRY(c->mask.ensure(m.size()));
+      CUDA_TRY(cudaMemcpy(c->mask.p, m.data(), m.size(), cudaMemcpyHostToDevice));
+    }
+  }
+  c->mask_valid = true;
+  return CRTB200_OK;
+}
+
+template <bool COUNT>
+static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, uint32_t level, uint32_t *work, cudaStream_t st) {
+  if (primary)
+    k_closest<true, COUNT, 20><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
+  else
+    k_closest<false, COUNT, 20><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
+}
+
+// Enqueue one frame on `st`.  d_rgb / d_rgb8 / d_hits / d_slab are device pointers (any may be null).
+static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_options *o, float *d_rgb,
+                         uint8_t *d_rgb8, HitRec *d_hits, float *d_slab, cudaStream_t st, bool timed) {
+  if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
+  if (o->max_depth > 31) return fail(CRTB200_ERR_ARG, "max_depth > 31 is not supported");
+  if (o->n_rects && !o->rects) return fail(CRTB200_ERR_ARG, "n_rects > 0 but rects is null");
+  if (o->traversal > 1) return fail(CRTB200_ERR_ARG, "unknown traversal mode");
+  const uint32_t shard_count = o->shard_count ? o->shard_count : 1;
+  if (o->shard_index >= shard_count) return fail(CRTB200_ERR_ARG, "shard_index >= shard_count");
+  int rc = plan_mask(c, o);
+  if (rc) return rc;
+  const uint32_t W = c->sc.width, H = c->sc.height;
+  Frame fr{};
+  for (int k = 0; k < 3; k++) fr.cam.pos[k] = cam->position[k];
+  for (int k = 0; k < 9; k++) fr.cam.rot[k] = cam->rotation[k];
+  fr.tiles_x = (W + 7) / 8;
+  fr.n_tiles = fr.tiles_x * ((H + 3) / 4);
+  fr.shard_index = o->shard_index;
+  fr.shard_count = shard_count;
+  fr.mask = c->mask_needed ? c->mask.p : nullptr;
+  fr.max_depth = o->max_depth;
+  fr.shadow_bias = o->shadow_bias;
+  fr.reflection_bias = o->reflection_bias;
+  fr.refraction_bias = o->refraction_bias;
+  const uint32_t shard_tiles = (fr.n_tiles > o->shard_index) ? (fr.n_tiles - o->shard_index + shard_count - 1) / shard_count : 0;
+  const uint32_t shard_items = shard_tiles * 32u;
+  rc = plan_queues(c, std::max(shard_items, 32u), o->max_depth);
+  if (rc) return rc;
+  const bool secondary = c->has_reflective || c->has_refractive;
+  const uint32_t levels = secondary ? o->max_depth + 1 : 1;
+  const int grid_simple = c->sm_count * 8;
+
+  CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 8 * sizeof(unsigned long long), st));
+  if (timed) CUDA_TRY(cudaEventRecord(c->ev[0], st));
+  uint32_t launches = 0;
+  for (uint32_t begin = 0; begin < shard_items; begin += c->cap_items) {
+    fr.item_begin = begin;
+    fr.n_items0 = std::min(c->cap_items, shard_items - begin);
+    CUDA_TRY(cudaMemsetAsync(c->counts.p, 0, (CRT_MAX_LEVELS + 1) * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(c->work.p, 0, (CRT_MAX_LEVELS + 2) * sizeof(uint32_t), st));
+    for (uint32_t l = 0; l < levels; l++) {
+      if (o->count_work)
+        launch_closest<true>(c, l == 0, fr, l, c->work.p + l, st);
+      else
+        launch_closest<false>(c, l == 0, fr, l, c->work.p + l, st);
+      k_shade<<<grid_simple, 256, 0, st>>>(c->sc, fr, c->lv, l);
+      launches += 2;
+    }
+    if (o->count_work)
+      k_shadow_accumulate<true, 20><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+    else
+      k_shadow_accumulate<false, 20><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+    launches++;
+    for (uint32_t l = levels - 1; l-- > 0;) {
+      k_resolve<<<grid_simple, 256, 0, st>>>(c->sc, fr, c->lv, l);
+      launches++;
+    }
+    k_store<<<grid_simple, 256, 0, st>>>(c->sc, fr, c->lv, d_rgb, d_rgb8, d_hits, d_slab);
+    launches++;
+    // shadow rays = diffuse hits x lights: fold this chunk's queue length into the stats before it is reset
+    // (done on the host from counts for the last chunk; earlier chunks are accumulated by k_store's stream order)
+    if (begin + c->cap_items < shard_items) {
+      // multi-chunk frames: accumulate per-chunk diffuse count into stats[1] with a tiny kernel-free trick:
+      // copy-add is not available, so read it back synchronously (rare path: only refractive 4K frames chunk).
+      uint32_t dq = 0;
+      CUDA_TRY(cudaMemcpyAsync(&dq, c->counts.p + CRT_MAX_LEVELS, 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      c->last.rays_shadow += (uint64_t)dq * c->sc.n_lights;
+    }
+  }
+  if (timed) CUDA_TRY(cudaEventRecord(c->ev[1], st));
+  CUDA_TRY(cudaGetLastError());
+  c->last.kernel_launches = launches;
+  c->last.levels = levels;
+  return CRTB200_OK;
+}
+
+static int collect_stats(crtb200_ctx *c, bool timed) {
+  unsigned long long st[8];
+  uint32_t dq = 0;
+  CUDA_TRY(cudaMemcpy(st, c->stats_dev.p, sizeof(st), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&dq, c->counts.p + CRT_MAX_LEVELS, 4, cudaMemcpyDeviceToHost));
+  c->last.rays_primary = st[0];
+  c->last.rays_shadow += (uint64_t)dq * c->sc.n_lights;
+  c->last.rays_reflection = st[2];
+  c->last.rays_refraction = st[3];
+  c->last.node_tests = st[4];
+  c->last.triangle_tests = st[5];
+  c->last.node_tests_visit_all = st[4];
+  c->last.triangle_tests_visit_all = st[5];
+  if (timed) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    c->last.device_ms = ms;
+    c->last.trace_ms = ms;
+  }
+  return CRTB200_OK;
+}
+
+extern "C" {
+
+int crtb200_render(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_options *o, float *rgb_out,
+                   uint8_t *rgb8_out, crtb200_hit *hits_out, crtb200_stats *stats) {
+  if (!c || !cam || !o) return fail(CRTB200_ERR_ARG, "null argument");
+  const auto t0 = std::chrono::steady_clock::now();
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
+  const size_t px = (size_t)c->sc.width * c->sc.height;
+  if (hits_out) CUDA_TRY(c->hits.ensure(px));
+  if (hits_out) CUDA_TRY(cudaMemsetAsync(c->hits.p, 0xFF, px * sizeof(HitRec), c->stream));
+  c->last = crtb200_stats{};
+  int rc = enqueue_frame(c, cam, o, c->frame.p, rgb8_out ? c->frame8.p : nullptr, hits_out ? c->hits.p : nullptr, nullptr,
+                         c->stream, true);
+  if (rc) return rc;
+  if (rgb_out) CUDA_TRY(cudaMemcpyAsync(rgb_out, c->frame.p, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (rgb8_out) CUDA_TRY(cudaMemcpyAsync(rgb8_out, c->frame8.p, px * 3, cudaMemcpyDeviceToHost, c->stream));
+  if (hits_out) CUDA_TRY(cudaMemcpyAsync(hits_out, c->hits.p, px * sizeof(HitRec), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  rc = collect_stats(c, true);
+  if (rc) return rc;
+  c->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) *stats = c->last;
+  return CRTB200_OK;
+}
+
+int crtb200_render_frames(crtb200_ctx *c, const crtb200_camera *cams, uint32_t n_frames, const crtb200_options *o,
+                          float *rgb_out, uint8_t *rgb8_out, crtb200_stats *stats) {
+  if (!c || !cams || !o) return fail(CRTB200_ERR_ARG, "null argument");
+  if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
+  const size_t px = (size_t)c->sc.width * c->sc.height;
+  crtb200_stats total{};
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t f = 0; f < n_frames; f++) {
+    crtb200_stats s{};
+    int rc = crtb200_render(c, cams + f, o, rgb_out ? rgb_out + f * px * 3 : nullptr, rgb8_out ? rgb8_out + f * px * 3 : nullptr,
+                            nullptr, &s);
+    if (rc) return rc;
+    total.rays_primary += s.rays_primary;
+    total.rays_shadow += s.rays_shadow;
+    total.rays_reflection += s.rays_reflection;
+    total.rays_refraction += s.rays_refraction;
+    total.node_tests += s.node_tests;
+    total.triangle_tests += s.triangle_tests;
+    total.node_tests_visit_all += s.node_tests_visit_all;
+    total.triangle_tests_visit_all += s.triangle_tests_visit_all;
+    total.device_ms += s.device_ms;
+    total.trace_ms += s.trace_ms;
+    total.kernel_launches += s.kernel_launches;
+    total.levels = s.levels;
+  }
+  total.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) *stats = total;
+  return CRTB200_OK;
+}
+
+int crtb200_render_device(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_options *o, float *d_rgb_out,
+                          uint8_t *d_rgb8_out, void *stream) {
+  if (!c || !cam || !o) return fail(CRTB200_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint32_t shard_count = o->shard_count ? o->shard_count : 1;
+  c->last = crtb200_stats{};
+  c->last_pending = true;
+  if (shard_count > 1) {
+    // sharded: d_rgb_out is the shard's compact slab (crtb200_shard_items x 3 floats), see crtb200_assemble_shards
+    if (d_rgb8_out) return fail(CRTB200_ERR_ARG, "sharded rendering writes a float slab only");
+    return enqueue_frame(c, cam, o, nullptr, nullptr, nullptr, d_rgb_out, (cudaStream_t)stream, true);
+  }
+  return enqueue_frame(c, cam, o, d_rgb_out, d_rgb8_out, nullptr, nullptr, (cudaStream_t)stream, true);
+}
+
+int crtb200_last_stats(crtb200_ctx *c, crtb200_stats *stats) {
+  if (!c || !stats) return fail(CRTB200_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (c->last_pending) {
+    CUDA_TRY(cudaEventSynchronize(c->ev[1]));
+    int rc = collect_stats(c, true);
+    if (rc) return rc;
+    c->last_pending = false;
+  }
+  *stats = c->last;
+  return CRTB200_OK;
+}
+
+int crtb200_shard_items(crtb200_ctx *c, uint32_t shard_count, uint32_t *items) {
+  if (!c || !items || shard_count == 0) return fail(CRTB200_ERR_ARG, "bad argument");
+  if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
+  const uint32_t tiles = ((c->sc.width + 7) / 8) * ((c->sc.height + 3) / 4);
+  *items = ((tiles + shard_count - 1) / shard_count) * 32u;
+  return CRTB200_OK;
+}
+
+int crtb200_assemble_shards(crtb200_ctx *c, const float *d_slabs, uint32_t shard_count, float *d_rgb_out,
+                            uint8_t *d_rgb8_out, void *stream) {
+  if (!c || !d_slabs || shard_count == 0) return fail(CRTB200_ERR_ARG, "bad argument");
+  if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
+  CUDA_TRY(cudaSetDevice(c->device));
+  uint32_t items = 0;
+  crtb200_shard_items(c, shard_count, &items);
+  Frame fr{};
+  fr.tiles_x = (c->sc.width + 7) / 8;
+  fr.n_tiles = fr.tiles_x * ((c->sc.height + 3) / 4);
+  fr.mask = nullptr;
+  k_assemble<<<c->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(c->sc, fr, d_slabs, items, shard_count, d_rgb_out, d_rgb8_out);
+  CUDA_TRY(cudaGetLastError());
+  return CRTB200_OK;
+}
+
+int crtb200_generate_rays(crtb200_ctx *c, const crtb200_camera *cam, float *rays_out) {
+  if (!c || !cam || !rays_out) return fail(CRTB200_ERR_ARG, "null argument");
+  if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->sc.width * c->sc.height;
+  DevBuf<float> d;
+  CUDA_TRY(d.ensure(n * 6));
+  DCamera dc;
+  for (int k = 0; k < 3; k++) dc.pos[k] = cam->position[k];
+  for (int k = 0; k < 9; k++) dc.rot[k] = cam->rotation[k];
+  k_generate_rays<<<c->sm_count * 8, 256, 0, c->stream>>>(c->sc, dc, d.p);
+  cudaError_t e = cudaMemcpyAsync(rays_out, d.p, n * 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  d.release();
+  CUDA_TRY(e);
+  return CRTB200_OK;
+}
+
+int crtb200_trace_rays(crtb200_ctx *c, const float *rays, uint32_t n, uint32_t ray_type, uint32_t traversal,
+                       const float *max_distance, crtb200_hit *hits_out, uint8_t *occluded_out) {
+  if (!c || !rays) return fail(CRTB200_ERR_ARG, "null argument");
+  if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
+  if (ray_type > 3) return fail(CRTB200_ERR_ARG, "bad ray type");
+  if (traversal > 1) return fail(CRTB200_ERR_ARG, "unknown traversal mode");
+  if (ray_type == CRTB200_RAY_SHADOW ? (!max_distance || !occluded_out) : !hits_out) return fail(CRTB200_ERR_ARG, "missing output / distance array");
+  if (n == 0) return CRTB200_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  DevBuf<float> d_rays, d_dist;
+  DevBuf<HitRec> d_hits;
+  DevBuf<uint8_t> d_occ;
+  cudaError_t e = d_rays.ensure((size_t)n * 6);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays.p, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+  if (ray_type == CRTB200_RAY_SHADOW) {
+    if (e == cudaSuccess) e = d_dist.ensure(n);
+    if (e == cudaSuccess) e = d_occ.ensure(n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_dist.p, max_distance, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+  } else if (e == cudaSuccess) {
+    e = d_hits.ensure(n);
+  }
+  if (e == cudaSuccess) {
+    k_query<<<c->sm_count * 8, 256, 0, c->stream>>>(c->sc, d_rays.p, n, ray_type, d_dist.p, d_hits.p, d_occ.p);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {
+    if (ray_type == CRTB200_RAY_SHADOW)
+      e = cudaMemcpyAsync(occluded_out, d_occ.p, n, cudaMemcpyDeviceToHost, c->stream);
+    else
+      e = cudaMemcpyAsync(hits_out, d_hits.p, (size_t)n * sizeof(HitRec), cudaMemcpyDeviceToHost, c->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  d_rays.release();
+  d_dist.release();
+  d_hits.release();
+  d_occ.release();
+  CUDA_TRY(e);
+  return CRTB200_OK;
+}
+
+}  // extern "C"
