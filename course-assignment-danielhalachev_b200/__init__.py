@@ -108,7 +108,6 @@ HIT_DTYPE = np.dtype([("mesh", np.int32), ("triangle", np.int32), ("t", np.float
 class Stats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_reflection", C.c_uint64),
                 ("rays_refraction", C.c_uint64), ("node_tests", C.c_uint64), ("triangle_tests", C.c_uint64),
-                ("node_tests_visit_all", C.c_uint64), ("triangle_tests_visit_all", C.c_uint64),
                 ("device_ms", C.c_double), ("trace_ms", C.c_double), ("total_ms", C.c_double),
                 ("kernel_launches", C.c_uint32), ("levels", C.c_uint32)]
 
@@ -131,7 +130,7 @@ _front = None
 
 
 def build(force: bool = False, verbose: bool = False) -> None:
-    from . import build as _b
+    from . import nativebuild as _b
     _b.build_all(force=force, verbose=verbose)
 
 
@@ -266,7 +265,7 @@ def write_ppm(path: str, rgb: np.ndarray) -> None:
 
 
 # ---- CUDA core ---------------------------------------------------------------------------------------------------
-def make_options(max_depth: int = 5, rects=None, n_rects: int = 0, traversal: int = 0, count_work: bool = False,
+def make_options(max_depth: int = 5, rects=None, n_rects: int = 0, traversal: int = 0, count_work: int = 0,
                  shard_index: int = 0, shard_count: int = 1, bias: float = 1e-4) -> Options:
     o = Options()
     o.max_depth = max_depth
@@ -274,7 +273,7 @@ def make_options(max_depth: int = 5, rects=None, n_rects: int = 0, traversal: in
     o.n_rects = n_rects if rects is not None else 0
     o.rects = C.cast(rects, C.POINTER(Rect)) if rects is not None else None
     o.traversal = traversal
-    o.count_work = 1 if count_work else 0
+    o.count_work = int(count_work)
     o.shard_index = shard_index
     o.shard_count = shard_count
     return o

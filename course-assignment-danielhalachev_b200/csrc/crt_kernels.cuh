@@ -382,7 +382,9 @@ __global__ void __launch_bounds__(256) k_shade(const DScene sc, const Frame fr, 
 // passes", so terminating on the first passing candidate is exact.  One lane owns one diffuse hit
 // and walks the lights in order so the sum is formed in the reference's order.
 // ------------------------------------------------------------------------------------------------------------
-template <bool COUNT, int REGROUP>
+// COUNT: 0 = no counters; 1 = count under the reference's visit-all rule (early termination disabled, same result);
+// 2 = count the work this kernel really does with early termination.
+template <int COUNT, int REGROUP>
 __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, const Frame fr, const Levels lv,
                                                           uint32_t *__restrict__ work_counter) {
   const uint32_t total = lv.counts[CRT_MAX_LEVELS];
@@ -443,9 +445,10 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, cons
         occluded = false;
         need_ray = false;
       }
-      if (tv.tref == tv.tend && !trav_to_leaf<true, COUNT>(tv, sc, ray, n_nodes)) {
-        // shadow ray finished without an accepted hit
-        acc = vadd(acc, sscale(contrib, base));  // finalColor += direct * albedo   RayTracer.cpp:321-327
+      if (tv.tref == tv.tend && !trav_to_leaf<true, (COUNT != 0)>(tv, sc, ray, n_nodes)) {
+        // shadow ray finished; unoccluded: finalColor += direct * albedo          RayTracer.cpp:318-327
+        if (!occluded) acc = vadd(acc, sscale(contrib, base));
+        occluded = false;
         light++;
         need_ray = true;
         continue;
@@ -462,11 +465,11 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, cons
           // (hitPoint - ray.origin).length() <= distanceToLight               AccelerationStructure.cpp:73-74
           if (vlen(vsub(p, ray.o)) <= dist) {
             occluded = true;
-            break;
+            if (COUNT != 1) break;
           }
         }
       }
-      if (occluded) {
+      if (COUNT != 1 && occluded) {
         tv.tref = tv.tend = 0;
         light++;
         need_ray = true;

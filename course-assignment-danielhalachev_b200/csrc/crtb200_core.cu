@@ -138,7 +138,7 @@ int crtb200_create(int device, crtb200_ctx **out) {
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, 20>, 256, 0);
   c->blocks_closest = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<false, 20>, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<0, 20>, 256, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
   *out = c;
   return CRTB200_OK;
@@ -509,6 +509,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   if (o->max_depth > 31) return fail(CRTB200_ERR_ARG, "max_depth > 31 is not supported");
   if (o->n_rects && !o->rects) return fail(CRTB200_ERR_ARG, "n_rects > 0 but rects is null");
   if (o->traversal > 1) return fail(CRTB200_ERR_ARG, "unknown traversal mode");
+  if (o->count_work > 2) return fail(CRTB200_ERR_ARG, "unknown count_work mode");
   const uint32_t shard_count = o->shard_count ? o->shard_count : 1;
   if (o->shard_index >= shard_count) return fail(CRTB200_ERR_ARG, "shard_index >= shard_count");
   int rc = plan_mask(c, o);
@@ -550,10 +551,12 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       k_shade<<<grid_simple, 256, 0, st>>>(c->sc, fr, c->lv, l);
       launches += 2;
     }
-    if (o->count_work)
-      k_shadow_accumulate<true, 20><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+    if (o->count_work == 1)
+      k_shadow_accumulate<1, 20><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+    else if (o->count_work == 2)
+      k_shadow_accumulate<2, 20><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
     else
-      k_shadow_accumulate<false, 20><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+      k_shadow_accumulate<0, 20><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
     launches++;
     for (uint32_t l = levels - 1; l-- > 0;) {
       k_resolve<<<grid_simple, 256, 0, st>>>(c->sc, fr, c->lv, l);
@@ -590,8 +593,6 @@ static int collect_stats(crtb200_ctx *c, bool timed) {
   c->last.rays_refraction = st[3];
   c->last.node_tests = st[4];
   c->last.triangle_tests = st[5];
-  c->last.node_tests_visit_all = st[4];
-  c->last.triangle_tests_visit_all = st[5];
   if (timed) {
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
@@ -645,8 +646,6 @@ int crtb200_render_frames(crtb200_ctx *c, const crtb200_camera *cams, uint32_t n
     total.rays_refraction += s.rays_refraction;
     total.node_tests += s.node_tests;
     total.triangle_tests += s.triangle_tests;
-    total.node_tests_visit_all += s.node_tests_visit_all;
-    total.triangle_tests_visit_all += s.triangle_tests_visit_all;
     total.device_ms += s.device_ms;
     total.trace_ms += s.trace_ms;
     total.kernel_launches += s.kernel_launches;

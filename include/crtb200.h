@@ -154,7 +154,9 @@ typedef struct crtb200_options {
   const crtb200_rect *rects;
   uint32_t traversal; /* 0 = exact: the reference's visit-all order (KDTree.cpp:48-87); bit-exact hit ids */
                       /* 1 = fast : near-to-far ordered + culled; identical except at documented ties     */
-  uint32_t count_work; /* 1 = also count node / triangle tests (slower; for the roofline arithmetic)       */
+  uint32_t count_work; /* 0 = off; 1 = count node / triangle tests under the reference's visit-all rule (shadow  */
+                       /* early termination disabled; same pixels) -- the figure the roofline arithmetic uses;  */
+                       /* 2 = count the tests the production kernels really perform                             */
   /* tile sharding (multi-GPU): render only tile blocks b with b % shard_count == shard_index; 0/1 = all */
   uint32_t shard_index, shard_count;
 } crtb200_options;
@@ -168,8 +170,7 @@ typedef struct crtb200_hit {
 
 typedef struct crtb200_stats {
   uint64_t rays_primary, rays_shadow, rays_reflection, rays_refraction; /* traced rays, SURVEY 8(d) definition */
-  uint64_t node_tests, triangle_tests; /* closest-hit + shadow, valid when count_work = 1                  */
-  uint64_t node_tests_visit_all, triangle_tests_visit_all; /* same, under the reference's visit-all rule     */
+  uint64_t node_tests, triangle_tests; /* closest-hit + shadow AABB / triangle tests, per options.count_work  */
   double device_ms;  /* CUDA-event time of the kernels of the last render (all levels)                      */
   double trace_ms;   /* of which: closest-hit + shadow traversal kernels                                    */
   double total_ms;   /* host wall time of the call, copies included                                         */
