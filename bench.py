@@ -1,0 +1,435 @@
+#!/usr/bin/env python3
+"""bench.py -- Mrays/s and ms/frame of the per-pixel hot path on N B200s (contract: see README / DESIGN.md section 6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one frame of the named workload: every primary, shadow, reflection and refraction ray the reference would
+trace for it (SURVEY.md 8(d) definition).  Default workload = BASELINE.json config 4, `hw14_dragon_class`: 1 009 200-triangle
+displaced cube-sphere + ground quad, 3840x2160, 2 point lights -- "the largest KD-tree scene" the north_star's target
+is quoted on that fits one GPU.
+
+  value      whole-job Mrays/s with the scene resident in HBM and the framebuffer left on the device
+             (crtb200_render_device); per-step CUDA events on the launching stream, L2 flushed between steps
+  e2e        the same metric through crtb200_render with HOST buffers: camera + options in, the float colour buffer
+             (what RayTracer::render returns) copied back to pinned host memory inside the timed region
+  roofline   dominant traversal kernel: algorithmic bytes (32 B/node test + 52 B/triangle test + 64 B/ray, counted
+             under the reference's visit-all rule) / its CUDA-event duration, vs the measured HBM copy peak
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/crt_ref) on this box's host cores, bounded sample
+
+N > 1 (torchrun): the frame's 8x4-pixel tiles are dealt round-robin to the ranks (scene replicated), each rank renders
+its compact slab, NCCL gathers the slabs to rank 0, which scatters them into the frame.  Strong scaling: total work fixed.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "course-assignment-danielhalachev_b200"
+
+WORKLOADS = {
+    # name: (builder, kwargs, textured, max_depth)
+    "hw14_dragon_class": ("hw14_dragon_class", dict(width=3840, height=2160, sphere_n=290), False, 5),
+    "hw07_scene0b": ("hw07_scene0b", dict(width=1920, height=1080, sphere_n=41), False, 5),
+    "hw11_room": ("hw11_room", dict(width=1920, height=1080, sphere_n=32), False, 5),
+    "hw11_room_128": ("hw11_room", dict(width=1920, height=1080, sphere_n=128), False, 5),
+    "hw12_textures": ("hw12_textures", dict(width=1920, height=1080, sphere_n=92), True, 5),
+    "synthetic_10M": ("synthetic_10M", dict(width=1920, height=1080, sphere_n=913), False, 5),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def scene_cache_dir() -> str:
+    d = os.environ.get("CRT_BENCH_CACHE", "/tmp/crtb200_bench")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def ensure_scene(name: str, overrides: dict) -> tuple[str, str, dict, bool, int]:
+    """Writes the workload's .crtscene (deterministic generator) once; returns (file, folder, kwargs, textured, depth)."""
+    scenes = importlib.import_module(PKG + ".scenes")
+    builder, kw, tex, depth = WORKLOADS[name]
+    kw = dict(kw)
+    kw.update({k: v for k, v in overrides.items() if v})
+    tag = name + "_" + "_".join(f"{k}{v}" for k, v in sorted(kw.items()))
+    folder = scene_cache_dir()
+    path = os.path.join(folder, tag + ".crtscene")
+    if not os.path.exists(path):
+        t = time.time()
+        scene = scenes.CONFIGS[builder](**kw)
+        if "textures" in scene:
+            for tx in scene["textures"]:
+                if tx["type"] == "bitmap":
+                    scenes.write_png_rgb(folder + tx["file_path"], scenes.pattern_bitmap(512))
+        tmp = path + f".tmp{os.getpid()}"
+        scenes.write_crtscene(tmp, scene)
+        os.replace(tmp, path)
+        log(f"[bench] generated {path} in {time.time() - t:.1f}s")
+    return tag + ".crtscene", folder, kw, tex, depth
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.rows = []
+        self.proc = None
+        self.dev = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(rays: int, node_tests: int, tri_tests: int) -> int:
+    """bytes(ray) = 32*n_node + 52*n_tri + 64."""
+    return 32 * node_tests + 52 * tri_tests + 64 * rays
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref) on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference_sample(scene_file, folder, tex, depth, kw, budget_s, repeats, builder):
+    """Picks the largest resolution whose `repeats` renders fit budget_s, runs crt_ref --repeat; returns dict."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import binding as ob
+    scenes = importlib.import_module(PKG + ".scenes")
+    if not ob.have_reference(tex):
+        return None
+    W, H = kw["width"], kw["height"]
+    # calibration frame at 1/64 of the pixels (tree build is untimed, like MEASURE_TIME)
+    cands = [(W, H), (W // 2, H // 2), (W // 4, H // 4), (W // 8, H // 8)]
+    cal_kw = dict(kw, width=cands[3][0], height=cands[3][1])
+    cal_path = os.path.join(folder, f"cal_{os.path.basename(scene_file)}")
+    if not os.path.exists(cal_path):
+        scenes.write_crtscene(cal_path, scenes.CONFIGS[builder](**cal_kw))
+    cal = ob.run_reference(os.path.basename(cal_path), folder, "-", textured=tex, depth=depth, hits=False, ppm=False)
+    per_px = cal["render_s"] / (cal_kw["width"] * cal_kw["height"])
+    pick = cands[3]
+    for (w, h) in cands:
+        if per_px * w * h * repeats <= budget_s:
+            pick = (w, h)
+            break
+    if pick == (W, H):
+        path = scene_file
+    else:
+        skw = dict(kw, width=pick[0], height=pick[1])
+        path = f"sample_{pick[0]}x{pick[1]}_{os.path.basename(scene_file)}"
+        if not os.path.exists(os.path.join(folder, path)):
+            scenes.write_crtscene(os.path.join(folder, path), scenes.CONFIGS[builder](**skw))
+    out = ob.run_reference(path, folder, "-", textured=tex, depth=depth, hits=False, ppm=False, repeat=repeats)
+    rays = sum(out["rays"].values())
+    out["rays_total"] = rays
+    out["sample"] = (f"{pick[0]}x{pick[1]} frame of the same scene ({out['triangles']} triangles), oracle/_ref/crt_ref "
+                     f"mode BVHBucketsThreadPool, MEASURE_TIME seconds; KD build {out['build_s']:.1f}s untimed")
+    return out
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    scene_file, folder, kw, tex, depth = ensure_scene(args.workload, dict(width=args.width, height=args.height))
+    builder = WORKLOADS[args.workload][0]
+    out = run_reference_sample(scene_file, folder, tex, depth, kw, budget_s=150.0, repeats=args.steps + args.warmup, builder=builder)
+    if out is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/crt_ref not built"}))
+        return 0
+    times = out["render_all_s"][args.warmup:]
+    sec = sum(times) / len(times)
+    v = out["rays_total"] / sec / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s (primary+secondary)", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "width": kw["width"], "height": kw["height"], "triangles": out["triangles"],
+                   "max_depth": depth, "sample": out["sample"]},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": out["threads"], "kind": "reference", "sample": out["sample"]},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rays_per_step": out["rays_total"],
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def ours_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    crt = importlib.import_module(PKG)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+
+    if rank == 0:
+        scene_file, folder, kw, tex, depth = ensure_scene(args.workload, dict(width=args.width, height=args.height))
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        scene_file, folder, kw, tex, depth = ensure_scene(args.workload, dict(width=args.width, height=args.height))
+
+    t0 = time.time()
+    sf = crt.SceneFile(scene_file, folder)
+    t_parse = time.time() - t0
+    flat = sf.flatten()
+    ctx = crt.Context(dev.index)
+    t1 = time.time()
+    ctx.upload(flat, keepalive=sf)
+    t_upload = time.time() - t1
+    W, H = sf.info.width, sf.info.height
+    cam = sf.camera()
+    if rank == 0:
+        log(f"[bench] {args.workload}: {sf.info.n_triangles} triangles, {W}x{H}; parse {t_parse:.2f}s, KD build+flatten "
+            f"{sf.build_seconds:.2f}s, upload {t_upload:.2f}s")
+
+    rects, n_rects = sf.rects(mode=crt.MODE_B200_WAVEFRONT)
+    stream = torch.cuda.current_stream().cuda_stream
+    frame = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    frame8 = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # one counting pass (untimed): ray counts and visit-all traversal work = the algorithmic bytes
+    if world == 1:
+        _, _, _, cst = ctx.render(cam, crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, count_work=1), want_rgb=False)
+    else:
+        cst = None
+
+    if world > 1:
+        items = ctx.shard_items(world)
+        slab = torch.zeros((items, 3), dtype=torch.float32, device=dev)
+        slabs = torch.zeros((world, items, 3), dtype=torch.float32, device=dev) if rank == 0 else None
+        gather_list = list(slabs.unbind(0)) if rank == 0 else None
+        opt = crt.make_options(max_depth=depth, shard_index=rank, shard_count=world, traversal=args.traversal)
+    else:
+        opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, traversal=args.traversal)
+
+    def step():
+        if world > 1:
+            ctx.render_device(cam, opt, d_rgb=slab.data_ptr(), stream=stream)
+            dist.gather(slab, gather_list, dst=0)
+            if rank == 0:
+                ctx.assemble_shards(slabs.data_ptr(), world, d_rgb=frame.data_ptr(), d_rgb8=frame8.data_ptr(), stream=stream)
+        else:
+            ctx.render_device(cam, opt, d_rgb=frame.data_ptr(), d_rgb8=frame8.data_ptr(), stream=stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kstats = []
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # L2 flush (256 MiB > 126 MB L2), outside the timed events
+        if world > 1:
+            dist.barrier()
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+        torch.cuda.synchronize()
+        kstats.append(ctx.last_stats())
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+
+    # ray count of one frame: identical every step; with shards, sum over ranks
+    rays_local = torch.tensor([kstats[-1]["rays_total"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(rays_local, op=dist.ReduceOp.SUM)
+    rays_frame = int(rays_local.item())
+    ms_per_step = total_ms / args.steps
+    value = rays_frame / (ms_per_step * 1e-3) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- e2e through crtb200_render with pinned host buffers (N = 1) / host copy of the gathered frame (N > 1) ----
+    host_rgb = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    e2e_ms = []
+    if world == 1:
+        e_opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, traversal=args.traversal)
+        for k in range(args.steps + 1):
+            flush.fill_(k & 0xFF)
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            ctx.render(cam, e_opt, rgb_out=host_rgb.numpy())
+            dt = (time.perf_counter() - t) * 1e3
+            if k:
+                e2e_ms.append(dt)
+        e2e = {"value": rays_frame / (statistics.mean(e2e_ms) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": statistics.mean(e2e_ms),
+               "h2d_bytes_per_step": 48 + 40 + 16 * n_rects, "d2h_bytes_per_step": W * H * 12,
+               "api": "crtb200_render(host camera/options -> pinned host float RGB)"}
+    else:
+        e2e = None
+
+    peak, peak_src = measured_hbm_peak()
+    roofline = None
+    if cst is not None:
+        c_ms = statistics.mean(s["closest_ms"] for s in kstats)
+        s_ms = statistics.mean(s["shadow_ms"] for s in kstats)
+        closest_rays = cst["rays_primary"] + cst["rays_reflection"] + cst["rays_refraction"]
+        b_closest = algorithmic_bytes(closest_rays, cst["node_tests_closest"], cst["triangle_tests_closest"])
+        b_shadow = algorithmic_bytes(cst["rays_shadow"], cst["node_tests_shadow"], cst["triangle_tests_shadow"])
+        dom = ("k_closest", b_closest, c_ms) if c_ms >= s_ms else ("k_shadow_accumulate", b_shadow, s_ms)
+        achieved = dom[1] / (dom[2] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload, {}).get(dom[0])
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[1], "kernel_ms": dom[2],
+                    "closest_ms": c_ms, "shadow_ms": s_ms, "closest_bytes": b_closest, "shadow_bytes": b_shadow,
+                    "frame_GBps_all_kernels": (b_closest + b_shadow + 12 * W * H) / (ms_per_step * 1e-3) / 1e9,
+                    "node_tests_per_ray": (cst["node_tests"]) / max(1, cst["rays_total"]),
+                    "triangle_tests_per_ray": (cst["triangle_tests"]) / max(1, cst["rays_total"])}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            builder = WORKLOADS[args.workload][0]
+            ref = run_reference_sample(scene_file, folder, tex, depth, kw, budget_s=25.0, repeats=1, builder=builder)
+            if ref is not None:
+                cpu_baseline = {"value": ref["rays_total"] / ref["render_s"] / 1e6, "unit": "Mrays/s", "cores": ref["threads"],
+                                "kind": "reference", "sample": ref["sample"], "seconds": ref["render_s"]}
+            else:
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import binding as ob
+                # bounded sample for the port: the top-left 1/16 of the frame's bucket grid
+                nb = max(1, n_rects // 16)
+                t = time.perf_counter()
+                _, _, ost = ob.render(flat, cam, crt.make_options(max_depth=depth, rects=rects, n_rects=nb), want_hits=False)
+                dt = time.perf_counter() - t
+                cpu_baseline = {"value": ost["rays_total"] / dt / 1e6, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{nb} of {n_rects} buckets of the frame, OpenMP over rows", "seconds": dt}
+        except Exception as e:  # the baseline is a report, never a reason to lose the bench line
+            cpu_baseline = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+
+    launches = kstats[-1]["kernel_launches"] + (1 if world > 1 else 0)
+    line = {
+        "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "width": W, "height": H, "triangles": int(sf.info.n_triangles), "max_depth": depth,
+                   "traversal": "exact (reference visit-all order)" if args.traversal == 0 else "fast (ordered+culled)",
+                   "parallelism": f"tiles{world}" if world > 1 else "single", "l2": "flushed between steps (256 MiB fill)",
+                   "rays_per_frame": rays_frame},
+        "clocks": clocks, "gpu_launches": launches * args.steps, "step_ms": step_ms,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if roofline:
+        line["roofline"] = roofline
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hw14_dragon_class", choices=list(WORKLOADS))
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--traversal", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", os.environ.get("MASTER_PORT", "29511"), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return ours_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

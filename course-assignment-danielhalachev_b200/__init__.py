@@ -107,13 +107,16 @@ HIT_DTYPE = np.dtype([("mesh", np.int32), ("triangle", np.int32), ("t", np.float
 
 class Stats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_reflection", C.c_uint64),
-                ("rays_refraction", C.c_uint64), ("node_tests", C.c_uint64), ("triangle_tests", C.c_uint64),
-                ("device_ms", C.c_double), ("trace_ms", C.c_double), ("total_ms", C.c_double),
+                ("rays_refraction", C.c_uint64), ("node_tests_closest", C.c_uint64), ("triangle_tests_closest", C.c_uint64),
+                ("node_tests_shadow", C.c_uint64), ("triangle_tests_shadow", C.c_uint64),
+                ("device_ms", C.c_double), ("closest_ms", C.c_double), ("shadow_ms", C.c_double), ("total_ms", C.c_double),
                 ("kernel_launches", C.c_uint32), ("levels", C.c_uint32)]
 
     def as_dict(self) -> dict:
         d = {n: getattr(self, n) for n, _ in self._fields_}
         d["rays_total"] = d["rays_primary"] + d["rays_shadow"] + d["rays_reflection"] + d["rays_refraction"]
+        d["node_tests"] = d["node_tests_closest"] + d["node_tests_shadow"]
+        d["triangle_tests"] = d["triangle_tests_closest"] + d["triangle_tests_shadow"]
         return d
 
 

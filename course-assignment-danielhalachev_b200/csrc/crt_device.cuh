@@ -163,50 +163,54 @@ CRT_DI void primary_ray(const DCamera &cam, uint32_t W, uint32_t H, uint32_t row
 }
 
 // BoundingBox::hasIntersection                                                  BoundingBox.h:85-108
-// (no t1 >= 0 test: boxes behind the origin pass; NaN bounds never reject -- both as in the reference)
+// (no t1 >= 0 test: boxes behind the origin pass; NaN bounds never reject -- both as in the reference).
+// Branch-free: the reference's early returns only skip work; every reject condition is evaluated on the same running
+// (t0, t1) it would have seen, so OR-ing them is exact.  An axis with |d| < FLT_EPSILON leaves (t0, t1) untouched.
 CRT_DI bool slab_test(const float4 lo, const float4 hi, const Ray &r) {
   float t0 = -CRT_FLT_MAX, t1 = CRT_FLT_MAX;
-#define CRT_SLAB_AXIS(bit, O, I, MN, MX)                     \
-  if (r.flags & bit) {                                       \
-    if (O < MN || O > MX) return false;                      \
-  } else {                                                   \
-    float tn = fmul(fsub(MN, O), I);                         \
-    float tf = fmul(fsub(MX, O), I);                         \
-    if (tn > tf) {                                           \
-      float tmp = tn;                                        \
-      tn = tf;                                               \
-      tf = tmp;                                              \
-    }                                                        \
-    t0 = stdmax(t0, tn);                                     \
-    t1 = stdmin(t1, tf);                                     \
-    if (t0 > t1) return false;                               \
+  bool reject = false;
+#define CRT_SLAB_AXIS(bit, O, I, MN, MX)                                  \
+  {                                                                       \
+    const bool par = (r.flags & bit) != 0u;                               \
+    const float a_ = fmul(fsub(MN, O), I);                                \
+    const float b_ = fmul(fsub(MX, O), I);                                \
+    const bool sw = a_ > b_;                                              \
+    const float tn = sw ? b_ : a_;                                        \
+    const float tf = sw ? a_ : b_;                                        \
+    const float n0 = stdmax(t0, tn);                                      \
+    const float n1 = stdmin(t1, tf);                                      \
+    t0 = par ? t0 : n0;                                                   \
+    t1 = par ? t1 : n1;                                                   \
+    reject = reject || (par ? (O < MN || O > MX) : (t0 > t1));            \
   }
   CRT_SLAB_AXIS(1u, r.o.x, r.inv.x, lo.x, hi.x)
   CRT_SLAB_AXIS(2u, r.o.y, r.inv.y, lo.y, hi.y)
   CRT_SLAB_AXIS(4u, r.o.z, r.inv.z, lo.z, hi.z)
 #undef CRT_SLAB_AXIS
-  return true;
+  return !reject;
 }
 
 // Ray::intersectWithTriangle + Triangle::pointIsInTriangle                       Ray.cpp:9-31, Triangle.cpp:37-57
-// Returns true for a candidate; t may be NaN / inf exactly like the reference.
+// Returns true for a candidate; t may be NaN / inf exactly like the reference.  Evaluated without
+// early exits (lanes of a warp test different triangles; the exits would only diverge): each reject condition is the
+// reference's, on the same operands.
 CRT_DI bool triangle_test(const float4 g0, const float4 g1, const float4 g2, const Ray &r, float &t_out, V3 &p_out) {
   const V3 n = mk(g0.w, g1.w, g2.w);
   const V3 v0 = mk(g0.x, g0.y, g0.z);
-  const float nd = vdot(r.d, n);
-  if ((r.flags & 8u) && nd >= 0.0f) return false;
-  const float dist = -vdot(v0, n);
-  const float t = fdiv(-fadd(vdot(n, r.o), dist), nd);
-  if (t < 0.0f) return false;
-  const V3 p = vadd(r.o, vscale(r.d, t));
   const V3 v1 = mk(g1.x, g1.y, g1.z);
   const V3 v2 = mk(g2.x, g2.y, g2.z);
-  if (vdot(n, vcross(vsub(v1, v0), vsub(p, v0))) < -CRT_FLT_EPSILON) return false;
-  if (vdot(n, vcross(vsub(v2, v1), vsub(p, v1))) < -CRT_FLT_EPSILON) return false;
-  if (vdot(n, vcross(vsub(v0, v2), vsub(p, v2))) < -CRT_FLT_EPSILON) return false;
+  const float nd = vdot(r.d, n);
+  const float dist = -vdot(v0, n);
+  const float t = fdiv(-fadd(vdot(n, r.o), dist), nd);
+  const V3 p = vadd(r.o, vscale(r.d, t));
+  const float e0 = vdot(n, vcross(vsub(v1, v0), vsub(p, v0)));
+  const float e1 = vdot(n, vcross(vsub(v2, v1), vsub(p, v1)));
+  const float e2 = vdot(n, vcross(vsub(v0, v2), vsub(p, v2)));
+  const bool culled = (r.flags & 8u) && nd >= 0.0f;
+  const bool miss = culled || (t < 0.0f) || (e0 < -CRT_FLT_EPSILON) || (e1 < -CRT_FLT_EPSILON) || (e2 < -CRT_FLT_EPSILON);
   t_out = t;
   p_out = p;
-  return true;
+  return !miss;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -227,50 +231,49 @@ CRT_DI void trav_begin(Trav &s, const DScene &sc) {
   s.tref = s.tend = 0;
 }
 
-// Advances until a triangle list is pending (returns true) or the traversal is complete (returns false).
+// One traversal micro-step.  Returns 0 = keep stepping, 1 = a triangle list is pending (tref..tend), 2 = traversal
+// complete.  Top-level and mesh-level AABB tests share one code path so lanes at different levels do not diverge.
 // SKIP_REFRACTIVE: shadow rays ignore refractive meshes (AccelerationStructure.cpp:67-71).
+enum { TRAV_STEP = 0, TRAV_LEAF = 1, TRAV_DONE = 2 };
 template <bool SKIP_REFRACTIVE, bool COUNT>
-CRT_DI bool trav_to_leaf(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests) {
-  for (;;) {
-    if (s.cur != s.cend) {
-      const float4 lo = __ldg(&sc.nodes[2 * (size_t)s.cur]);
-      const float4 hi = __ldg(&sc.nodes[2 * (size_t)s.cur + 1]);
-      const uint32_t a = __float_as_uint(lo.w);
-      if (COUNT) node_tests++;
-      if (slab_test(lo, hi, r)) {
-        s.cur += 1;
-        if (a & CRT_LEAF_FLAG) {
-          s.tref = __float_as_uint(hi.w);
-          s.tend = s.tref + (a & ~CRT_LEAF_FLAG);
-          return true;
-        }
-      } else {
-        s.cur = (a & CRT_LEAF_FLAG) ? s.cur + 1 : a;
-      }
-    } else if (s.mref != s.mend) {
-      const uint32_t m = __ldg(&sc.top_refs[s.mref++]);
-      const DMesh me = sc.meshes[m];
-      if (SKIP_REFRACTIVE && sc.materials[me.material].type == 3u) continue;
-      s.cur = me.node_begin;
-      s.cend = me.node_end;
-    } else if (s.top != sc.top_end) {
-      const float4 lo = __ldg(&sc.nodes[2 * (size_t)s.top]);
-      const float4 hi = __ldg(&sc.nodes[2 * (size_t)s.top + 1]);
-      const uint32_t a = __float_as_uint(lo.w);
-      if (COUNT) node_tests++;
-      if (slab_test(lo, hi, r)) {
-        s.top += 1;
-        if (a & CRT_LEAF_FLAG) {
-          s.mref = __float_as_uint(hi.w);
-          s.mend = s.mref + (a & ~CRT_LEAF_FLAG);
-        }
-      } else {
-        s.top = (a & CRT_LEAF_FLAG) ? s.top + 1 : a;
+CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests) {
+  const bool in_mesh = s.cur != s.cend;
+  if (in_mesh || (s.mref == s.mend && s.top != sc.top_end)) {
+    const uint32_t idx = in_mesh ? s.cur : s.top;
+    const float4 lo = __ldg(&sc.nodes[2 * (size_t)idx]);
+    const float4 hi = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
+    const uint32_t a = __float_as_uint(lo.w);
+    const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
+    if (COUNT) node_tests++;
+    const bool pass = slab_test(lo, hi, r);
+    const uint32_t next = (pass || leaf) ? idx + 1 : a;
+    const uint32_t first = __float_as_uint(hi.w), last = first + (a & ~CRT_LEAF_FLAG);
+    if (in_mesh) {
+      s.cur = next;
+      if (pass && leaf) {
+        s.tref = first;
+        s.tend = last;
+        return TRAV_LEAF;
       }
     } else {
-      return false;
+      s.top = next;
+      if (pass && leaf) {
+        s.mref = first;
+        s.mend = last;
+      }
     }
+    return TRAV_STEP;
   }
+  if (s.mref != s.mend) {
+    const uint32_t m = __ldg(&sc.top_refs[s.mref++]);
+    const DMesh me = sc.meshes[m];
+    if (!(SKIP_REFRACTIVE && sc.materials[me.material].type == 3u)) {
+      s.cur = me.node_begin;
+      s.cend = me.node_end;
+    }
+    return TRAV_STEP;
+  }
+  return TRAV_DONE;
 }
 
 // Closest-hit bookkeeping = "closest = intersections[0]; min = inf; for c: if (c.t < min) ..." (KDTree.cpp:75-86,

@@ -39,7 +39,7 @@ struct Levels {
   uint4 *comb;        // per node: {kind, childA, childB / material, bits(F)}
   float4 *dq;         // diffuse queue, 3 x float4 per item: {P, bits(node)} {N, base.r} {base.g, base.b, -, -}
   uint32_t *counts;   // [CRT_MAX_LEVELS] rays per level; [CRT_MAX_LEVELS] = diffuse queue length
-  unsigned long long *stats;  // [0..3] rays by type, [4] node tests, [5] triangle tests
+  unsigned long long *stats;  // [0..3] rays by type, [4],[5] closest node / triangle tests, [6],[7] shadow
   uint32_t offset[CRT_MAX_LEVELS + 1];
 };
 
@@ -82,10 +82,16 @@ CRT_DI bool item_pixel(const Frame &fr, const DScene &sc, uint32_t item, uint32_
 
 // ------------------------------------------------------------------------------------------------------------
 // K2: closest hit.  Replaces RayTracer::trace -> KDTree<ObjectKDTreeSubTree>::intersect -> KDTree<Triangle>::intersect
-// (RayTracer.cpp:453-458, KDTree.cpp:127-166, 48-87).  Persistent: lanes pull rays from a global cursor with one
-// atomic per refill; a warp regroups (refills idle lanes) when fewer than REGROUP lanes are still traversing.
+// (RayTracer.cpp:453-458, KDTree.cpp:127-166, 48-87).
+//
+// Persistent warps, one ray per lane.  Every loop below has a WARP-UNIFORM trip count (its condition is a vote), so the
+// 32 lanes stay converged under independent thread scheduling; per-lane work is predicated.  (A first version with
+// per-lane `while (active)` loops ran at 1.8-5 active threads per instruction: ncu profiles/r1a.)  One outer round =
+//   refill    when >= REFILL lanes are idle, one atomicAdd per warp hands them the next rays of the global cursor
+//   node phase   every lane steps its stack-free KD walk until it reaches a leaf or the end of the tree
+//   leaf phase   every lane tests the triangles of its pending leaf
 // ------------------------------------------------------------------------------------------------------------
-template <bool PRIMARY, bool COUNT, int REGROUP>
+template <bool PRIMARY, bool COUNT, int REFILL>
 __global__ void __launch_bounds__(256) k_closest(const DScene sc, const Frame fr, const Levels lv, const uint32_t level,
                                                 uint32_t *__restrict__ work_counter) {
   const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
@@ -97,50 +103,57 @@ __global__ void __launch_bounds__(256) k_closest(const DScene sc, const Frame fr
   Trav tv;
   Closest cl;
   tv.tref = tv.tend = 0;
+  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
+  ray.flags = 0;
+  trav_begin(tv, sc);
+  closest_begin(cl);
   for (;;) {
     const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !active);
-    if (!exhausted && idle) {
+    if (!exhausted && __popc(idle) >= REFILL) {
       const uint32_t want = __popc(idle);
       uint32_t start = 0;
       if (lane == 0) start = atomicAdd(work_counter, want);
       start = __shfl_sync(CRT_FULL_MASK, start, 0);
       if (start + want >= total) exhausted = true;
-      if (!active) {
-        const uint32_t i = start + __popc(idle & lanemask_lt());
-        if (i < total) {
-          bool valid = true;
-          if (PRIMARY) {
-            uint32_t row, col;
-            valid = item_pixel(fr, sc, fr.item_begin + i, row, col);
-            if (valid) primary_ray(fr.cam, sc.width, sc.height, row, col, ray.o, ray.d);
-          } else {
-            const float4 o = lv.ray_o[node_base - lv.offset[1] + i];
-            const float4 d = lv.ray_d[node_base - lv.offset[1] + i];
-            ray.o = mk(o.x, o.y, o.z);
-            ray.d = mk(d.x, d.y, d.z);
-          }
-          if (valid) {
-            ray_prepare(ray, PRIMARY);
-            trav_begin(tv, sc);
-            closest_begin(cl);
-            node = node_base + i;
-            active = true;
-          }
+      const uint32_t i = start + __popc(idle & lanemask_lt());
+      if (!active && i < total) {
+        bool valid = true;
+        if (PRIMARY) {
+          uint32_t row, col;
+          valid = item_pixel(fr, sc, fr.item_begin + i, row, col);
+          if (valid) primary_ray(fr.cam, sc.width, sc.height, row, col, ray.o, ray.d);
+        } else {
+          const float4 o = lv.ray_o[node_base - lv.offset[1] + i];
+          const float4 d = lv.ray_d[node_base - lv.offset[1] + i];
+          ray.o = mk(o.x, o.y, o.z);
+          ray.d = mk(d.x, d.y, d.z);
+        }
+        if (valid) {
+          ray_prepare(ray, PRIMARY);
+          trav_begin(tv, sc);
+          closest_begin(cl);
+          node = node_base + i;
+          active = true;
         }
       }
     }
-    if (__ballot_sync(CRT_FULL_MASK, active) == 0) {
+    if (!__any_sync(CRT_FULL_MASK, active)) {
       if (exhausted) break;
       continue;
     }
-    while (active) {
-      if (tv.tref == tv.tend && !trav_to_leaf<false, COUNT>(tv, sc, ray, n_nodes)) {
-        lv.hit_tri[node] = cl.best_tri;
-        lv.hit_t[node] = cl.best_t;
-        active = false;
-        break;
-      }
-      while (tv.tref != tv.tend) {
+    // ---- node phase ----
+    int st = active ? TRAV_STEP : TRAV_DONE;
+    while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
+      if (st == TRAV_STEP) st = trav_step<false, COUNT>(tv, sc, ray, n_nodes);
+    }
+    if (active && st == TRAV_DONE) {
+      lv.hit_tri[node] = cl.best_tri;
+      lv.hit_t[node] = cl.best_t;
+      active = false;
+    }
+    // ---- leaf phase ----
+    while (__any_sync(CRT_FULL_MASK, tv.tref != tv.tend)) {
+      if (tv.tref != tv.tend) {
         const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
         const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
         const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
@@ -150,7 +163,6 @@ __global__ void __launch_bounds__(256) k_closest(const DScene sc, const Frame fr
         if (COUNT) n_tris++;
         if (triangle_test(g0, g1, g2, ray, t, p)) closest_offer(cl, tri, t);
       }
-      if (REGROUP > 0 && !exhausted && __popc(__activemask()) < REGROUP) break;
     }
   }
   if (COUNT) {
@@ -383,8 +395,8 @@ __global__ void __launch_bounds__(256) k_shade(const DScene sc, const Frame fr, 
 // and walks the lights in order so the sum is formed in the reference's order.
 // ------------------------------------------------------------------------------------------------------------
 // COUNT: 0 = no counters; 1 = count under the reference's visit-all rule (early termination disabled, same result);
-// 2 = count the work this kernel really does with early termination.
-template <int COUNT, int REGROUP>
+// 2 = count the work this kernel really does with early termination.  Loop structure: see k_closest.
+template <int COUNT, int REFILL>
 __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, const Frame fr, const Levels lv,
                                                           uint32_t *__restrict__ work_counter) {
   const uint32_t total = lv.counts[CRT_MAX_LEVELS];
@@ -396,48 +408,47 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, cons
   float contrib = 0.0f, dist = 0.0f;
   Ray ray;
   Trav tv;
-  tv.tref = tv.tend = 0;
+  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
+  ray.flags = 0;
+  trav_begin(tv, sc);
   for (;;) {
     const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !active);
-    if (!exhausted && idle) {
+    if (!exhausted && __popc(idle) >= REFILL) {
       const uint32_t want = __popc(idle);
       uint32_t start = 0;
       if (lane == 0) start = atomicAdd(work_counter, want);
       start = __shfl_sync(CRT_FULL_MASK, start, 0);
       if (start + want >= total) exhausted = true;
-      if (!active) {
-        const uint32_t i = start + __popc(idle & lanemask_lt());
-        if (i < total) {
-          const float4 q0 = lv.dq[3 * (size_t)i], q1 = lv.dq[3 * (size_t)i + 1], q2 = lv.dq[3 * (size_t)i + 2];
-          P = mk(q0.x, q0.y, q0.z);
-          node = __float_as_uint(q0.w);
-          N = mk(q1.x, q1.y, q1.z);
-          base = mk(q1.w, q2.x, q2.y);
-          acc = mk(0, 0, 0);
-          light = 0;
-          active = true;
-          need_ray = true;
-        }
+      const uint32_t i = start + __popc(idle & lanemask_lt());
+      if (!active && i < total) {
+        const float4 q0 = lv.dq[3 * (size_t)i], q1 = lv.dq[3 * (size_t)i + 1], q2 = lv.dq[3 * (size_t)i + 2];
+        P = mk(q0.x, q0.y, q0.z);
+        node = __float_as_uint(q0.w);
+        N = mk(q1.x, q1.y, q1.z);
+        base = mk(q1.w, q2.x, q2.y);
+        acc = mk(0, 0, 0);
+        light = 0;
+        active = true;
+        need_ray = true;
       }
     }
-    if (__ballot_sync(CRT_FULL_MASK, active) == 0) {
+    if (!__any_sync(CRT_FULL_MASK, active)) {
       if (exhausted) break;
       continue;
     }
-    while (active) {
-      if (need_ray) {
-        if (light == sc.n_lights) {
-          lv.color[node] = make_float4(acc.x, acc.y, acc.z, 0.f);
-          active = false;
-          break;
-        }
+    // ---- next shadow ray of this lane's diffuse hit, or retire the hit ----
+    if (active && need_ray) {
+      if (light == sc.n_lights) {
+        lv.color[node] = make_float4(acc.x, acc.y, acc.z, 0.f);
+        active = false;
+      } else {
         const DLight L = sc.lights[light];
         V3 ld = vsub(mk(L.pos[0], L.pos[1], L.pos[2]), P);
         dist = vlen(ld);
-        const float area = fmul(fmul(fmul(4.0f, dist), dist), PI);  // 4 * r * r * PI
+        const float area = fmul(fmul(fmul(4.0f, dist), dist), PI);  // 4 * r * r * PI   RayTracer.cpp:311-312
         ld = vnorm(ld);
         const float angle = stdmax(0.0f, vdot(ld, N));
-        contrib = fmul(fdiv(L.intensity, area), angle);  // (float(I) / area * angle)
+        contrib = fmul(fdiv(L.intensity, area), angle);  // (float(I) / area * angle)     RayTracer.cpp:320
         ray.o = vadd(P, vscale(N, fr.shadow_bias));
         ray.d = ld;
         ray_prepare(ray, false);
@@ -445,15 +456,21 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, cons
         occluded = false;
         need_ray = false;
       }
-      if (tv.tref == tv.tend && !trav_to_leaf<true, (COUNT != 0)>(tv, sc, ray, n_nodes)) {
-        // shadow ray finished; unoccluded: finalColor += direct * albedo          RayTracer.cpp:318-327
-        if (!occluded) acc = vadd(acc, sscale(contrib, base));
-        occluded = false;
-        light++;
-        need_ray = true;
-        continue;
-      }
-      while (tv.tref != tv.tend) {
+    }
+    // ---- node phase ----
+    int st = (active && !need_ray) ? TRAV_STEP : TRAV_DONE;
+    while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
+      if (st == TRAV_STEP) st = trav_step<true, (COUNT != 0)>(tv, sc, ray, n_nodes);
+    }
+    if (active && !need_ray && st == TRAV_DONE) {
+      // shadow ray finished; unoccluded: finalColor += direct * albedo            RayTracer.cpp:318-327
+      if (!occluded) acc = vadd(acc, sscale(contrib, base));
+      light++;
+      need_ray = true;
+    }
+    // ---- leaf phase ----
+    while (__any_sync(CRT_FULL_MASK, tv.tref != tv.tend)) {
+      if (tv.tref != tv.tend) {
         const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
         const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
         const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
@@ -461,22 +478,16 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, cons
         float t;
         V3 p;
         if (COUNT) n_tris++;
-        if (triangle_test(g0, g1, g2, ray, t, p)) {
-          // (hitPoint - ray.origin).length() <= distanceToLight               AccelerationStructure.cpp:73-74
-          if (vlen(vsub(p, ray.o)) <= dist) {
-            occluded = true;
-            if (COUNT != 1) break;
+        // (hitPoint - ray.origin).length() <= distanceToLight                   AccelerationStructure.cpp:73-74
+        if (triangle_test(g0, g1, g2, ray, t, p) && vlen(vsub(p, ray.o)) <= dist) {
+          occluded = true;
+          if (COUNT != 1) {  // early termination: the rest of the walk cannot change the answer
+            tv.tref = tv.tend = 0;
+            light++;
+            need_ray = true;
           }
         }
       }
-      if (COUNT != 1 && occluded) {
-        tv.tref = tv.tend = 0;
-        light++;
-        need_ray = true;
-        occluded = false;
-        continue;
-      }
-      if (REGROUP > 0 && !exhausted && __popc(__activemask()) < REGROUP) break;
     }
   }
   if (COUNT) {
@@ -487,8 +498,8 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, cons
       b += __shfl_xor_sync(CRT_FULL_MASK, b, d);
     }
     if (lane == 0) {
-      atomicAdd(&lv.stats[4], a);
-      atomicAdd(&lv.stats[5], b);
+      atomicAdd(&lv.stats[6], a);
+      atomicAdd(&lv.stats[7], b);
     }
   }
 }
@@ -641,17 +652,17 @@ __global__ void __launch_bounds__(256) k_query(const DScene sc, const float *__r
     if (ray_type == 1u) {
       const float dist = max_distance[i];
       bool occ = false;
-      while (!occ && trav_to_leaf<true, false>(tv, sc, ray, dummy)) {
+      for (;;) {
+        int st = TRAV_STEP;
+        while (st == TRAV_STEP) st = trav_step<true, false>(tv, sc, ray, dummy);
+        if (st == TRAV_DONE || occ) break;
         while (tv.tref != tv.tend) {
           const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
           float t;
           V3 p;
           if (triangle_test(__ldg(&sc.tri_geom[3 * (size_t)tri]), __ldg(&sc.tri_geom[3 * (size_t)tri + 1]),
                             __ldg(&sc.tri_geom[3 * (size_t)tri + 2]), ray, t, p)) {
-            if (vlen(vsub(p, ray.o)) <= dist) {
-              occ = true;
-              break;
-            }
+            if (vlen(vsub(p, ray.o)) <= dist) occ = true;
           }
         }
       }
@@ -659,7 +670,10 @@ __global__ void __launch_bounds__(256) k_query(const DScene sc, const float *__r
     } else {
       Closest cl;
       closest_begin(cl);
-      while (trav_to_leaf<false, false>(tv, sc, ray, dummy)) {
+      for (;;) {
+        int st = TRAV_STEP;
+        while (st == TRAV_STEP) st = trav_step<false, false>(tv, sc, ray, dummy);
+        if (st == TRAV_DONE) break;
         while (tv.tref != tv.tend) {
           const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
           float t;

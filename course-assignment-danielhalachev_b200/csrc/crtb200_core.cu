@@ -15,6 +15,10 @@
 
 using namespace crtd;
 
+#ifndef CRT_REFILL
+#define CRT_REFILL 8  // refill a warp when at least this many lanes are idle
+#endif
+
 static thread_local std::string g_error;
 static int fail(int code, const std::string &msg) {
   g_error = msg;
@@ -59,6 +63,9 @@ struct crtb200_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> kev;  // per-launch event pairs: K2 / K3 timing
+  std::vector<int> kev_kind;     // 0 = closest, 1 = shadow (one entry per pair)
+  size_t kev_used = 0;
   bool have_scene = false;
   uint64_t queue_budget = 16ull << 30;
 
@@ -136,9 +143,9 @@ int crtb200_create(int device, crtb200_ctx **out) {
   }
   for (auto &e : c->ev) cudaEventCreate(&e);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, 20>, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL>, 256, 0);
   c->blocks_closest = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<0, 20>, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<0, CRT_REFILL>, 256, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
   *out = c;
   return CRTB200_OK;
@@ -156,6 +163,7 @@ int crtb200_destroy(crtb200_ctx *c) {
   c->stats_dev.release();
   for (auto &e : c->ev)
     if (e) cudaEventDestroy(e);
+  for (auto &e : c->kev) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return CRTB200_OK;
@@ -494,12 +502,21 @@ static int plan_mask(crtb200_ctx *c, const crtb200_options *o) {
   return CRTB200_OK;
 }
 
+static cudaEvent_t next_event(crtb200_ctx *c) {
+  if (c->kev_used == c->kev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->kev.push_back(e);
+  }
+  return c->kev[c->kev_used++];
+}
+
 template <bool COUNT>
 static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, uint32_t level, uint32_t *work, cudaStream_t st) {
   if (primary)
-    k_closest<true, COUNT, 20><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
+    k_closest<true, COUNT, CRT_REFILL><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
   else
-    k_closest<false, COUNT, 20><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
+    k_closest<false, COUNT, CRT_REFILL><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
 }
 
 // Enqueue one frame on `st`.  d_rgb / d_rgb8 / d_hits / d_slab are device pointers (any may be null).
@@ -536,6 +553,8 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   const int grid_simple = c->sm_count * 8;
 
   CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 8 * sizeof(unsigned long long), st));
+  c->kev_used = 0;
+  c->kev_kind.clear();
   if (timed) CUDA_TRY(cudaEventRecord(c->ev[0], st));
   uint32_t launches = 0;
   for (uint32_t begin = 0; begin < shard_items; begin += c->cap_items) {
@@ -544,19 +563,29 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     CUDA_TRY(cudaMemsetAsync(c->counts.p, 0, (CRT_MAX_LEVELS + 1) * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(c->work.p, 0, (CRT_MAX_LEVELS + 2) * sizeof(uint32_t), st));
     for (uint32_t l = 0; l < levels; l++) {
+      if (timed) {
+        cudaEventRecord(next_event(c), st);
+        c->kev_kind.push_back(0);
+      }
       if (o->count_work)
         launch_closest<true>(c, l == 0, fr, l, c->work.p + l, st);
       else
         launch_closest<false>(c, l == 0, fr, l, c->work.p + l, st);
+      if (timed) cudaEventRecord(next_event(c), st);
       k_shade<<<grid_simple, 256, 0, st>>>(c->sc, fr, c->lv, l);
       launches += 2;
     }
+    if (timed) {
+      cudaEventRecord(next_event(c), st);
+      c->kev_kind.push_back(1);
+    }
     if (o->count_work == 1)
-      k_shadow_accumulate<1, 20><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+      k_shadow_accumulate<1, CRT_REFILL><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
     else if (o->count_work == 2)
-      k_shadow_accumulate<2, 20><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+      k_shadow_accumulate<2, CRT_REFILL><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
     else
-      k_shadow_accumulate<0, 20><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+      k_shadow_accumulate<0, CRT_REFILL><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+    if (timed) cudaEventRecord(next_event(c), st);
     launches++;
     for (uint32_t l = levels - 1; l-- > 0;) {
       k_resolve<<<grid_simple, 256, 0, st>>>(c->sc, fr, c->lv, l);
@@ -591,13 +620,20 @@ static int collect_stats(crtb200_ctx *c, bool timed) {
   c->last.rays_shadow += (uint64_t)dq * c->sc.n_lights;
   c->last.rays_reflection = st[2];
   c->last.rays_refraction = st[3];
-  c->last.node_tests = st[4];
-  c->last.triangle_tests = st[5];
+  c->last.node_tests_closest = st[4];
+  c->last.triangle_tests_closest = st[5];
+  c->last.node_tests_shadow = st[6];
+  c->last.triangle_tests_shadow = st[7];
   if (timed) {
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
     c->last.device_ms = ms;
-    c->last.trace_ms = ms;
+    c->last.closest_ms = c->last.shadow_ms = 0.0;
+    for (size_t k = 0; k < c->kev_kind.size() && 2 * k + 1 < c->kev_used; k++) {
+      float kms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&kms, c->kev[2 * k], c->kev[2 * k + 1]));
+      (c->kev_kind[k] == 0 ? c->last.closest_ms : c->last.shadow_ms) += kms;
+    }
   }
   return CRTB200_OK;
 }
@@ -644,10 +680,13 @@ int crtb200_render_frames(crtb200_ctx *c, const crtb200_camera *cams, uint32_t n
     total.rays_shadow += s.rays_shadow;
     total.rays_reflection += s.rays_reflection;
     total.rays_refraction += s.rays_refraction;
-    total.node_tests += s.node_tests;
-    total.triangle_tests += s.triangle_tests;
+    total.node_tests_closest += s.node_tests_closest;
+    total.triangle_tests_closest += s.triangle_tests_closest;
+    total.node_tests_shadow += s.node_tests_shadow;
+    total.triangle_tests_shadow += s.triangle_tests_shadow;
     total.device_ms += s.device_ms;
-    total.trace_ms += s.trace_ms;
+    total.closest_ms += s.closest_ms;
+    total.shadow_ms += s.shadow_ms;
     total.kernel_launches += s.kernel_launches;
     total.levels = s.levels;
   }

@@ -170,10 +170,13 @@ typedef struct crtb200_hit {
 
 typedef struct crtb200_stats {
   uint64_t rays_primary, rays_shadow, rays_reflection, rays_refraction; /* traced rays, SURVEY 8(d) definition */
-  uint64_t node_tests, triangle_tests; /* closest-hit + shadow AABB / triangle tests, per options.count_work  */
-  double device_ms;  /* CUDA-event time of the kernels of the last render (all levels)                      */
-  double trace_ms;   /* of which: closest-hit + shadow traversal kernels                                    */
-  double total_ms;   /* host wall time of the call, copies included                                         */
+  /* AABB / triangle tests per options.count_work, split by kernel: closest-hit (K2) and shadow (K3) */
+  uint64_t node_tests_closest, triangle_tests_closest;
+  uint64_t node_tests_shadow, triangle_tests_shadow;
+  double device_ms;  /* CUDA-event time of the whole frame on the launching stream                          */
+  double closest_ms; /* of which: closest-hit traversal launches (K2, all levels)                            */
+  double shadow_ms;  /* of which: shadow any-hit + accumulate launches (K3)                                  */
+  double total_ms;   /* host wall time of the call, copies included                                          */
   uint32_t kernel_launches;
   uint32_t levels;
 } crtb200_stats;

@@ -23,11 +23,14 @@ HIT_DTYPE = np.dtype([("mesh", np.int32), ("triangle", np.int32), ("t", np.float
 
 class OracleStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays_primary", "rays_shadow", "rays_reflection", "rays_refraction",
-                                          "node_tests", "triangle_tests")]
+                                          "node_tests_closest", "triangle_tests_closest", "node_tests_shadow",
+                                          "triangle_tests_shadow", "max_query_tests")]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_}
         d["rays_total"] = d["rays_primary"] + d["rays_shadow"] + d["rays_reflection"] + d["rays_refraction"]
+        d["node_tests"] = d["node_tests_closest"] + d["node_tests_shadow"]
+        d["triangle_tests"] = d["triangle_tests_closest"] + d["triangle_tests_shadow"]
         return d
 
 

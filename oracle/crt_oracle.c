@@ -56,7 +56,9 @@ typedef struct {
   float shadow_bias, reflection_bias, refraction_bias;
   /* per-thread counters */
   uint64_t rays[4];
-  uint64_t node_tests, tri_tests;
+  uint64_t node_tests[2], tri_tests[2]; /* [0] closest-hit queries, [1] shadow queries */
+  int shadow_query;
+  uint64_t max_query_tests; /* most AABB + triangle tests spent on a single query (latency tail) */
 } octx;
 
 /* ---- BoundingBox::hasIntersection  include/tracer/BoundingBox.h:85-108 ---- */
@@ -134,14 +136,14 @@ static hitinfo mesh_intersect(octx *c, uint32_t mesh_index, const ray_t *r) {
   stack[sp++] = 0;
   while (sp > 0) {
     const crtb200_kdnode *n = &nodes[stack[--sp]];
-    c->node_tests++;
+    c->node_tests[c->shadow_query]++;
     if (!box_hit(n, r)) continue;
     if (n->leaf_count) {
       for (uint32_t k = 0; k < n->leaf_count; k++) {
         uint32_t tri = m->first_triangle + refs[n->leaf_start + k];
         float t;
         v3 p;
-        c->tri_tests++;
+        c->tri_tests[c->shadow_query]++;
         if (ray_tri(s, r, tri, &t, &p)) {
           /* intersections[0] is the initial closest (KDTree.cpp:78); strict < afterwards (:80-85) */
           if (!best.has) {
@@ -182,11 +184,13 @@ static hitinfo scene_intersect(octx *c, const ray_t *r) {
   uint32_t stack[STACK_MAX];
   int sp = 0;
   if (r->type >= 0 && r->type < 4) c->rays[r->type]++;
+  c->shadow_query = 0;
+  const uint64_t before = c->node_tests[0] + c->tri_tests[0];
   if (s->n_top_nodes == 0) return best;
   stack[sp++] = 0;
   while (sp > 0) {
     const crtb200_kdnode *n = &s->top_nodes[stack[--sp]];
-    c->node_tests++;
+    c->node_tests[c->shadow_query]++;
     if (!box_hit(n, r)) continue;
     if (n->leaf_count) {
       for (uint32_t k = 0; k < n->leaf_count; k++) {
@@ -201,6 +205,10 @@ static hitinfo scene_intersect(octx *c, const ray_t *r) {
       if (n->child[0] != CRTB200_INVALID && sp < STACK_MAX) stack[sp++] = n->child[0];
       if (n->child[1] != CRTB200_INVALID && sp < STACK_MAX) stack[sp++] = n->child[1];
     }
+  }
+  {
+    const uint64_t spent = c->node_tests[0] + c->tri_tests[0] - before;
+    if (spent > c->max_query_tests) c->max_query_tests = spent;
   }
   if (!best.has) return best;
   const crtb200_material *mat = &s->materials[s->meshes[best.mesh].material];
@@ -229,11 +237,12 @@ static int scene_occluded(octx *c, const ray_t *r, float distance_to_light) {
   uint32_t stack[STACK_MAX];
   int sp = 0;
   c->rays[CRTB200_RAY_SHADOW]++;
+  c->shadow_query = 1;
   if (s->n_top_nodes == 0) return 0;
   stack[sp++] = 0;
   while (sp > 0) {
     const crtb200_kdnode *n = &s->top_nodes[stack[--sp]];
-    c->node_tests++;
+    c->node_tests[c->shadow_query]++;
     if (!box_hit(n, r)) continue;
     if (n->leaf_count) {
       for (uint32_t k = 0; k < n->leaf_count; k++) {
@@ -397,14 +406,14 @@ int crt_oracle_render(const crtb200_scene *s, const crtb200_camera *cam, const c
   crtb200_rect full = {0, 0, s->width, s->height};
   const crtb200_rect *rects = opt->n_rects ? opt->rects : &full;
   uint32_t n_rects = opt->n_rects ? opt->n_rects : 1;
-  uint64_t tot_rays[4] = {0, 0, 0, 0}, tot_nodes = 0, tot_tris = 0;
+  uint64_t tot_rays[4] = {0, 0, 0, 0}, tot_nodes[2] = {0, 0}, tot_tris[2] = {0, 0}, max_q = 0;
   if (threads <= 0) threads = 1;
   /* ---- RayTracer::renderRectangle  src/RayTracer.cpp:82-112, one work item per image row of a rectangle ---- */
   for (uint32_t ri = 0; ri < n_rects; ri++) {
     const crtb200_rect rc = rects[ri];
     uint32_t row_limit = rc.row + rc.height < s->height ? rc.row + rc.height : s->height;
     uint32_t col_limit = rc.col + rc.width < s->width ? rc.col + rc.width : s->width;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : tot_nodes, tot_tris, tot_rays[:4])
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : tot_nodes[:2], tot_tris[:2], tot_rays[:4]) reduction(max : max_q)
     for (uint32_t row = rc.row; row < row_limit; row++) {
       octx c;
       memset(&c, 0, sizeof(c));
@@ -433,9 +442,12 @@ int crt_oracle_render(const crtb200_scene *s, const crtb200_camera *cam, const c
         float *px = rgb + ((size_t)row * s->width + col) * 3;
         px[0] = col_out.x; px[1] = col_out.y; px[2] = col_out.z;
       }
-      tot_nodes += c.node_tests;
-      tot_tris += c.tri_tests;
+      for (int k = 0; k < 2; k++) {
+        tot_nodes[k] += c.node_tests[k];
+        tot_tris[k] += c.tri_tests[k];
+      }
       for (int k = 0; k < 4; k++) tot_rays[k] += c.rays[k];
+      if (c.max_query_tests > max_q) max_q = c.max_query_tests;
     }
   }
   if (stats) {
@@ -443,8 +455,11 @@ int crt_oracle_render(const crtb200_scene *s, const crtb200_camera *cam, const c
     stats->rays_shadow += tot_rays[CRTB200_RAY_SHADOW];
     stats->rays_reflection += tot_rays[CRTB200_RAY_REFLECTION];
     stats->rays_refraction += tot_rays[CRTB200_RAY_REFRACTION];
-    stats->node_tests += tot_nodes;
-    stats->triangle_tests += tot_tris;
+    stats->node_tests_closest += tot_nodes[0];
+    stats->triangle_tests_closest += tot_tris[0];
+    stats->node_tests_shadow += tot_nodes[1];
+    stats->triangle_tests_shadow += tot_tris[1];
+    if (max_q > stats->max_query_tests) stats->max_query_tests = max_q;
   }
   return 0;
 }

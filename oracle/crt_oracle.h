@@ -12,7 +12,9 @@ extern "C" {
 
 typedef struct crt_oracle_stats {
   uint64_t rays_primary, rays_shadow, rays_reflection, rays_refraction;
-  uint64_t node_tests, triangle_tests; /* under the reference's visit-all traversal, all ray types */
+  /* AABB / triangle tests under the reference's visit-all traversal, split by query kind */
+  uint64_t node_tests_closest, triangle_tests_closest, node_tests_shadow, triangle_tests_shadow;
+  uint64_t max_query_tests; /* most tests spent on one closest-hit query */
 } crt_oracle_stats;
 
 /* RayTracer::render (RayTracer.cpp:204-298) over options->rects; rgb = H*W*3 floats, pixels outside the rects

@@ -67,7 +67,8 @@ def test_render_matches_oracle_and_golden(name, gpu, loaded, ob, crt):
     for k in ("rays_primary", "rays_shadow", "rays_reflection", "rays_refraction"):
         assert st[k] == o_st[k], (k, st[k], o_st[k])
     assert [st["rays_primary"], st["rays_shadow"], st["rays_reflection"], st["rays_refraction"]] == list(g["rays"])
-    assert st["node_tests"] == o_st["node_tests"] and st["triangle_tests"] == o_st["triangle_tests"]
+    for k in ("node_tests_closest", "triangle_tests_closest", "node_tests_shadow", "triangle_tests_shadow"):
+        assert st[k] == o_st[k], (k, st[k], o_st[k])
 
 
 def test_uncovered_pixels_persist(gpu, loaded, crt):
