@@ -259,20 +259,15 @@ def ours_arm(args):
         cst = None
 
     if world > 1:
-        items = ctx.shard_items(world)
-        slab = torch.zeros((items, 3), dtype=torch.float32, device=dev)
-        slabs = torch.zeros((world, items, 3), dtype=torch.float32, device=dev) if rank == 0 else None
-        gather_list = list(slabs.unbind(0)) if rank == 0 else None
-        opt = crt.make_options(max_depth=depth, shard_index=rank, shard_count=world, traversal=args.traversal)
+        mg = importlib.import_module(PKG + ".multigpu")
+        sharded = mg.ShardedRenderer(crt, ctx, torch, dist, dev)
     else:
         opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, traversal=args.traversal)
 
     def step():
         if world > 1:
-            ctx.render_device(cam, opt, d_rgb=slab.data_ptr(), stream=stream)
-            dist.gather(slab, gather_list, dst=0)
-            if rank == 0:
-                ctx.assemble_shards(slabs.data_ptr(), world, d_rgb=frame.data_ptr(), d_rgb8=frame8.data_ptr(), stream=stream)
+            sharded.render(cam, max_depth=depth, traversal=args.traversal, frame=frame if rank == 0 else None,
+                           frame8=frame8 if rank == 0 else None)
         else:
             ctx.render_device(cam, opt, d_rgb=frame.data_ptr(), d_rgb8=frame8.data_ptr(), stream=stream)
 

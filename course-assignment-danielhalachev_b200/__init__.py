@@ -18,7 +18,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-CORE_PATH = os.path.join(CSRC, "libcrtb200.so")
+# CRT_CORE_LIB: load a differently-tuned build of the same CUDA core (tools/ tuning runs only)
+CORE_PATH = os.environ.get("CRT_CORE_LIB") or os.path.join(CSRC, "libcrtb200.so")
 FRONT_PATH = os.path.join(CSRC, "libcrtfront.so")
 
 INVALID = 0xFFFFFFFF

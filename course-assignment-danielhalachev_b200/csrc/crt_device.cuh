@@ -191,26 +191,28 @@ CRT_DI bool slab_test(const float4 lo, const float4 hi, const Ray &r) {
 }
 
 // Ray::intersectWithTriangle + Triangle::pointIsInTriangle                       Ray.cpp:9-31, Triangle.cpp:37-57
-// Returns true for a candidate; t may be NaN / inf exactly like the reference.  Evaluated without
-// early exits (lanes of a warp test different triangles; the exits would only diverge): each reject condition is the
-// reference's, on the same operands.
+// Returns true for a candidate; t may be NaN / inf exactly like the reference.  The early exits are
+// structured `if`s (immediate reconvergence), in the reference's order: cull, t < 0, edge 0, edge 1, edge 2.
 CRT_DI bool triangle_test(const float4 g0, const float4 g1, const float4 g2, const Ray &r, float &t_out, V3 &p_out) {
   const V3 n = mk(g0.w, g1.w, g2.w);
   const V3 v0 = mk(g0.x, g0.y, g0.z);
-  const V3 v1 = mk(g1.x, g1.y, g1.z);
-  const V3 v2 = mk(g2.x, g2.y, g2.z);
   const float nd = vdot(r.d, n);
   const float dist = -vdot(v0, n);
   const float t = fdiv(-fadd(vdot(n, r.o), dist), nd);
-  const V3 p = vadd(r.o, vscale(r.d, t));
-  const float e0 = vdot(n, vcross(vsub(v1, v0), vsub(p, v0)));
-  const float e1 = vdot(n, vcross(vsub(v2, v1), vsub(p, v1)));
-  const float e2 = vdot(n, vcross(vsub(v0, v2), vsub(p, v2)));
-  const bool culled = (r.flags & 8u) && nd >= 0.0f;
-  const bool miss = culled || (t < 0.0f) || (e0 < -CRT_FLT_EPSILON) || (e1 < -CRT_FLT_EPSILON) || (e2 < -CRT_FLT_EPSILON);
-  t_out = t;
-  p_out = p;
-  return !miss;
+  bool hit = !(((r.flags & 8u) && nd >= 0.0f) || (t < 0.0f));
+  if (hit) {
+    const V3 p = vadd(r.o, vscale(r.d, t));
+    const V3 v1 = mk(g1.x, g1.y, g1.z);
+    hit = !(vdot(n, vcross(vsub(v1, v0), vsub(p, v0))) < -CRT_FLT_EPSILON);
+    if (hit) {
+      const V3 v2 = mk(g2.x, g2.y, g2.z);
+      hit = !(vdot(n, vcross(vsub(v2, v1), vsub(p, v1))) < -CRT_FLT_EPSILON) &&
+            !(vdot(n, vcross(vsub(v0, v2), vsub(p, v2))) < -CRT_FLT_EPSILON);
+      t_out = t;
+      p_out = p;
+    }
+  }
+  return hit;
 }
 
 // ------------------------------------------------------------------------------------------------------------

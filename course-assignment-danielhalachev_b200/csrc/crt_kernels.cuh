@@ -91,7 +91,9 @@ CRT_DI bool item_pixel(const Frame &fr, const DScene &sc, uint32_t item, uint32_
 //   node phase   every lane steps its stack-free KD walk until it reaches a leaf or the end of the tree
 //   leaf phase   every lane tests the triangles of its pending leaf
 // ------------------------------------------------------------------------------------------------------------
-template <bool PRIMARY, bool COUNT, int REFILL>
+// MODE 0: while-while (node phase to the next leaf, then leaf phase).  MODE 1: merged loop -- per iteration a lane does
+// one AABB step or one triangle test, whichever it needs (better when lanes reach leaves at very different times).
+template <bool PRIMARY, bool COUNT, int REFILL, int MODE>
 __global__ void __launch_bounds__(256) k_closest(const DScene sc, const Frame fr, const Levels lv, const uint32_t level,
                                                 uint32_t *__restrict__ work_counter) {
   const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
@@ -141,27 +143,52 @@ __global__ void __launch_bounds__(256) k_closest(const DScene sc, const Frame fr
       if (exhausted) break;
       continue;
     }
-    // ---- node phase ----
-    int st = active ? TRAV_STEP : TRAV_DONE;
-    while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
-      if (st == TRAV_STEP) st = trav_step<false, COUNT>(tv, sc, ray, n_nodes);
-    }
-    if (active && st == TRAV_DONE) {
-      lv.hit_tri[node] = cl.best_tri;
-      lv.hit_t[node] = cl.best_t;
-      active = false;
-    }
-    // ---- leaf phase ----
-    while (__any_sync(CRT_FULL_MASK, tv.tref != tv.tend)) {
-      if (tv.tref != tv.tend) {
-        const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
-        const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
-        const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
-        const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
-        float t;
-        V3 p;
-        if (COUNT) n_tris++;
-        if (triangle_test(g0, g1, g2, ray, t, p)) closest_offer(cl, tri, t);
+    if (MODE == 0) {
+      // ---- node phase ----
+      int st = active ? TRAV_STEP : TRAV_DONE;
+      while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
+        if (st == TRAV_STEP) st = trav_step<false, COUNT>(tv, sc, ray, n_nodes);
+      }
+      if (active && st == TRAV_DONE) {
+        lv.hit_tri[node] = cl.best_tri;
+        lv.hit_t[node] = cl.best_t;
+        active = false;
+      }
+      // ---- leaf phase ----
+      while (__any_sync(CRT_FULL_MASK, tv.tref != tv.tend)) {
+        if (tv.tref != tv.tend) {
+          const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
+          const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
+          const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
+          const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+          float t;
+          V3 p;
+          if (COUNT) n_tris++;
+          if (triangle_test(g0, g1, g2, ray, t, p)) closest_offer(cl, tri, t);
+        }
+      }
+    } else {
+      // ---- merged loop: runs until REFILL lanes have retired (or all, once the queue is exhausted) ----
+      bool running = active;
+      const int quota = exhausted ? 0 : 32 - REFILL;  // keep going while more than `quota` lanes still run
+      while (__popc(__ballot_sync(CRT_FULL_MASK, running)) > quota) {
+        if (running) {
+          if (tv.tref != tv.tend) {
+            const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
+            const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
+            const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
+            const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+            float t;
+            V3 p;
+            if (COUNT) n_tris++;
+            if (triangle_test(g0, g1, g2, ray, t, p)) closest_offer(cl, tri, t);
+          } else if (trav_step<false, COUNT>(tv, sc, ray, n_nodes) == TRAV_DONE) {
+            lv.hit_tri[node] = cl.best_tri;
+            lv.hit_t[node] = cl.best_t;
+            active = false;
+            running = false;
+          }
+        }
       }
     }
   }
@@ -396,7 +423,7 @@ __global__ void __launch_bounds__(256) k_shade(const DScene sc, const Frame fr, 
 // ------------------------------------------------------------------------------------------------------------
 // COUNT: 0 = no counters; 1 = count under the reference's visit-all rule (early termination disabled, same result);
 // 2 = count the work this kernel really does with early termination.  Loop structure: see k_closest.
-template <int COUNT, int REFILL>
+template <int COUNT, int REFILL, int MODE>
 __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, const Frame fr, const Levels lv,
                                                           uint32_t *__restrict__ work_counter) {
   const uint32_t total = lv.counts[CRT_MAX_LEVELS];
@@ -457,34 +484,67 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, cons
         need_ray = false;
       }
     }
-    // ---- node phase ----
-    int st = (active && !need_ray) ? TRAV_STEP : TRAV_DONE;
-    while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
-      if (st == TRAV_STEP) st = trav_step<true, (COUNT != 0)>(tv, sc, ray, n_nodes);
-    }
-    if (active && !need_ray && st == TRAV_DONE) {
-      // shadow ray finished; unoccluded: finalColor += direct * albedo            RayTracer.cpp:318-327
-      if (!occluded) acc = vadd(acc, sscale(contrib, base));
-      light++;
-      need_ray = true;
-    }
-    // ---- leaf phase ----
-    while (__any_sync(CRT_FULL_MASK, tv.tref != tv.tend)) {
-      if (tv.tref != tv.tend) {
-        const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
-        const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
-        const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
-        const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
-        float t;
-        V3 p;
-        if (COUNT) n_tris++;
-        // (hitPoint - ray.origin).length() <= distanceToLight                   AccelerationStructure.cpp:73-74
-        if (triangle_test(g0, g1, g2, ray, t, p) && vlen(vsub(p, ray.o)) <= dist) {
-          occluded = true;
-          if (COUNT != 1) {  // early termination: the rest of the walk cannot change the answer
-            tv.tref = tv.tend = 0;
+    if (MODE == 0) {
+      // ---- node phase ----
+      int st = (active && !need_ray) ? TRAV_STEP : TRAV_DONE;
+      while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
+        if (st == TRAV_STEP) st = trav_step<true, (COUNT != 0)>(tv, sc, ray, n_nodes);
+      }
+      if (active && !need_ray && st == TRAV_DONE) {
+        // shadow ray finished; unoccluded: finalColor += direct * albedo            RayTracer.cpp:318-327
+        if (!occluded) acc = vadd(acc, sscale(contrib, base));
+        light++;
+        need_ray = true;
+      }
+      // ---- leaf phase ----
+      while (__any_sync(CRT_FULL_MASK, tv.tref != tv.tend)) {
+        if (tv.tref != tv.tend) {
+          const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
+          const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
+          const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
+          const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+          float t;
+          V3 p;
+          if (COUNT) n_tris++;
+          // (hitPoint - ray.origin).length() <= distanceToLight                   AccelerationStructure.cpp:73-74
+          if (triangle_test(g0, g1, g2, ray, t, p) && vlen(vsub(p, ray.o)) <= dist) {
+            occluded = true;
+            if (COUNT != 1) {  // early termination: the rest of the walk cannot change the answer
+              tv.tref = tv.tend = 0;
+              light++;
+              need_ray = true;
+            }
+          }
+        }
+      }
+    } else {
+      // ---- merged loop: until REFILL lanes need a new shadow ray ----
+      bool running = active && !need_ray;
+      const int quota = exhausted ? 0 : 32 - REFILL;
+      while (__popc(__ballot_sync(CRT_FULL_MASK, running)) > quota) {
+        if (running) {
+          if (tv.tref != tv.tend) {
+            const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
+            const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
+            const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
+            const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+            float t;
+            V3 p;
+            if (COUNT) n_tris++;
+            if (triangle_test(g0, g1, g2, ray, t, p) && vlen(vsub(p, ray.o)) <= dist) {
+              occluded = true;
+              if (COUNT != 1) {
+                tv.tref = tv.tend = 0;
+                light++;
+                need_ray = true;
+                running = false;
+              }
+            }
+          } else if (trav_step<true, (COUNT != 0)>(tv, sc, ray, n_nodes) == TRAV_DONE) {
+            if (!occluded) acc = vadd(acc, sscale(contrib, base));
             light++;
             need_ray = true;
+            running = false;
           }
         }
       }

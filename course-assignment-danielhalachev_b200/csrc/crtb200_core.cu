@@ -18,6 +18,9 @@ using namespace crtd;
 #ifndef CRT_REFILL
 #define CRT_REFILL 8  // refill a warp when at least this many lanes are idle
 #endif
+#ifndef CRT_LOOP_MODE
+#define CRT_LOOP_MODE 1  // 0 = while-while, 1 = merged loop (crt_kernels.cuh); measured: profiles/r1_tuning.md
+#endif
 
 static thread_local std::string g_error;
 static int fail(int code, const std::string &msg) {
@@ -143,9 +146,9 @@ int crtb200_create(int device, crtb200_ctx **out) {
   }
   for (auto &e : c->ev) cudaEventCreate(&e);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL>, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL, CRT_LOOP_MODE>, 256, 0);
   c->blocks_closest = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<0, CRT_REFILL>, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE>, 256, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
   *out = c;
   return CRTB200_OK;
@@ -514,9 +517,9 @@ static cudaEvent_t next_event(crtb200_ctx *c) {
 template <bool COUNT>
 static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, uint32_t level, uint32_t *work, cudaStream_t st) {
   if (primary)
-    k_closest<true, COUNT, CRT_REFILL><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
+    k_closest<true, COUNT, CRT_REFILL, CRT_LOOP_MODE><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
   else
-    k_closest<false, COUNT, CRT_REFILL><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
+    k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
 }
 
 // Enqueue one frame on `st`.  d_rgb / d_rgb8 / d_hits / d_slab are device pointers (any may be null).
@@ -580,11 +583,11 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       c->kev_kind.push_back(1);
     }
     if (o->count_work == 1)
-      k_shadow_accumulate<1, CRT_REFILL><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+      k_shadow_accumulate<1, CRT_REFILL, CRT_LOOP_MODE><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
     else if (o->count_work == 2)
-      k_shadow_accumulate<2, CRT_REFILL><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+      k_shadow_accumulate<2, CRT_REFILL, CRT_LOOP_MODE><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
     else
-      k_shadow_accumulate<0, CRT_REFILL><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+      k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
     if (timed) cudaEventRecord(next_event(c), st);
     launches++;
     for (uint32_t l = levels - 1; l-- > 0;) {

@@ -46,7 +46,12 @@ def nvcc_path() -> str:
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
-def build_core(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
+def build_core(force: bool = False, verbose: bool = False, extra: list[str] | None = None, out: str | None = None) -> str:
+    """extra: additional nvcc flags (e.g. -DCRT_LOOP_MODE=1 for a tuning variant written to `out`)."""
+    if out:
+        src = os.path.join(CSRC, "crtb200_core.cu")
+        _run([nvcc_path(), *NVCC_FLAGS, *(extra or []), "-o", out, src], verbose)
+        return out
     srcs = [os.path.join(CSRC, f) for f in ("crtb200_core.cu", "crt_kernels.cuh", "crt_device.cuh")]
     srcs.append(os.path.join(ROOT, "include", "crtb200.h"))
     if force or not _newer(CORE_SO, srcs):
