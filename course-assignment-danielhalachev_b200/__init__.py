@@ -160,6 +160,7 @@ def core() -> C.CDLL:
         lib.crtb200_generate_rays.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_void_p]
         lib.crtb200_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.crtb200_device_count.argtypes = [C.POINTER(C.c_int)]
+        lib.crtb200_debug_powf5.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _core = lib
     return _core
 
@@ -360,6 +361,12 @@ class Context:
         hits = np.zeros(n, HIT_DTYPE)
         _check_core(core().crtb200_trace_rays(self._h, rays.ctypes.data, n, ray_type, traversal, None, hits.ctypes.data, None))
         return hits
+
+    def debug_powf5(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros_like(x)
+        _check_core(core().crtb200_debug_powf5(self._h, x.ctypes.data, x.size, out.ctypes.data))
+        return out
 
     def close(self):
         if self._h:

@@ -13,6 +13,7 @@
 // persistent grids sized to 148 SMs x resident CTAs, warp-aggregated queue compaction (ballot / shuffle).
 #pragma once
 #include "crt_device.cuh"
+#include "crt_powf5.h"
 
 namespace crtd {
 
@@ -241,16 +242,6 @@ CRT_DI V3 texture_color(const DScene &sc, const DTexture &t, const uint4 sh, flo
   return mk(px[0], px[1], px[2]);
 }
 
-// (1 - x)^5 as the reference's std::powf(1.0f - cosineAlpha, 5) (RayTracer.cpp:407): glibc's powf evaluates in
-// binary64 and rounds once; x^5 by binary64 multiplies rounded once agrees except in ~0.07 % of inputs (1 ulp),
-// SURVEY.md section 7.  See DESIGN.md section 3.5.
-CRT_DI float pow5_like_glibc(float x) {
-  const double d = (double)x;
-  const double d2 = __dmul_rn(d, d);
-  const double d4 = __dmul_rn(d2, d2);
-  return __double2float_rn(__dmul_rn(d4, d));
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // K4/K5: shade + spawn for one level.  Replaces the body of RayTracer::shootRay after trace() (RayTracer.cpp:430-450),
 // the hit post-processing of KDTree<ObjectKDTreeSubTree>::intersect (KDTree.cpp:167-190), Triangle::
@@ -349,7 +340,7 @@ __global__ void __launch_bounds__(256) k_shade(const DScene sc, const Frame fr, 
         if (sin_b < 1.0f) {
           const float r = fdiv(fsub(eta1, eta2), fadd(eta1, eta2));
           const float r0 = fmul(r, r);  // powf(r, 2) == r*r bit for bit
-          fresnel = fadd(r0, fmul(fsub(1.0f, r0), pow5_like_glibc(fsub(1.0f, cos_a))));
+          fresnel = fadd(r0, fmul(fsub(1.0f, r0), crt_powf5(fsub(1.0f, cos_a))));
           const float cos_b = fsqrt(stdmax(0.0f, fsub(1.0f, fmul(sin_b, sin_b))));
           const V3 dir = vsub(sscale(eta, vadd(d, sscale(cos_a, n))), sscale(cos_b, n));
           c1o = vsub(P, vscale(n, fr.refraction_bias));
@@ -679,6 +670,11 @@ __global__ void __launch_bounds__(256) k_assemble(const DScene sc, Frame fr, con
       rgb8[3 * pix + 2] = quantize(s[2]);
     }
   }
+}
+
+// Test hook: crt_powf5 on the device, for the bit-equality test against the host libm's powf(x, 5).
+__global__ void __launch_bounds__(256) k_powf5(const float *__restrict__ x, uint32_t n, float *__restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = crt_powf5(x[i]);
 }
 
 // K1 standalone: RayTracer::getRay + shootRay's re-normalisation, for the ray parity test.

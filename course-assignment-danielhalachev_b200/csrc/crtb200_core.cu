@@ -768,6 +768,26 @@ int crtb200_generate_rays(crtb200_ctx *c, const crtb200_camera *cam, float *rays
   return CRTB200_OK;
 }
 
+int crtb200_debug_powf5(crtb200_ctx *c, const float *x, uint32_t n, float *out) {
+  if (!c || !x || !out) return fail(CRTB200_ERR_ARG, "null argument");
+  if (n == 0) return CRTB200_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  DevBuf<float> dx, dy;
+  cudaError_t e = dx.ensure(n);
+  if (e == cudaSuccess) e = dy.ensure(n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    k_powf5<<<c->sm_count * 8, 256, 0, c->stream>>>(dx.p, n, dy.p);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dy.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  dx.release();
+  dy.release();
+  CUDA_TRY(e);
+  return CRTB200_OK;
+}
+
 int crtb200_trace_rays(crtb200_ctx *c, const float *rays, uint32_t n, uint32_t ray_type, uint32_t traversal,
                        const float *max_distance, crtb200_hit *hits_out, uint8_t *occluded_out) {
   if (!c || !rays) return fail(CRTB200_ERR_ARG, "null argument");

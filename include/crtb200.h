@@ -238,6 +238,10 @@ int crtb200_generate_rays(crtb200_ctx *ctx, const crtb200_camera *camera, float 
 int crtb200_trace_rays(crtb200_ctx *ctx, const float *rays, uint32_t n, uint32_t ray_type, uint32_t traversal,
                        const float *max_distance, crtb200_hit *hits_out, uint8_t *occluded_out);
 
+/* Test hook: evaluates the device's (1 - cos)^5 routine (csrc/crt_powf5.h), the stand-in for glibc's
+ * std::powf(x, 5) of RayTracer.cpp:407, on n host floats -- so the parity suite can check it bit for bit against libm. */
+int crtb200_debug_powf5(crtb200_ctx *ctx, const float *x, uint32_t n, float *out);
+
 #ifdef __cplusplus
 }
 #endif

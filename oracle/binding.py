@@ -105,7 +105,8 @@ def have_reference(textured: bool = False) -> bool:
 
 
 def run_reference(scene_file: str, folder: str, out_prefix: str, textured: bool = False, depth: int = 5,
-                  hits: bool = True, ppm: bool = True, repeat: int = 1, camera=None, timeout: float = 3600.0) -> dict:
+                  hits: bool = True, ppm: bool = True, repeat: int = 1, camera=None, timeout: float = 3600.0,
+                  dump_tree: str | None = None) -> dict:
     """Runs oracle/_ref/crt_ref[_tex]; returns its JSON stats plus loaded arrays ('rgb', 'hits', 'ppm_path')."""
     exe = REF_BIN_TEX if textured else REF_BIN
     cmd = [exe, scene_file, folder, out_prefix, "--depth", str(depth), "--repeat", str(repeat)]
@@ -113,6 +114,8 @@ def run_reference(scene_file: str, folder: str, out_prefix: str, textured: bool 
         cmd.append("--no-hits")
     if not ppm:
         cmd.append("--no-ppm")
+    if dump_tree:
+        cmd += ["--dump-tree", dump_tree]
     if camera is not None:
         cmd += ["--cam"] + ["%.9g" % float(v) for v in list(camera.position) + list(camera.rotation)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
@@ -127,6 +130,36 @@ def run_reference(scene_file: str, folder: str, out_prefix: str, textured: bool 
             out["hits"] = np.fromfile(out_prefix + ".hits", dtype=HIT_DTYPE).reshape(h, w)
         out["ppm_path"] = out_prefix + ".ppm"
     return out
+
+
+def read_reference_trees(path: str):
+    """Parses `crt_ref --dump-tree`: list of per-mesh trees + the top-level tree; each a list of
+    (box[6], child0, child1, indexes) in the reference's node numbering."""
+    data = np.fromfile(path, dtype=np.uint8).tobytes()
+    off = 0
+
+    def u32():
+        nonlocal off
+        v = int(np.frombuffer(data, np.uint32, 1, off)[0])
+        off += 4
+        return v
+
+    def tree():
+        nonlocal off
+        nodes = []
+        for _ in range(u32()):
+            box = np.frombuffer(data, np.float32, 6, off).copy()
+            off += 24
+            c0, c1, n = u32(), u32(), u32()
+            idx = np.frombuffer(data, np.uint32, n, off).copy()
+            off += 4 * n
+            nodes.append((box, c0, c1, idx))
+        return nodes
+
+    n_mesh = u32()
+    meshes = [tree() for _ in range(n_mesh)]
+    top = tree()
+    return meshes, top
 
 
 def read_ppm_p3(path: str) -> np.ndarray:

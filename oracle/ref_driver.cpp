@@ -72,6 +72,7 @@ int main(int argc, char **argv) {
   unsigned depth = 5;
   int mode = BVHBucketsThreadPool;
   bool dumpHits = true, writePpm = true, haveCam = false;
+  std::string treePath;
   int repeat = 1;
   float cam[12];
   for (int i = 4; i < argc; i++) {
@@ -80,6 +81,7 @@ int main(int argc, char **argv) {
     else if (!std::strcmp(argv[i], "--no-hits")) dumpHits = false;
     else if (!std::strcmp(argv[i], "--no-ppm")) writePpm = false;
     else if (!std::strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = std::atoi(argv[++i]);
+    else if (!std::strcmp(argv[i], "--dump-tree") && i + 1 < argc) treePath = argv[++i];
     else if (!std::strcmp(argv[i], "--cam") && i + 12 < argc) {
       for (int k = 0; k < 12; k++) cam[k] = std::strtof(argv[++i], nullptr);
       haveCam = true;
@@ -97,6 +99,30 @@ int main(int argc, char **argv) {
     tracer.setCamera().setPosition() = Vector(cam[0], cam[1], cam[2]);
     tracer.setCamera().setRotationMatrix() =
         Matrix<3>(std::vector<float>{cam[3], cam[4], cam[5], cam[6], cam[7], cam[8], cam[9], cam[10], cam[11]});
+  }
+  if (!treePath.empty()) {
+    // The reference's own KD trees (KDTree::nodes is protected, KDTree.h:29), node for node, for the build-parity test:
+    // per tree: u32 n_nodes, then per node {6 x f32 box, u32 child0, u32 child1, u32 n_indexes, n_indexes x u32}.
+    std::ofstream f(treePath, std::ios::binary);
+    auto dump = [&f](const auto &nodes) {
+      unsigned n = static_cast<unsigned>(nodes.size());
+      f.write(reinterpret_cast<const char *>(&n), 4);
+      for (const auto &node : nodes) {
+        float box[6] = {node.box.minPoint[0], node.box.minPoint[1], node.box.minPoint[2],
+                        node.box.maxPoint[0], node.box.maxPoint[1], node.box.maxPoint[2]};
+        f.write(reinterpret_cast<const char *>(box), sizeof(box));
+        unsigned c[3] = {node.children[0], node.children[1], static_cast<unsigned>(node.indexes.size())};
+        f.write(reinterpret_cast<const char *>(c), sizeof(c));
+        for (size_t idx : node.indexes) {
+          unsigned v = static_cast<unsigned>(idx);
+          f.write(reinterpret_cast<const char *>(&v), 4);
+        }
+      }
+    };
+    unsigned nMesh = static_cast<unsigned>(tracer.accelerationStructure.container->size());
+    f.write(reinterpret_cast<const char *>(&nMesh), 4);
+    for (const auto &sub : *tracer.accelerationStructure.container) dump(sub.tree.nodes);
+    dump(tracer.accelerationStructure.nodes);
   }
   const unsigned W = tracer.scene.sceneSettings.image.width, H = tracer.scene.sceneSettings.image.height;
   RenderOptions options{static_cast<RenderOptimization>(mode), depth, false};
