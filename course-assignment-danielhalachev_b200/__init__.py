@@ -155,6 +155,7 @@ def core() -> C.CDLL:
         lib.crtb200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         lib.crtb200_destroy.argtypes = [C.c_void_p]
         lib.crtb200_set_queue_budget.argtypes = [C.c_void_p, C.c_uint64]
+        lib.crtb200_set_concurrency.argtypes = [C.c_void_p, C.c_uint32]
         lib.crtb200_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         lib.crtb200_shard_items.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
         lib.crtb200_generate_rays.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_void_p]
@@ -300,6 +301,9 @@ class Context:
 
     def set_queue_budget(self, nbytes: int) -> None:
         _check_core(core().crtb200_set_queue_budget(self._h, nbytes))
+
+    def set_concurrency(self, chunks_in_flight: int) -> None:
+        _check_core(core().crtb200_set_concurrency(self._h, chunks_in_flight))
 
     def render(self, camera: Camera, options: Options, want_rgb: bool = True, want_rgb8: bool = False,
                want_hits: bool = False, rgb_out: Optional[np.ndarray] = None, rgb8_out: Optional[np.ndarray] = None):

@@ -67,6 +67,7 @@ struct DScene {
   uint32_t top_begin, top_end;
   uint32_t width, height;
   float bg[3];
+  uint32_t dedup_meshes;  // 1 when n_meshes <= 64: per-ray visited-mesh bitmask is usable
 };
 
 struct DCamera {
@@ -166,8 +167,9 @@ CRT_DI void primary_ray(const DCamera &cam, uint32_t W, uint32_t H, uint32_t row
 // (no t1 >= 0 test: boxes behind the origin pass; NaN bounds never reject -- both as in the reference).
 // Branch-free: the reference's early returns only skip work; every reject condition is evaluated on the same running
 // (t0, t1) it would have seen, so OR-ing them is exact.  An axis with |d| < FLT_EPSILON leaves (t0, t1) untouched.
-CRT_DI bool slab_test(const float4 lo, const float4 hi, const Ray &r) {
-  float t0 = -CRT_FLT_MAX, t1 = CRT_FLT_MAX;
+CRT_DI bool slab_test(const float4 lo, const float4 hi, const Ray &r, float &t0, float &t1) {
+  t0 = -CRT_FLT_MAX;
+  t1 = CRT_FLT_MAX;
   bool reject = false;
 #define CRT_SLAB_AXIS(bit, O, I, MN, MX)                                  \
   {                                                                       \
@@ -225,20 +227,29 @@ CRT_DI bool triangle_test(const float4 g0, const float4 g1, const float4 g2, con
 // ------------------------------------------------------------------------------------------------------------
 struct Trav {
   uint32_t top, mref, mend, cur, cend, tref, tend;
+  unsigned long long seen;  // meshes already traversed for this ray (scenes with <= 64 meshes)
 };
 CRT_DI void trav_begin(Trav &s, const DScene &sc) {
   s.top = sc.top_begin;
   s.mref = s.mend = 0;
   s.cur = s.cend = 0;
   s.tref = s.tend = 0;
+  s.seen = 0ull;
 }
 
 // One traversal micro-step.  Returns 0 = keep stepping, 1 = a triangle list is pending (tref..tend), 2 = traversal
 // complete.  Top-level and mesh-level AABB tests share one code path so lanes at different levels do not diverge.
-// SKIP_REFRACTIVE: shadow rays ignore refractive meshes (AccelerationStructure.cpp:67-71).
+//   SKIP_REFRACTIVE  shadow rays ignore refractive meshes (AccelerationStructure.cpp:67-71).
+//   DEDUP            a mesh listed in several top-level leaves is traversed once per ray instead of once per listing.
+//                    Exact: a repeated traversal (KDTree.cpp:131-155 does repeat it) yields the same candidates again,
+//                    which can neither replace the kept one (strict <) nor be the first candidate.  Off when counting
+//                    the reference's visit-all work.
+//   CULL             traversal mode 1: additionally skip subtrees whose box lies wholly behind the ray origin (t1 < 0)
+//                    or wholly beyond t_limit (the best hit so far / the light).  NOT the reference's candidate set:
+//                    see DESIGN.md section 3.6 for what can differ and the measured mismatch counts.
 enum { TRAV_STEP = 0, TRAV_LEAF = 1, TRAV_DONE = 2 };
-template <bool SKIP_REFRACTIVE, bool COUNT>
-CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests) {
+template <bool SKIP_REFRACTIVE, bool COUNT, bool DEDUP, bool CULL>
+CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float t_limit) {
   const bool in_mesh = s.cur != s.cend;
   if (in_mesh || (s.mref == s.mend && s.top != sc.top_end)) {
     const uint32_t idx = in_mesh ? s.cur : s.top;
@@ -247,7 +258,9 @@ CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tes
     const uint32_t a = __float_as_uint(lo.w);
     const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
     if (COUNT) node_tests++;
-    const bool pass = slab_test(lo, hi, r);
+    float t0, t1;
+    bool pass = slab_test(lo, hi, r, t0, t1);
+    if (CULL) pass = pass && !(t1 < 0.0f) && !(t0 > t_limit);
     const uint32_t next = (pass || leaf) ? idx + 1 : a;
     const uint32_t first = __float_as_uint(hi.w), last = first + (a & ~CRT_LEAF_FLAG);
     if (in_mesh) {
@@ -269,7 +282,13 @@ CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tes
   if (s.mref != s.mend) {
     const uint32_t m = __ldg(&sc.top_refs[s.mref++]);
     const DMesh me = sc.meshes[m];
-    if (!(SKIP_REFRACTIVE && sc.materials[me.material].type == 3u)) {
+    bool skip = SKIP_REFRACTIVE && sc.materials[me.material].type == 3u;
+    if (DEDUP && sc.dedup_meshes) {
+      const unsigned long long bit = 1ull << (m & 63u);
+      skip = skip || (s.seen & bit) != 0ull;
+      s.seen |= bit;
+    }
+    if (!skip) {
       s.cur = me.node_begin;
       s.cend = me.node_end;
     }

@@ -94,7 +94,7 @@ CRT_DI bool item_pixel(const Frame &fr, const DScene &sc, uint32_t item, uint32_
 // ------------------------------------------------------------------------------------------------------------
 // MODE 0: while-while (node phase to the next leaf, then leaf phase).  MODE 1: merged loop -- per iteration a lane does
 // one AABB step or one triangle test, whichever it needs (better when lanes reach leaves at very different times).
-template <bool PRIMARY, bool COUNT, int REFILL, int MODE>
+template <bool PRIMARY, bool COUNT, int REFILL, int MODE, bool CULL>
 __global__ void __launch_bounds__(256) k_closest(const DScene sc, const Frame fr, const Levels lv, const uint32_t level,
                                                 uint32_t *__restrict__ work_counter) {
   const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) k_closest(const DScene sc, const Frame fr
       // ---- node phase ----
       int st = active ? TRAV_STEP : TRAV_DONE;
       while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
-        if (st == TRAV_STEP) st = trav_step<false, COUNT>(tv, sc, ray, n_nodes);
+        if (st == TRAV_STEP) st = trav_step<false, COUNT, !COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t);
       }
       if (active && st == TRAV_DONE) {
         lv.hit_tri[node] = cl.best_tri;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) k_closest(const DScene sc, const Frame fr
             V3 p;
             if (COUNT) n_tris++;
             if (triangle_test(g0, g1, g2, ray, t, p)) closest_offer(cl, tri, t);
-          } else if (trav_step<false, COUNT>(tv, sc, ray, n_nodes) == TRAV_DONE) {
+          } else if (trav_step<false, COUNT, !COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t) == TRAV_DONE) {
             lv.hit_tri[node] = cl.best_tri;
             lv.hit_t[node] = cl.best_t;
             active = false;
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256) k_shade(const DScene sc, const Frame fr, 
 // ------------------------------------------------------------------------------------------------------------
 // COUNT: 0 = no counters; 1 = count under the reference's visit-all rule (early termination disabled, same result);
 // 2 = count the work this kernel really does with early termination.  Loop structure: see k_closest.
-template <int COUNT, int REFILL, int MODE>
+template <int COUNT, int REFILL, int MODE, bool CULL>
 __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, const Frame fr, const Levels lv,
                                                           uint32_t *__restrict__ work_counter) {
   const uint32_t total = lv.counts[CRT_MAX_LEVELS];
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, cons
   bool active = false, exhausted = false, need_ray = false, occluded = false;
   uint32_t node = 0, light = 0, n_nodes = 0, n_tris = 0;
   V3 P = mk(0, 0, 0), N = P, base = P, acc = P;
-  float contrib = 0.0f, dist = 0.0f;
+  float contrib = 0.0f, dist = 0.0f, t_limit = 0.0f;
   Ray ray;
   Trav tv;
   ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, cons
         ray.d = ld;
         ray_prepare(ray, false);
         trav_begin(tv, sc);
+        t_limit = fadd(fmul(dist, 1.0001f), 1e-4f);  // CULL only: nothing beyond the light can satisfy |P - o| <= dist
         occluded = false;
         need_ray = false;
       }
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, cons
       // ---- node phase ----
       int st = (active && !need_ray) ? TRAV_STEP : TRAV_DONE;
       while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
-        if (st == TRAV_STEP) st = trav_step<true, (COUNT != 0)>(tv, sc, ray, n_nodes);
+        if (st == TRAV_STEP) st = trav_step<true, (COUNT != 0), (COUNT != 1), CULL>(tv, sc, ray, n_nodes, t_limit);
       }
       if (active && !need_ray && st == TRAV_DONE) {
         // shadow ray finished; unoccluded: finalColor += direct * albedo            RayTracer.cpp:318-327
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, cons
                 running = false;
               }
             }
-          } else if (trav_step<true, (COUNT != 0)>(tv, sc, ray, n_nodes) == TRAV_DONE) {
+          } else if (trav_step<true, (COUNT != 0), (COUNT != 1), CULL>(tv, sc, ray, n_nodes, t_limit) == TRAV_DONE) {
             if (!occluded) acc = vadd(acc, sscale(contrib, base));
             light++;
             need_ray = true;
@@ -605,6 +606,9 @@ struct HitRec {
 __global__ void __launch_bounds__(256) k_store(const DScene sc, const Frame fr, const Levels lv, float *__restrict__ rgb,
                                               uint8_t *__restrict__ rgb8, HitRec *__restrict__ hits,
                                               float *__restrict__ slab) {
+  // shadow rays traced for this chunk = diffuse hits x lights (one per pair even when cos = 0, RayTracer.cpp:314-317)
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&lv.stats[1], (unsigned long long)lv.counts[CRT_MAX_LEVELS] * sc.n_lights);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fr.n_items0; i += gridDim.x * blockDim.x) {
     uint32_t row, col;
     const bool valid = item_pixel(fr, sc, fr.item_begin + i, row, col);
@@ -710,7 +714,7 @@ __global__ void __launch_bounds__(256) k_query(const DScene sc, const float *__r
       bool occ = false;
       for (;;) {
         int st = TRAV_STEP;
-        while (st == TRAV_STEP) st = trav_step<true, false>(tv, sc, ray, dummy);
+        while (st == TRAV_STEP) st = trav_step<true, false, true, false>(tv, sc, ray, dummy, 0.0f);
         if (st == TRAV_DONE || occ) break;
         while (tv.tref != tv.tend) {
           const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
@@ -728,7 +732,7 @@ __global__ void __launch_bounds__(256) k_query(const DScene sc, const float *__r
       closest_begin(cl);
       for (;;) {
         int st = TRAV_STEP;
-        while (st == TRAV_STEP) st = trav_step<false, false>(tv, sc, ray, dummy);
+        while (st == TRAV_STEP) st = trav_step<false, false, true, false>(tv, sc, ray, dummy, 0.0f);
         if (st == TRAV_DONE) break;
         while (tv.tref != tv.tend) {
           const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);

@@ -94,15 +94,29 @@ struct crtb200_ctx {
   std::vector<crtb200_rect> mask_rects;
   bool mask_valid = false, mask_needed = false;
 
-  // queues
-  Levels lv{};
-  DevBuf<float4> ray_o, ray_d, color, dq;
-  DevBuf<uint32_t> hit_tri, counts, work;
-  DevBuf<float> hit_t;
-  DevBuf<uint4> comb;
+  // queues: `concurrency` independent buffer sets, each with its own stream.  Consecutive chunks of a frame go to the
+  // sets round-robin, so the latency-bound tails of one chunk's persistent kernels (and the small secondary-level
+  // launches of reflective / refractive scenes) are filled by the other chunks' kernels.
+  struct QueueSet {
+    Levels lv{};
+    DevBuf<float4> ray_o, ray_d, color, dq;
+    DevBuf<uint32_t> hit_tri, counts, work;
+    DevBuf<float> hit_t;
+    DevBuf<uint4> comb;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void release() {
+      ray_o.release(); ray_d.release(); color.release(); dq.release(); hit_tri.release(); counts.release();
+      work.release(); hit_t.release(); comb.release();
+    }
+  };
+  std::vector<QueueSet> sets;
+  uint32_t concurrency = 4;
+  cudaEvent_t fork_ev = nullptr;
   DevBuf<unsigned long long> stats_dev;
   uint32_t cap_items = 0;
   uint32_t cap_depth = 0xFFFFFFFFu;
+  uint32_t cap_sets = 0;
 
   int blocks_closest = 0, blocks_shadow = 0;
   crtb200_stats last{};
@@ -146,9 +160,9 @@ int crtb200_create(int device, crtb200_ctx **out) {
   }
   for (auto &e : c->ev) cudaEventCreate(&e);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL, CRT_LOOP_MODE>, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL, CRT_LOOP_MODE, false>, 256, 0);
   c->blocks_closest = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE>, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, false>, 256, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
   *out = c;
   return CRTB200_OK;
@@ -161,14 +175,27 @@ int crtb200_destroy(crtb200_ctx *c) {
   c->nodes.release(); c->tri_geom.release(); c->vtx_normal.release(); c->leaf_refs.release(); c->top_refs.release();
   c->tri_shade.release(); c->vtx_uv.release(); c->meshes.release(); c->materials.release(); c->textures.release();
   c->texels.release(); c->lights.release(); c->frame.release(); c->frame8.release(); c->hits.release();
-  c->mask.release(); c->ray_o.release(); c->ray_d.release(); c->color.release(); c->dq.release();
-  c->hit_tri.release(); c->counts.release(); c->work.release(); c->hit_t.release(); c->comb.release();
+  c->mask.release();
+  for (auto &q : c->sets) {
+    q.release();
+    if (q.stream) cudaStreamDestroy(q.stream);
+    if (q.done) cudaEventDestroy(q.done);
+  }
+  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
   c->stats_dev.release();
   for (auto &e : c->ev)
     if (e) cudaEventDestroy(e);
   for (auto &e : c->kev) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+  return CRTB200_OK;
+}
+
+int crtb200_set_concurrency(crtb200_ctx *c, uint32_t chunks_in_flight) {
+  if (!c) return fail(CRTB200_ERR_ARG, "ctx is null");
+  if (chunks_in_flight < 1 || chunks_in_flight > 16) return fail(CRTB200_ERR_ARG, "concurrency must be 1..16");
+  c->concurrency = chunks_in_flight;
+  c->cap_items = 0;
   return CRTB200_OK;
 }
 
@@ -400,14 +427,13 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   d.width = s->width;
   d.height = s->height;
   for (int k = 0; k < 3; k++) d.bg[k] = s->background[k];
+  d.dedup_meshes = s->n_meshes <= 64 ? 1u : 0u;
 
   const size_t px = (size_t)s->width * s->height;
   CUDA_TRY(c->frame.ensure(px * 3));
   CUDA_TRY(cudaMemset(c->frame.p, 0, px * 3 * sizeof(float)));  // colorBuffer starts at (0,0,0), RayTracer.cpp:47-50
   CUDA_TRY(c->frame8.ensure(px * 3));
   CUDA_TRY(cudaMemset(c->frame8.p, 0, px * 3));
-  CUDA_TRY(c->counts.ensure(CRT_MAX_LEVELS + 1));
-  CUDA_TRY(c->work.ensure(CRT_MAX_LEVELS + 2));
   CUDA_TRY(c->stats_dev.ensure(8));
   c->mask_valid = false;
   c->cap_items = 0;
@@ -443,37 +469,50 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth)
   uint64_t sum = 0;
   for (uint32_t l = 0; l <= max_depth; l++) sum += per_level[l];
   const uint64_t bytes_per_node = 32 + 8 + 16 + 16 + 48;  // ray + hit + colour + comb + diffuse item
-  uint64_t items = c->queue_budget / (bytes_per_node * sum);
+  // sets used: up to `concurrency`, but never chunks smaller than 64 Ki items (launch overhead would dominate)
+  uint32_t n_sets = std::max<uint32_t>(1, std::min<uint32_t>(c->concurrency, (shard_items + 65535u) / 65536u));
+  uint64_t items = c->queue_budget / (bytes_per_node * sum * n_sets);
   items &= ~31ull;
   if (items < 32 * 64) return fail(CRTB200_ERR_MEMORY, "queue budget too small for one chunk at this ray depth");
-  items = std::min<uint64_t>(items, (shard_items + 31u) & ~31u);
+  const uint64_t even = (((uint64_t)shard_items + n_sets - 1) / n_sets + 31u) & ~31ull;  // one chunk per set when it fits
+  items = std::min<uint64_t>(items, even);
   if (items * sum >= 0x7FFFFFFFull) items = ((0x7FFFFFFFull / sum) - 32) & ~31ull;
-  if (c->cap_items == items && c->cap_depth == max_depth) return CRTB200_OK;
-  uint64_t total = 0;
-  for (uint32_t l = 0; l <= max_depth; l++) {
-    c->lv.offset[l] = (uint32_t)total;
-    total += per_level[l] * items;
+  if (c->cap_items == items && c->cap_depth == max_depth && c->cap_sets == n_sets) return CRTB200_OK;
+  if (c->sets.size() < n_sets) c->sets.resize(n_sets);
+  if (!c->fork_ev) CUDA_TRY(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+  for (uint32_t k = 0; k < n_sets; k++) {
+    crtb200_ctx::QueueSet &q = c->sets[k];
+    if (!q.stream) CUDA_TRY(cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking));
+    if (!q.done) CUDA_TRY(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
+    uint64_t total = 0;
+    for (uint32_t l = 0; l <= max_depth; l++) {
+      q.lv.offset[l] = (uint32_t)total;
+      total += per_level[l] * items;
+    }
+    for (uint32_t l = max_depth + 1; l <= CRT_MAX_LEVELS; l++) q.lv.offset[l] = (uint32_t)total;
+    const uint64_t secondary = total - items;
+    CUDA_TRY(q.ray_o.ensure(std::max<uint64_t>(secondary, 1)));
+    CUDA_TRY(q.ray_d.ensure(std::max<uint64_t>(secondary, 1)));
+    CUDA_TRY(q.hit_tri.ensure(total));
+    CUDA_TRY(q.hit_t.ensure(total));
+    CUDA_TRY(q.color.ensure(total));
+    CUDA_TRY(q.comb.ensure(total));
+    CUDA_TRY(q.dq.ensure(3 * total));
+    CUDA_TRY(q.counts.ensure(CRT_MAX_LEVELS + 1));
+    CUDA_TRY(q.work.ensure(CRT_MAX_LEVELS + 2));
+    q.lv.ray_o = q.ray_o.p;
+    q.lv.ray_d = q.ray_d.p;
+    q.lv.hit_tri = q.hit_tri.p;
+    q.lv.hit_t = q.hit_t.p;
+    q.lv.color = q.color.p;
+    q.lv.comb = q.comb.p;
+    q.lv.dq = q.dq.p;
+    q.lv.counts = q.counts.p;
+    q.lv.stats = c->stats_dev.p;
   }
-  for (uint32_t l = max_depth + 1; l <= CRT_MAX_LEVELS; l++) c->lv.offset[l] = (uint32_t)total;
-  const uint64_t secondary = total - items;
-  CUDA_TRY(c->ray_o.ensure(std::max<uint64_t>(secondary, 1)));
-  CUDA_TRY(c->ray_d.ensure(std::max<uint64_t>(secondary, 1)));
-  CUDA_TRY(c->hit_tri.ensure(total));
-  CUDA_TRY(c->hit_t.ensure(total));
-  CUDA_TRY(c->color.ensure(total));
-  CUDA_TRY(c->comb.ensure(total));
-  CUDA_TRY(c->dq.ensure(3 * total));
-  c->lv.ray_o = c->ray_o.p;
-  c->lv.ray_d = c->ray_d.p;
-  c->lv.hit_tri = c->hit_tri.p;
-  c->lv.hit_t = c->hit_t.p;
-  c->lv.color = c->color.p;
-  c->lv.comb = c->comb.p;
-  c->lv.dq = c->dq.p;
-  c->lv.counts = c->counts.p;
-  c->lv.stats = c->stats_dev.p;
   c->cap_items = (uint32_t)items;
   c->cap_depth = max_depth;
+  c->cap_sets = n_sets;
   return CRTB200_OK;
 }
 
@@ -514,12 +553,13 @@ static cudaEvent_t next_event(crtb200_ctx *c) {
   return c->kev[c->kev_used++];
 }
 
-template <bool COUNT>
-static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, uint32_t level, uint32_t *work, cudaStream_t st) {
+template <bool COUNT, bool CULL>
+static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, uint32_t *work,
+                           cudaStream_t st) {
   if (primary)
-    k_closest<true, COUNT, CRT_REFILL, CRT_LOOP_MODE><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
+    k_closest<true, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, lv, level, work);
   else
-    k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, c->lv, level, work);
+    k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, lv, level, work);
 }
 
 // Enqueue one frame on `st`.  d_rgb / d_rgb8 / d_hits / d_slab are device pointers (any may be null).
@@ -530,6 +570,9 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   if (o->n_rects && !o->rects) return fail(CRTB200_ERR_ARG, "n_rects > 0 but rects is null");
   if (o->traversal > 1) return fail(CRTB200_ERR_ARG, "unknown traversal mode");
   if (o->count_work > 2) return fail(CRTB200_ERR_ARG, "unknown count_work mode");
+  if (o->traversal == 1 && o->count_work == 1)
+    return fail(CRTB200_ERR_ARG, "count_work = 1 counts the reference's visit-all work and needs traversal = 0");
+  const bool cull = o->traversal == 1;
   const uint32_t shard_count = o->shard_count ? o->shard_count : 1;
   if (o->shard_index >= shard_count) return fail(CRTB200_ERR_ARG, "shard_index >= shard_count");
   int rc = plan_mask(c, o);
@@ -559,53 +602,64 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   c->kev_used = 0;
   c->kev_kind.clear();
   if (timed) CUDA_TRY(cudaEventRecord(c->ev[0], st));
-  uint32_t launches = 0;
-  for (uint32_t begin = 0; begin < shard_items; begin += c->cap_items) {
+  // fork: every set's stream waits for the caller's stream, chunks go round-robin, the caller's stream joins at the end.
+  // Per-kernel event pairs are only recorded without concurrency (overlapping kernels would inflate each other).
+  const uint32_t n_sets = c->cap_sets;
+  const bool per_kernel = timed && n_sets == 1;
+  CUDA_TRY(cudaEventRecord(c->fork_ev, st));
+  for (uint32_t k = 0; k < n_sets; k++) CUDA_TRY(cudaStreamWaitEvent(c->sets[k].stream, c->fork_ev, 0));
+  uint32_t launches = 0, chunk = 0;
+  for (uint32_t begin = 0; begin < shard_items; begin += c->cap_items, chunk++) {
+    crtb200_ctx::QueueSet &q = c->sets[chunk % n_sets];
+    cudaStream_t qs = q.stream;
     fr.item_begin = begin;
     fr.n_items0 = std::min(c->cap_items, shard_items - begin);
-    CUDA_TRY(cudaMemsetAsync(c->counts.p, 0, (CRT_MAX_LEVELS + 1) * sizeof(uint32_t), st));
-    CUDA_TRY(cudaMemsetAsync(c->work.p, 0, (CRT_MAX_LEVELS + 2) * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(q.counts.p, 0, (CRT_MAX_LEVELS + 1) * sizeof(uint32_t), qs));
+    CUDA_TRY(cudaMemsetAsync(q.work.p, 0, (CRT_MAX_LEVELS + 2) * sizeof(uint32_t), qs));
     for (uint32_t l = 0; l < levels; l++) {
-      if (timed) {
-        cudaEventRecord(next_event(c), st);
+      if (per_kernel) {
+        cudaEventRecord(next_event(c), qs);
         c->kev_kind.push_back(0);
       }
-      if (o->count_work)
-        launch_closest<true>(c, l == 0, fr, l, c->work.p + l, st);
+      if (o->count_work && cull)
+        launch_closest<true, true>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
+      else if (o->count_work)
+        launch_closest<true, false>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
+      else if (cull)
+        launch_closest<false, true>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
       else
-        launch_closest<false>(c, l == 0, fr, l, c->work.p + l, st);
-      if (timed) cudaEventRecord(next_event(c), st);
-      k_shade<<<grid_simple, 256, 0, st>>>(c->sc, fr, c->lv, l);
+        launch_closest<false, false>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
+      if (per_kernel) cudaEventRecord(next_event(c), qs);
+      k_shade<<<grid_simple, 256, 0, qs>>>(c->sc, fr, q.lv, l);
       launches += 2;
     }
-    if (timed) {
-      cudaEventRecord(next_event(c), st);
+    if (per_kernel) {
+      cudaEventRecord(next_event(c), qs);
       c->kev_kind.push_back(1);
     }
+    uint32_t *swork = q.work.p + CRT_MAX_LEVELS;
     if (o->count_work == 1)
-      k_shadow_accumulate<1, CRT_REFILL, CRT_LOOP_MODE><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+      k_shadow_accumulate<1, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, 256, 0, qs>>>(c->sc, fr, q.lv, swork);
+    else if (o->count_work == 2 && cull)
+      k_shadow_accumulate<2, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, 256, 0, qs>>>(c->sc, fr, q.lv, swork);
     else if (o->count_work == 2)
-      k_shadow_accumulate<2, CRT_REFILL, CRT_LOOP_MODE><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
+      k_shadow_accumulate<2, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, 256, 0, qs>>>(c->sc, fr, q.lv, swork);
+    else if (cull)
+      k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, 256, 0, qs>>>(c->sc, fr, q.lv, swork);
     else
-      k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE><<<c->blocks_shadow, 256, 0, st>>>(c->sc, fr, c->lv, c->work.p + CRT_MAX_LEVELS);
-    if (timed) cudaEventRecord(next_event(c), st);
+      k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, 256, 0, qs>>>(c->sc, fr, q.lv, swork);
+    if (per_kernel) cudaEventRecord(next_event(c), qs);
     launches++;
     for (uint32_t l = levels - 1; l-- > 0;) {
-      k_resolve<<<grid_simple, 256, 0, st>>>(c->sc, fr, c->lv, l);
+      k_resolve<<<grid_simple, 256, 0, qs>>>(c->sc, fr, q.lv, l);
       launches++;
     }
-    k_store<<<grid_simple, 256, 0, st>>>(c->sc, fr, c->lv, d_rgb, d_rgb8, d_hits, d_slab);
+    k_store<<<grid_simple, 256, 0, qs>>>(c->sc, fr, q.lv, d_rgb, d_rgb8, d_hits, d_slab);
     launches++;
-    // shadow rays = diffuse hits x lights: fold this chunk's queue length into the stats before it is reset
-    // (done on the host from counts for the last chunk; earlier chunks are accumulated by k_store's stream order)
-    if (begin + c->cap_items < shard_items) {
-      // multi-chunk frames: accumulate per-chunk diffuse count into stats[1] with a tiny kernel-free trick:
-      // copy-add is not available, so read it back synchronously (rare path: only refractive 4K frames chunk).
-      uint32_t dq = 0;
-      CUDA_TRY(cudaMemcpyAsync(&dq, c->counts.p + CRT_MAX_LEVELS, 4, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      c->last.rays_shadow += (uint64_t)dq * c->sc.n_lights;
-    }
+  }
+  for (uint32_t k = 0; k < n_sets; k++) {
+    CUDA_TRY(cudaEventRecord(c->sets[k].done, c->sets[k].stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, c->sets[k].done, 0));
   }
   if (timed) CUDA_TRY(cudaEventRecord(c->ev[1], st));
   CUDA_TRY(cudaGetLastError());
@@ -616,11 +670,9 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
 
 static int collect_stats(crtb200_ctx *c, bool timed) {
   unsigned long long st[8];
-  uint32_t dq = 0;
   CUDA_TRY(cudaMemcpy(st, c->stats_dev.p, sizeof(st), cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(&dq, c->counts.p + CRT_MAX_LEVELS, 4, cudaMemcpyDeviceToHost));
   c->last.rays_primary = st[0];
-  c->last.rays_shadow += (uint64_t)dq * c->sc.n_lights;
+  c->last.rays_shadow = st[1];
   c->last.rays_reflection = st[2];
   c->last.rays_refraction = st[3];
   c->last.node_tests_closest = st[4];
@@ -793,7 +845,7 @@ int crtb200_trace_rays(crtb200_ctx *c, const float *rays, uint32_t n, uint32_t r
   if (!c || !rays) return fail(CRTB200_ERR_ARG, "null argument");
   if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
   if (ray_type > 3) return fail(CRTB200_ERR_ARG, "bad ray type");
-  if (traversal > 1) return fail(CRTB200_ERR_ARG, "unknown traversal mode");
+  if (traversal != 0) return fail(CRTB200_ERR_ARG, "traversal mode 1 (ordered + culled) is not available in this build");
   if (ray_type == CRTB200_RAY_SHADOW ? (!max_distance || !occluded_out) : !hits_out) return fail(CRTB200_ERR_ARG, "missing output / distance array");
   if (n == 0) return CRTB200_OK;
   CUDA_TRY(cudaSetDevice(c->device));

@@ -152,8 +152,11 @@ typedef struct crtb200_options {
   float refraction_bias; /* REFRACTION_BIAS, default 1e-4f */
   uint32_t n_rects;
   const crtb200_rect *rects;
-  uint32_t traversal; /* 0 = exact: the reference's visit-all order (KDTree.cpp:48-87); bit-exact hit ids */
-                      /* 1 = fast : near-to-far ordered + culled; identical except at documented ties     */
+  uint32_t traversal; /* 0 = exact: the reference's visit-all candidate set and order (KDTree.cpp:48-87): bit-exact */
+                      /*     hit ids and float RGB.  DEFAULT, and what every parity claim refers to.               */
+                      /* 1 = culled: same walk, but subtrees whose box is wholly behind the ray origin or wholly    */
+                      /*     beyond the best hit / the light are skipped.  Not the reference's    */
+                      /*     candidate set; measured deviations per scene are in DESIGN.md section 3.6.             */
   uint32_t count_work; /* 0 = off; 1 = count node / triangle tests under the reference's visit-all rule (shadow  */
                        /* early termination disabled; same pixels) -- the figure the roofline arithmetic uses;  */
                        /* 2 = count the tests the production kernels really perform                             */
@@ -193,6 +196,9 @@ int crtb200_create(int device, crtb200_ctx **out);
 int crtb200_destroy(crtb200_ctx *ctx);
 /* device budget in bytes for the per-frame ray queues (default 16 GiB); frames that need more are chunked */
 int crtb200_set_queue_budget(crtb200_ctx *ctx, uint64_t bytes);
+/* chunks of a frame rendered concurrently on separate streams (default 4; 1 = strictly sequential kernels, which is
+ * what the per-kernel timers closest_ms / shadow_ms of crtb200_stats require -- they read 0 otherwise) */
+int crtb200_set_concurrency(crtb200_ctx *ctx, uint32_t chunks_in_flight);
 
 /* replaces: the data RayTracer keeps in `scene`, `boundingBox`, `accelerationStructure` (RayTracer.h:64-67).
  * Copies + re-lays-out everything to device SoA during the call (host flattener H1). */

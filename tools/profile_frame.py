@@ -22,12 +22,14 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--count", type=int, default=0)
+    ap.add_argument("--concurrency", type=int, default=4)
     args = ap.parse_args()
     crt = importlib.import_module(bench.PKG)
     f, folder, kw, tex, depth = bench.ensure_scene(args.workload, dict(width=args.width, height=args.height))
     sf = crt.SceneFile(f, folder)
     ctx = crt.Context(0)
     ctx.upload(sf.flatten(), keepalive=sf)
+    ctx.set_concurrency(args.concurrency)
     rects, n = sf.rects()
     opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n, traversal=args.traversal, count_work=args.count)
     for i in range(args.frames):
