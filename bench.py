@@ -369,6 +369,33 @@ def ours_arm(args):
                     "node_tests_per_ray": (cst["node_tests"]) / max(1, cst["rays_total"]),
                     "triangle_tests_per_ray": (cst["triangle_tests"]) / max(1, cst["rays_total"])}
 
+    # opt-in culled traversal (mode 1), reported beside the exact headline together with its pixel difference to it
+    culled = None
+    if world == 1 and args.traversal == 0:
+        try:
+            ex = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+            cu = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+            ctx.render_device(cam, opt, d_rgb=ex.data_ptr(), stream=stream)
+            c_opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, traversal=1)
+            for _ in range(3):
+                ctx.render_device(cam, c_opt, d_rgb=cu.data_ptr(), stream=stream)
+            cms = []
+            for k in range(args.steps):
+                flush.fill_(k & 0xFF)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ctx.render_device(cam, c_opt, d_rgb=cu.data_ptr(), stream=stream)
+                b.record()
+                torch.cuda.synchronize()
+                cms.append(a.elapsed_time(b))
+            diff = ((ex.view(torch.int32) != cu.view(torch.int32)) & ~(torch.isnan(ex) & torch.isnan(cu))).any(dim=2)
+            culled = {"value": rays_frame / (statistics.mean(cms) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": statistics.mean(cms),
+                      "pixels_differing_from_exact": int(diff.sum().item()), "pixels": W * H,
+                      "note": "traversal=1: subtrees wholly behind the origin / beyond the best hit are skipped; not the headline"}
+            del ex, cu
+        except Exception as e:
+            culled = {"error": str(e)}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -407,6 +434,8 @@ def ours_arm(args):
         line["roofline"] = roofline
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
+    if culled:
+        line["culled_mode"] = culled
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -132,8 +132,11 @@ CRT_DI float stdmin(float a, float b) { return (b < a) ? b : a; }
 struct Ray {
   V3 o, d;
   V3 inv;         // 1.0f / d per axis (BoundingBox.h:95), hoisted: depends on the ray only
-  uint32_t flags; // bit i: |d_i| < FLT_EPSILON (BoundingBox.h:90); bit 3: primary ray (back-face cull, Ray.cpp:13)
+  uint32_t flags; // bit i: |d_i| < FLT_EPSILON (BoundingBox.h:90); bit 3: primary ray (back-face cull, Ray.cpp:13);
+                  // bit 4: some component of o / d / inv is NaN or inf (slab test must take the select-exact path)
 };
+
+#define CRT_RAY_SLOW_MASK 0x17u  // any axis-parallel flag or the non-finite flag
 
 CRT_DI void ray_prepare(Ray &r, bool primary) {
   r.flags = primary ? 8u : 0u;
@@ -143,6 +146,16 @@ CRT_DI void ray_prepare(Ray &r, bool primary) {
   r.inv.x = fdiv(1.0f, r.d.x);
   r.inv.y = fdiv(1.0f, r.d.y);
   r.inv.z = fdiv(1.0f, r.d.z);
+  // exponent all-ones <=> NaN or inf.  inv of a flagged (parallel) axis is never used, so it does not count.
+  uint32_t e = __float_as_uint(r.o.x) | __float_as_uint(r.o.y) | __float_as_uint(r.o.z);
+  const uint32_t nf = 0x7f800000u;
+  bool bad = ((__float_as_uint(r.o.x) & nf) == nf) || ((__float_as_uint(r.o.y) & nf) == nf) || ((__float_as_uint(r.o.z) & nf) == nf) ||
+             ((__float_as_uint(r.d.x) & nf) == nf) || ((__float_as_uint(r.d.y) & nf) == nf) || ((__float_as_uint(r.d.z) & nf) == nf);
+  (void)e;
+  if (!(r.flags & 1u)) bad = bad || ((__float_as_uint(r.inv.x) & nf) == nf);
+  if (!(r.flags & 2u)) bad = bad || ((__float_as_uint(r.inv.y) & nf) == nf);
+  if (!(r.flags & 4u)) bad = bad || ((__float_as_uint(r.inv.z) & nf) == nf);
+  if (bad) r.flags |= 16u;
 }
 
 // RayTracer::getRay + the second normalisation of shootRay                      RayTracer.cpp:61-80, 420
@@ -165,9 +178,11 @@ CRT_DI void primary_ray(const DCamera &cam, uint32_t W, uint32_t H, uint32_t row
 
 // BoundingBox::hasIntersection                                                  BoundingBox.h:85-108
 // (no t1 >= 0 test: boxes behind the origin pass; NaN bounds never reject -- both as in the reference).
-// Branch-free: the reference's early returns only skip work; every reject condition is evaluated on the same running
-// (t0, t1) it would have seen, so OR-ing them is exact.  An axis with |d| < FLT_EPSILON leaves (t0, t1) untouched.
-CRT_DI bool slab_test(const float4 lo, const float4 hi, const Ray &r, float &t0, float &t1) {
+//
+// slab_test_exact: the reference's statements as selects (std::max / std::min / swap NaN behaviour included); the early
+// returns of the reference only skip work, every reject condition is evaluated on the same running (t0, t1), so OR-ing
+// them is exact.  An axis with |d| < FLT_EPSILON leaves (t0, t1) untouched.
+CRT_DI bool slab_test_exact(const float4 lo, const float4 hi, const Ray &r, float &t0, float &t1) {
   t0 = -CRT_FLT_MAX;
   t1 = CRT_FLT_MAX;
   bool reject = false;
@@ -190,6 +205,20 @@ CRT_DI bool slab_test(const float4 lo, const float4 hi, const Ray &r, float &t0,
   CRT_SLAB_AXIS(4u, r.o.z, r.inv.z, lo.z, hi.z)
 #undef CRT_SLAB_AXIS
   return !reject;
+}
+
+// Fast path for the overwhelmingly common ray: all of o, d, 1/d finite and no axis-parallel component.  Then every
+// (bound - o) * inv is finite (finite boxes), so the swap / std::max / std::min selects see no NaN and equal the hardware
+// min / max up to the sign of zero, which no later comparison observes; and because t0 only grows and t1 only
+// shrinks, the reference's three "t0 > t1" early returns collapse into one final test.
+CRT_DI bool slab_test(const float4 lo, const float4 hi, const Ray &r, float &t0, float &t1) {
+  if (r.flags & CRT_RAY_SLOW_MASK) return slab_test_exact(lo, hi, r, t0, t1);
+  const float ax = fmul(fsub(lo.x, r.o.x), r.inv.x), bx = fmul(fsub(hi.x, r.o.x), r.inv.x);
+  const float ay = fmul(fsub(lo.y, r.o.y), r.inv.y), by = fmul(fsub(hi.y, r.o.y), r.inv.y);
+  const float az = fmul(fsub(lo.z, r.o.z), r.inv.z), bz = fmul(fsub(hi.z, r.o.z), r.inv.z);
+  t0 = fmaxf(fmaxf(fmaxf(-CRT_FLT_MAX, fminf(ax, bx)), fminf(ay, by)), fminf(az, bz));
+  t1 = fminf(fminf(fminf(CRT_FLT_MAX, fmaxf(ax, bx)), fmaxf(ay, by)), fmaxf(az, bz));
+  return !(t0 > t1);
 }
 
 // Ray::intersectWithTriangle + Triangle::pointIsInTriangle                       Ray.cpp:9-31, Triangle.cpp:37-57
@@ -226,14 +255,20 @@ CRT_DI bool triangle_test(const float4 g0, const float4 g1, const float4 g2, con
 // Order of events = the reference's: KDTree.cpp:127-166 (top level) around KDTree.cpp:48-87 (per mesh).
 // ------------------------------------------------------------------------------------------------------------
 struct Trav {
-  uint32_t top, mref, mend, cur, cend, tref, tend;
+  uint32_t cur, cend;     // node cursor and its end: inside a mesh tree, or in the top-level tree
+  uint32_t resume;        // top-level cursor to continue from once the current leaf's meshes are done
+  uint32_t mref, mend;    // cursor in the current top-level leaf's mesh list
+  uint32_t tref, tend;    // cursor in the current mesh leaf's triangle list
+  uint32_t below;         // 1 while working below a top-level leaf (mesh list / mesh trees)
   unsigned long long seen;  // meshes already traversed for this ray (scenes with <= 64 meshes)
 };
 CRT_DI void trav_begin(Trav &s, const DScene &sc) {
-  s.top = sc.top_begin;
+  s.cur = sc.top_begin;
+  s.cend = sc.top_end;
+  s.resume = sc.top_end;
   s.mref = s.mend = 0;
-  s.cur = s.cend = 0;
   s.tref = s.tend = 0;
+  s.below = 0;
   s.seen = 0ull;
 }
 
@@ -250,9 +285,8 @@ CRT_DI void trav_begin(Trav &s, const DScene &sc) {
 enum { TRAV_STEP = 0, TRAV_LEAF = 1, TRAV_DONE = 2 };
 template <bool SKIP_REFRACTIVE, bool COUNT, bool DEDUP, bool CULL>
 CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float t_limit) {
-  const bool in_mesh = s.cur != s.cend;
-  if (in_mesh || (s.mref == s.mend && s.top != sc.top_end)) {
-    const uint32_t idx = in_mesh ? s.cur : s.top;
+  if (s.cur != s.cend) {
+    const uint32_t idx = s.cur;
     const float4 lo = __ldg(&sc.nodes[2 * (size_t)idx]);
     const float4 hi = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
     const uint32_t a = __float_as_uint(lo.w);
@@ -260,22 +294,26 @@ CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tes
     if (COUNT) node_tests++;
     float t0, t1;
     bool pass = slab_test(lo, hi, r, t0, t1);
-    if (CULL) pass = pass && !(t1 < 0.0f) && !(t0 > t_limit);
-    const uint32_t next = (pass || leaf) ? idx + 1 : a;
-    const uint32_t first = __float_as_uint(hi.w), last = first + (a & ~CRT_LEAF_FLAG);
-    if (in_mesh) {
-      s.cur = next;
-      if (pass && leaf) {
+    if (CULL) {
+      // safety margins (1e-5 relative, ~170 ulp): a leaf that holds the hit point can only be culled by a rounding
+      // coincidence that is orders of magnitude larger than the slab arithmetic's error
+      const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
+      const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
+      pass = pass && !behind && !beyond;
+    }
+    s.cur = (pass || leaf) ? idx + 1 : a;
+    if (pass && leaf) {
+      const uint32_t first = __float_as_uint(hi.w), last = first + (a & ~CRT_LEAF_FLAG);
+      if (s.below) {
         s.tref = first;
         s.tend = last;
         return TRAV_LEAF;
       }
-    } else {
-      s.top = next;
-      if (pass && leaf) {
-        s.mref = first;
-        s.mend = last;
-      }
+      s.mref = first;  // a top-level leaf: remember where to continue, then walk its meshes
+      s.mend = last;
+      s.resume = s.cur;
+      s.cur = s.cend;
+      s.below = 1u;
     }
     return TRAV_STEP;
   }
@@ -292,6 +330,12 @@ CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tes
       s.cur = me.node_begin;
       s.cend = me.node_end;
     }
+    return TRAV_STEP;
+  }
+  if (s.below) {  // meshes of this top-level leaf are done: back to the top-level tree
+    s.below = 0u;
+    s.cur = s.resume;
+    s.cend = sc.top_end;
     return TRAV_STEP;
   }
   return TRAV_DONE;

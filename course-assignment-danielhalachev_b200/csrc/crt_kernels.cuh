@@ -18,6 +18,12 @@
 namespace crtd {
 
 #define CRT_FULL_MASK 0xFFFFFFFFu
+#ifndef CRT_TRAV_BLOCK
+#define CRT_TRAV_BLOCK 256      // threads per CTA of the persistent traversal kernels
+#endif
+#ifndef CRT_TRAV_MIN_BLOCKS
+#define CRT_TRAV_MIN_BLOCKS 4   // resident CTAs per SM the register allocation is bounded for
+#endif
 #define CRT_MAX_LEVELS 34
 
 struct Frame {
@@ -95,7 +101,7 @@ CRT_DI bool item_pixel(const Frame &fr, const DScene &sc, uint32_t item, uint32_
 // MODE 0: while-while (node phase to the next leaf, then leaf phase).  MODE 1: merged loop -- per iteration a lane does
 // one AABB step or one triangle test, whichever it needs (better when lanes reach leaves at very different times).
 template <bool PRIMARY, bool COUNT, int REFILL, int MODE, bool CULL>
-__global__ void __launch_bounds__(256) k_closest(const DScene sc, const Frame fr, const Levels lv, const uint32_t level,
+__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest(const DScene sc, const Frame fr, const Levels lv, const uint32_t level,
                                                 uint32_t *__restrict__ work_counter) {
   const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
   const uint32_t node_base = lv.offset[level];
@@ -415,7 +421,7 @@ __global__ void __launch_bounds__(256) k_shade(const DScene sc, const Frame fr, 
 // COUNT: 0 = no counters; 1 = count under the reference's visit-all rule (early termination disabled, same result);
 // 2 = count the work this kernel really does with early termination.  Loop structure: see k_closest.
 template <int COUNT, int REFILL, int MODE, bool CULL>
-__global__ void __launch_bounds__(256) k_shadow_accumulate(const DScene sc, const Frame fr, const Levels lv,
+__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_accumulate(const DScene sc, const Frame fr, const Levels lv,
                                                           uint32_t *__restrict__ work_counter) {
   const uint32_t total = lv.counts[CRT_MAX_LEVELS];
   const uint32_t lane = lane_id();

@@ -160,9 +160,9 @@ int crtb200_create(int device, crtb200_ctx **out) {
   }
   for (auto &e : c->ev) cudaEventCreate(&e);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL, CRT_LOOP_MODE, false>, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_closest = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, false>, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
   *out = c;
   return CRTB200_OK;
@@ -557,9 +557,9 @@ template <bool COUNT, bool CULL>
 static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, uint32_t *work,
                            cudaStream_t st) {
   if (primary)
-    k_closest<true, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, lv, level, work);
+    k_closest<true, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
   else
-    k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, 256, 0, st>>>(c->sc, fr, lv, level, work);
+    k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
 }
 
 // Enqueue one frame on `st`.  d_rgb / d_rgb8 / d_hits / d_slab are device pointers (any may be null).
@@ -639,15 +639,15 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     }
     uint32_t *swork = q.work.p + CRT_MAX_LEVELS;
     if (o->count_work == 1)
-      k_shadow_accumulate<1, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, 256, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow_accumulate<1, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else if (o->count_work == 2 && cull)
-      k_shadow_accumulate<2, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, 256, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow_accumulate<2, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else if (o->count_work == 2)
-      k_shadow_accumulate<2, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, 256, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow_accumulate<2, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else if (cull)
-      k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, 256, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else
-      k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, 256, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     if (per_kernel) cudaEventRecord(next_event(c), qs);
     launches++;
     for (uint32_t l = levels - 1; l-- > 0;) {

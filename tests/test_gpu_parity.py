@@ -152,3 +152,30 @@ def test_chunked_frame_identical(gpu, loaded, crt):
     gpu.set_queue_budget(16 << 30)
     assert same_f32(a, b).all()
     assert sa["rays_total"] == sb["rays_total"]
+
+
+@pytest.mark.parametrize("name", [n for n in SMALL_SCENES if n != "degenerate_uv"])
+def test_culled_mode_matches_exact_on_test_scenes(name, gpu, loaded, crt):
+    """traversal = 1 (skip subtrees wholly behind the origin / beyond the best hit or the light) is NOT guaranteed to
+    see the reference's candidate set; on every clean test scene it must nevertheless reproduce the
+    exact mode bit for bit.  (The NaN-triangle scene is excluded: non-finite candidates are position-independent.)"""
+    sf, flat, rects, n = loaded[name]
+    gpu.upload(flat, keepalive=sf)
+    a, _, ha, sa = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=0), want_hits=True)
+    b, _, hb, sb = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=1, count_work=2), want_hits=True)
+    assert same_f32(a, b).all()
+    assert np.array_equal(ha["mesh"], hb["mesh"]) and np.array_equal(ha["triangle"], hb["triangle"])
+    assert sa["rays_total"] == sb["rays_total"]
+    with pytest.raises(crt.CrtError):  # visit-all counting is only defined for the exact walk
+        gpu.render(sf.camera(), crt.make_options(traversal=1, count_work=1))
+
+
+def test_dedup_does_less_work_than_visit_all_with_same_pixels(gpu, loaded, crt):
+    """Production exact mode traverses a mesh once per ray even when several top-level leaves list it; count_work = 1
+    reproduces the reference's repeated traversals (and its counters), count_work = 2 reports the real work."""
+    sf, flat, rects, n = loaded["hw11_room"]
+    gpu.upload(flat, keepalive=sf)
+    a, _, _, visit_all = gpu.render(sf.camera(), crt.make_options(count_work=1))
+    b, _, _, real = gpu.render(sf.camera(), crt.make_options(count_work=2))
+    assert same_f32(a, b).all()
+    assert real["node_tests"] < visit_all["node_tests"] and real["triangle_tests"] < visit_all["triangle_tests"]
