@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -164,6 +165,10 @@ int crtb200_create(int device, crtb200_ctx **out) {
   c->blocks_closest = std::max(1, occ) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
+  if (const char *env = getenv("CRT_BLOCKS_PER_SM")) {  // tuning only (tools/): resident persistent CTAs per SM
+    const int b = atoi(env);
+    if (b > 0) c->blocks_closest = c->blocks_shadow = b * c->sm_count;
+  }
   *out = c;
   return CRTB200_OK;
 }
@@ -463,7 +468,7 @@ static uint32_t branching_sum(const crtb200_ctx *c, uint32_t max_depth, uint64_t
   return (uint32_t)std::min<uint64_t>(sum, 0xFFFFFFFFull);
 }
 
-static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth) {
+static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth, uint32_t row_items, bool pipelined) {
   uint64_t per_level[CRT_MAX_LEVELS] = {0};
   branching_sum(c, max_depth, per_level);
   uint64_t sum = 0;
@@ -471,12 +476,20 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth)
   const uint64_t bytes_per_node = 32 + 8 + 16 + 16 + 48;  // ray + hit + colour + comb + diffuse item
   // sets used: up to `concurrency`, but never chunks smaller than 64 Ki items (launch overhead would dominate)
   uint32_t n_sets = std::max<uint32_t>(1, std::min<uint32_t>(c->concurrency, (shard_items + 65535u) / 65536u));
+  // measured (profiles/r1_tuning.md): overlapping chunks only pays when band copies to the host ride along; the
+  // persistent kernels already fill the GPU, extra chunks just add launches and tails
+  if (!pipelined) n_sets = 1;
   uint64_t items = c->queue_budget / (bytes_per_node * sum * n_sets);
   items &= ~31ull;
   if (items < 32 * 64) return fail(CRTB200_ERR_MEMORY, "queue budget too small for one chunk at this ray depth");
-  const uint64_t even = (((uint64_t)shard_items + n_sets - 1) / n_sets + 31u) & ~31ull;  // one chunk per set when it fits
+  // one chunk per set when it fits; two per set when the bands are copied back to the host as they finish, so the
+  // copy of one band overlaps the traversal of the next
+  const uint32_t parts = n_sets * ((pipelined && n_sets > 1) ? 2u : 1u);
+  uint64_t even = ((uint64_t)shard_items + parts - 1) / parts;
+  even = ((even + row_items - 1) / row_items) * row_items;
   items = std::min<uint64_t>(items, even);
   if (items * sum >= 0x7FFFFFFFull) items = ((0x7FFFFFFFull / sum) - 32) & ~31ull;
+  if (items >= row_items) items = (items / row_items) * row_items;  // whole tile rows (band copies need it)
   if (c->cap_items == items && c->cap_depth == max_depth && c->cap_sets == n_sets) return CRTB200_OK;
   if (c->sets.size() < n_sets) c->sets.resize(n_sets);
   if (!c->fork_ev) CUDA_TRY(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
@@ -562,9 +575,18 @@ static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const 
     k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
 }
 
+// Host destinations of crtb200_render: each chunk's band of rows is copied back on the chunk's own stream right after
+// its k_store, so the device->host copy of band k overlaps the traversal of the other chunks.
+struct HostOut {
+  float *rgb = nullptr;
+  uint8_t *rgb8 = nullptr;
+  crtb200_hit *hits = nullptr;
+};
+
 // Enqueue one frame on `st`.  d_rgb / d_rgb8 / d_hits / d_slab are device pointers (any may be null).
 static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_options *o, float *d_rgb,
-                         uint8_t *d_rgb8, HitRec *d_hits, float *d_slab, cudaStream_t st, bool timed) {
+                         uint8_t *d_rgb8, HitRec *d_hits, float *d_slab, cudaStream_t st, bool timed,
+                         const HostOut *host = nullptr) {
   if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
   if (o->max_depth > 31) return fail(CRTB200_ERR_ARG, "max_depth > 31 is not supported");
   if (o->n_rects && !o->rects) return fail(CRTB200_ERR_ARG, "n_rects > 0 but rects is null");
@@ -592,7 +614,9 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   fr.refraction_bias = o->refraction_bias;
   const uint32_t shard_tiles = (fr.n_tiles > o->shard_index) ? (fr.n_tiles - o->shard_index + shard_count - 1) / shard_count : 0;
   const uint32_t shard_items = shard_tiles * 32u;
-  rc = plan_queues(c, std::max(shard_items, 32u), o->max_depth);
+  // unsharded frames: chunks are whole rows of tiles, so a chunk owns a contiguous band of image rows
+  const uint32_t row_items = (shard_count == 1) ? fr.tiles_x * 32u : 32u;
+  rc = plan_queues(c, std::max(shard_items, 32u), o->max_depth, row_items, host != nullptr);
   if (rc) return rc;
   const bool secondary = c->has_reflective || c->has_refractive;
   const uint32_t levels = secondary ? o->max_depth + 1 : 1;
@@ -656,6 +680,14 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     }
     k_store<<<grid_simple, 256, 0, qs>>>(c->sc, fr, q.lv, d_rgb, d_rgb8, d_hits, d_slab);
     launches++;
+    if (host && shard_count == 1) {
+      const uint32_t row0 = (begin / row_items) * 4u;
+      const uint32_t row1 = std::min<uint32_t>(H, ((begin + fr.n_items0 + row_items - 1) / row_items) * 4u);
+      const size_t off = (size_t)row0 * W, cnt = (size_t)(row1 - row0) * W;
+      if (host->rgb) CUDA_TRY(cudaMemcpyAsync(host->rgb + off * 3, d_rgb + off * 3, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, qs));
+      if (host->rgb8) CUDA_TRY(cudaMemcpyAsync(host->rgb8 + off * 3, d_rgb8 + off * 3, cnt * 3, cudaMemcpyDeviceToHost, qs));
+      if (host->hits) CUDA_TRY(cudaMemcpyAsync(host->hits + off, d_hits + off, cnt * sizeof(HitRec), cudaMemcpyDeviceToHost, qs));
+    }
   }
   for (uint32_t k = 0; k < n_sets; k++) {
     CUDA_TRY(cudaEventRecord(c->sets[k].done, c->sets[k].stream));
@@ -705,12 +737,24 @@ int crtb200_render(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_opti
   if (hits_out) CUDA_TRY(c->hits.ensure(px));
   if (hits_out) CUDA_TRY(cudaMemsetAsync(c->hits.p, 0xFF, px * sizeof(HitRec), c->stream));
   c->last = crtb200_stats{};
-  int rc = enqueue_frame(c, cam, o, c->frame.p, rgb8_out ? c->frame8.p : nullptr, hits_out ? c->hits.p : nullptr, nullptr,
-                         c->stream, true);
+  // Rectangle grids that leave pixels uncovered keep the previous frame there (colorBuffer persistence), so the whole
+  // persistent frame is copied after the render; otherwise each chunk's band is copied as soon as it is stored.
+  const bool shard = o->shard_count > 1;
+  HostOut host;
+  host.rgb = rgb_out;
+  host.rgb8 = rgb8_out;
+  host.hits = hits_out;
+  int rc = plan_mask(c, o);
   if (rc) return rc;
-  if (rgb_out) CUDA_TRY(cudaMemcpyAsync(rgb_out, c->frame.p, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  if (rgb8_out) CUDA_TRY(cudaMemcpyAsync(rgb8_out, c->frame8.p, px * 3, cudaMemcpyDeviceToHost, c->stream));
-  if (hits_out) CUDA_TRY(cudaMemcpyAsync(hits_out, c->hits.p, px * sizeof(HitRec), cudaMemcpyDeviceToHost, c->stream));
+  const bool banded = !shard && !c->mask_needed && (rgb_out || rgb8_out || hits_out);
+  rc = enqueue_frame(c, cam, o, c->frame.p, rgb8_out ? c->frame8.p : nullptr, hits_out ? c->hits.p : nullptr, nullptr,
+                     c->stream, true, banded ? &host : nullptr);
+  if (rc) return rc;
+  if (!banded) {
+    if (rgb_out) CUDA_TRY(cudaMemcpyAsync(rgb_out, c->frame.p, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (rgb8_out) CUDA_TRY(cudaMemcpyAsync(rgb8_out, c->frame8.p, px * 3, cudaMemcpyDeviceToHost, c->stream));
+    if (hits_out) CUDA_TRY(cudaMemcpyAsync(hits_out, c->hits.p, px * sizeof(HitRec), cudaMemcpyDeviceToHost, c->stream));
+  }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   rc = collect_stats(c, true);
   if (rc) return rc;

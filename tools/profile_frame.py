@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--count", type=int, default=0)
     ap.add_argument("--concurrency", type=int, default=4)
+    ap.add_argument("--shards", type=int, default=1, help="render shard 0 of N (per-rank work of an N-GPU run)")
     args = ap.parse_args()
     crt = importlib.import_module(bench.PKG)
     f, folder, kw, tex, depth = bench.ensure_scene(args.workload, dict(width=args.width, height=args.height))
@@ -31,9 +32,19 @@ def main():
     ctx.upload(sf.flatten(), keepalive=sf)
     ctx.set_concurrency(args.concurrency)
     rects, n = sf.rects()
-    opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n, traversal=args.traversal, count_work=args.count)
+    if args.shards > 1:
+        import torch
+        opt = crt.make_options(max_depth=depth, traversal=args.traversal, count_work=args.count, shard_index=0, shard_count=args.shards)
+        slab = torch.zeros((ctx.shard_items(args.shards), 3), dtype=torch.float32, device="cuda")
+    else:
+        opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n, traversal=args.traversal, count_work=args.count)
     for i in range(args.frames):
-        _, _, _, st = ctx.render(sf.camera(), opt, want_rgb=False)
+        if args.shards > 1:
+            ctx.render_device(sf.camera(), opt, d_rgb=slab.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            st = ctx.last_stats()
+        else:
+            _, _, _, st = ctx.render(sf.camera(), opt, want_rgb=False)
         print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in st.items()}))
     ctx.close()
 
