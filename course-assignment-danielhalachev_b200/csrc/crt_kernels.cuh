@@ -4,7 +4,8 @@
 //   K2  k_closest                   persistent closest-hit traversal, one ray per lane, stack-free two-level KD walk
 //   K4/K5 k_shade                   per-hit: barycentrics, smooth normal, texture sample, material switch,
 //                                   reflect / refract + Fresnel, compaction of children into the next level's queue
-//   K3  k_shadow_accumulate         persistent any-hit traversal per (diffuse hit, light) + in-order light sum
+//   K3  k_shadow                    persistent any-hit traversal, one (diffuse hit, light) pair per lane -> visibility
+//   K3b k_accumulate                in-order light sum per diffuse hit
 //   K6  k_resolve                   bottom-up combine of the ray tree in the reference's expression order
 //   K7  k_store                     level-0 colours -> framebuffer (f32 + PPMColor u8)
 //
@@ -45,6 +46,7 @@ struct Levels {
   float4 *color;      // per node: resolved colour
   uint4 *comb;        // per node: {kind, childA, childB / material, bits(F)}
   float4 *dq;         // diffuse queue, 3 x float4 per item: {P, bits(node)} {N, base.r} {base.g, base.b, -, -}
+  uint8_t *vis;       // per (diffuse item, light): 1 = the light is visible from the hit
   uint32_t *counts;   // [CRT_MAX_LEVELS] rays per level; [CRT_MAX_LEVELS] = diffuse queue length
   unsigned long long *stats;  // [0..3] rays by type, [4],[5] closest node / triangle tests, [6],[7] shadow
   uint32_t offset[CRT_MAX_LEVELS + 1];
@@ -411,25 +413,39 @@ __global__ void __launch_bounds__(256) k_shade(const DScene sc, const Frame fr, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K3: shadow any-hit + diffuse accumulation.  Replaces the light loop of RayTracer::calculateDiffusion
-// (RayTracer.cpp:308-330) and RayTracer::hasIntersection -> ObjectKDTree::checkForIntersection
-// (RayTracer.cpp:507-518, AccelerationStructure.cpp:56-94).  The reference runs a full closest-hit per mesh and
-// accepts iff |P - o| <= distanceToLight; because that length is monotone in t, "closest passes" == "some candidate
-// passes", so terminating on the first passing candidate is exact.  One lane owns one diffuse hit
-// and walks the lights in order so the sum is formed in the reference's order.
-// ------------------------------------------------------------------------------------------------------------
+// K3: shadow any-hit.  Replaces RayTracer::hasIntersection -> ObjectKDTree::checkForIntersection (RayTracer.cpp:507-518,
+// AccelerationStructure.cpp:56-94) for the shadow rays of RayTracer::calculateDiffusion (RayTracer.cpp:308-317).
+// The reference runs a full closest-hit per mesh and accepts iff |P - o| <= distanceToLight; because that length is
+// monotone in t, "closest passes" == "some candidate passes", so terminating on the first passing candidate is exact
+// (SURVEY App. A-11).  Work item = one (diffuse hit, light) pair, light-major so a warp's lanes shoot towards the same
+// light from neighbouring hits; the result is one visibility byte per pair.  (One item per pair, not per hit: the
+// kernel's tail is its longest item, profiles/r1_tuning.md.)
 // COUNT: 0 = no counters; 1 = count under the reference's visit-all rule (early termination disabled, same result);
 // 2 = count the work this kernel really does with early termination.  Loop structure: see k_closest.
-template <int COUNT, int REFILL, int MODE, bool CULL>
-__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_accumulate(const DScene sc, const Frame fr, const Levels lv,
-                                                          uint32_t *__restrict__ work_counter) {
-  const uint32_t total = lv.counts[CRT_MAX_LEVELS];
-  const uint32_t lane = lane_id();
+// ------------------------------------------------------------------------------------------------------------
+CRT_DI void shadow_ray_setup(const DScene &sc, const Frame &fr, const V3 P, const V3 N, const uint32_t light, Ray &ray,
+                             float &dist, float &contrib) {
   const float PI = 3.14159274101257324219f;  // M_PIf                            RayTracer.cpp:27
-  bool active = false, exhausted = false, need_ray = false, occluded = false;
-  uint32_t node = 0, light = 0, n_nodes = 0, n_tris = 0;
-  V3 P = mk(0, 0, 0), N = P, base = P, acc = P;
-  float contrib = 0.0f, dist = 0.0f, t_limit = 0.0f;
+  const DLight L = sc.lights[light];
+  V3 ld = vsub(mk(L.pos[0], L.pos[1], L.pos[2]), P);  // RayTracer.cpp:309
+  dist = vlen(ld);
+  const float area = fmul(fmul(fmul(4.0f, dist), dist), PI);  // 4 * r * r * PI   RayTracer.cpp:311-312
+  ld = vnorm(ld);
+  const float angle = stdmax(0.0f, vdot(ld, N));
+  contrib = fmul(fdiv(L.intensity, area), angle);  // (float(I) / area * angle)     RayTracer.cpp:320
+  ray.o = vadd(P, vscale(N, fr.shadow_bias));        // RayTracer.cpp:316
+  ray.d = ld;
+}
+
+template <int COUNT, int REFILL, int MODE, bool CULL>
+__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(const DScene sc, const Frame fr, const Levels lv,
+                                                                             uint32_t *__restrict__ work_counter) {
+  const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];
+  const uint32_t total = n_hits * sc.n_lights;
+  const uint32_t lane = lane_id();
+  bool active = false, exhausted = false, occluded = false;
+  uint32_t slot = 0, n_nodes = 0, n_tris = 0;
+  float dist = 0.0f, t_limit = 0.0f;
   Ray ray;
   Trav tv;
   ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
@@ -445,56 +461,31 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
       if (start + want >= total) exhausted = true;
       const uint32_t i = start + __popc(idle & lanemask_lt());
       if (!active && i < total) {
-        const float4 q0 = lv.dq[3 * (size_t)i], q1 = lv.dq[3 * (size_t)i + 1], q2 = lv.dq[3 * (size_t)i + 2];
-        P = mk(q0.x, q0.y, q0.z);
-        node = __float_as_uint(q0.w);
-        N = mk(q1.x, q1.y, q1.z);
-        base = mk(q1.w, q2.x, q2.y);
-        acc = mk(0, 0, 0);
-        light = 0;
+        const uint32_t light = i / n_hits, hit = i - light * n_hits;
+        const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
+        float contrib;
+        shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
+        ray_prepare(ray, false);
+        trav_begin(tv, sc);
+        t_limit = fadd(fmul(dist, 1.0001f), 1e-4f);  // CULL only: nothing beyond the light can satisfy |P - o| <= dist
+        occluded = false;
+        slot = hit * sc.n_lights + light;
         active = true;
-        need_ray = true;
       }
     }
     if (!__any_sync(CRT_FULL_MASK, active)) {
       if (exhausted) break;
       continue;
     }
-    // ---- next shadow ray of this lane's diffuse hit, or retire the hit ----
-    if (active && need_ray) {
-      if (light == sc.n_lights) {
-        lv.color[node] = make_float4(acc.x, acc.y, acc.z, 0.f);
-        active = false;
-      } else {
-        const DLight L = sc.lights[light];
-        V3 ld = vsub(mk(L.pos[0], L.pos[1], L.pos[2]), P);
-        dist = vlen(ld);
-        const float area = fmul(fmul(fmul(4.0f, dist), dist), PI);  // 4 * r * r * PI   RayTracer.cpp:311-312
-        ld = vnorm(ld);
-        const float angle = stdmax(0.0f, vdot(ld, N));
-        contrib = fmul(fdiv(L.intensity, area), angle);  // (float(I) / area * angle)     RayTracer.cpp:320
-        ray.o = vadd(P, vscale(N, fr.shadow_bias));
-        ray.d = ld;
-        ray_prepare(ray, false);
-        trav_begin(tv, sc);
-        t_limit = fadd(fmul(dist, 1.0001f), 1e-4f);  // CULL only: nothing beyond the light can satisfy |P - o| <= dist
-        occluded = false;
-        need_ray = false;
-      }
-    }
     if (MODE == 0) {
-      // ---- node phase ----
-      int st = (active && !need_ray) ? TRAV_STEP : TRAV_DONE;
+      int st = active ? TRAV_STEP : TRAV_DONE;
       while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
         if (st == TRAV_STEP) st = trav_step<true, (COUNT != 0), (COUNT != 1), CULL>(tv, sc, ray, n_nodes, t_limit);
       }
-      if (active && !need_ray && st == TRAV_DONE) {
-        // shadow ray finished; unoccluded: finalColor += direct * albedo            RayTracer.cpp:318-327
-        if (!occluded) acc = vadd(acc, sscale(contrib, base));
-        light++;
-        need_ray = true;
+      if (active && st == TRAV_DONE) {
+        lv.vis[slot] = occluded ? 0 : 1;
+        active = false;
       }
-      // ---- leaf phase ----
       while (__any_sync(CRT_FULL_MASK, tv.tref != tv.tend)) {
         if (tv.tref != tv.tend) {
           const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
@@ -509,15 +500,14 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
             occluded = true;
             if (COUNT != 1) {  // early termination: the rest of the walk cannot change the answer
               tv.tref = tv.tend = 0;
-              light++;
-              need_ray = true;
+              lv.vis[slot] = 0;
+              active = false;
             }
           }
         }
       }
     } else {
-      // ---- merged loop: until REFILL lanes need a new shadow ray ----
-      bool running = active && !need_ray;
+      bool running = active;
       const int quota = exhausted ? 0 : 32 - REFILL;
       while (__popc(__ballot_sync(CRT_FULL_MASK, running)) > quota) {
         if (running) {
@@ -533,15 +523,14 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
               occluded = true;
               if (COUNT != 1) {
                 tv.tref = tv.tend = 0;
-                light++;
-                need_ray = true;
+                lv.vis[slot] = 0;
+                active = false;
                 running = false;
               }
             }
           } else if (trav_step<true, (COUNT != 0), (COUNT != 1), CULL>(tv, sc, ray, n_nodes, t_limit) == TRAV_DONE) {
-            if (!occluded) acc = vadd(acc, sscale(contrib, base));
-            light++;
-            need_ray = true;
+            lv.vis[slot] = occluded ? 0 : 1;
+            active = false;
             running = false;
           }
         }
@@ -559,6 +548,26 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
       atomicAdd(&lv.stats[6], a);
       atomicAdd(&lv.stats[7], b);
     }
+  }
+}
+
+// K3b: the light loop of RayTracer::calculateDiffusion (RayTracer.cpp:308-330): per diffuse hit, walk the lights IN
+// ORDER and add `direct * albedo` for the unshadowed ones, so the float sum is formed exactly like the reference's.
+__global__ void __launch_bounds__(256) k_accumulate(const DScene sc, const Frame fr, const Levels lv) {
+  const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hits; i += gridDim.x * blockDim.x) {
+    const float4 q0 = lv.dq[3 * (size_t)i], q1 = lv.dq[3 * (size_t)i + 1], q2 = lv.dq[3 * (size_t)i + 2];
+    const V3 P = mk(q0.x, q0.y, q0.z), N = mk(q1.x, q1.y, q1.z), base = mk(q1.w, q2.x, q2.y);
+    V3 acc = mk(0.f, 0.f, 0.f);
+    for (uint32_t l = 0; l < sc.n_lights; l++) {
+      if (lv.vis[(size_t)i * sc.n_lights + l]) {
+        Ray ray;
+        float dist, contrib;
+        shadow_ray_setup(sc, fr, P, N, l, ray, dist, contrib);
+        acc = vadd(acc, sscale(contrib, base));  // finalColor += direct * albedo   RayTracer.cpp:321-327
+      }
+    }
+    lv.color[__float_as_uint(q0.w)] = make_float4(acc.x, acc.y, acc.z, 0.f);
   }
 }
 

@@ -104,11 +104,12 @@ struct crtb200_ctx {
     DevBuf<uint32_t> hit_tri, counts, work;
     DevBuf<float> hit_t;
     DevBuf<uint4> comb;
+    DevBuf<uint8_t> vis;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     void release() {
       ray_o.release(); ray_d.release(); color.release(); dq.release(); hit_tri.release(); counts.release();
-      work.release(); hit_t.release(); comb.release();
+      work.release(); hit_t.release(); comb.release(); vis.release();
     }
   };
   std::vector<QueueSet> sets;
@@ -163,7 +164,7 @@ int crtb200_create(int device, crtb200_ctx **out) {
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_closest = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
   if (const char *env = getenv("CRT_BLOCKS_PER_SM")) {  // tuning only (tools/): resident persistent CTAs per SM
     const int b = atoi(env);
@@ -511,6 +512,7 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     CUDA_TRY(q.color.ensure(total));
     CUDA_TRY(q.comb.ensure(total));
     CUDA_TRY(q.dq.ensure(3 * total));
+    CUDA_TRY(q.vis.ensure(std::max<uint64_t>(1, total * std::max<uint32_t>(1, c->sc.n_lights))));
     CUDA_TRY(q.counts.ensure(CRT_MAX_LEVELS + 1));
     CUDA_TRY(q.work.ensure(CRT_MAX_LEVELS + 2));
     q.lv.ray_o = q.ray_o.p;
@@ -520,6 +522,7 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     q.lv.color = q.color.p;
     q.lv.comb = q.comb.p;
     q.lv.dq = q.dq.p;
+    q.lv.vis = q.vis.p;
     q.lv.counts = q.counts.p;
     q.lv.stats = c->stats_dev.p;
   }
@@ -663,17 +666,18 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     }
     uint32_t *swork = q.work.p + CRT_MAX_LEVELS;
     if (o->count_work == 1)
-      k_shadow_accumulate<1, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow<1, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else if (o->count_work == 2 && cull)
-      k_shadow_accumulate<2, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow<2, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else if (o->count_work == 2)
-      k_shadow_accumulate<2, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow<2, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else if (cull)
-      k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else
-      k_shadow_accumulate<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     if (per_kernel) cudaEventRecord(next_event(c), qs);
-    launches++;
+    k_accumulate<<<grid_simple, 256, 0, qs>>>(c->sc, fr, q.lv);
+    launches += 2;
     for (uint32_t l = levels - 1; l-- > 0;) {
       k_resolve<<<grid_simple, 256, 0, qs>>>(c->sc, fr, q.lv, l);
       launches++;
