@@ -90,6 +90,93 @@ CRT_DI bool item_pixel(const Frame &fr, const DScene &sc, uint32_t item, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// MODE 2 building blocks: warp-cooperative triangle phase.
+//
+// ncu (profiles/r1c) showed the merged loop's triangle path running at ~8 of 32 lanes (its three edge tests at 3 / 2 / 1
+// lanes) serialised with a ~16-lane node path in every iteration.  MODE 2 splits the round differently:
+//   node phase   lanes that need an AABB step take one per iteration while at least CRT_NODE_MIN lanes do; a lane that
+//                reaches a leaf parks with its triangle range pending
+//   tri phase    the pending ranges of ALL parked lanes are concatenated (shuffle prefix sum) and dealt out 32 at a
+//                time: slot g of the concatenation is tested by lane g % 32 against its OWNER's ray, which every lane
+//                can read from the warp's shared-memory ray table.  Owners are found from a ballot of segment heads.
+//                Candidates are handed back to their owners in slot order, i.e. in the reference's encounter order
+//                (a lane has at most one pending leaf), so closest_offer sees exactly the sequence of KDTree.cpp:59-63.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef CRT_NODE_MIN
+#define CRT_NODE_MIN 16  // leave the node phase when fewer lanes than this still need an AABB step (and leaves wait)
+#endif
+
+struct __align__(16) WarpShare {
+  float4 ro[32];         // ray origin of lane i, w = distance to the light (shadow rays)
+  float4 rd[32];         // ray direction of lane i
+  uint32_t refbase[32];  // owner lane i: first pending leaf reference minus its start slot
+  uint32_t owner[32];    // window slot h holding a segment head -> owner lane
+};
+
+// Runs the triangle tests of every parked lane.  `pending` lanes have tv.tref..tv.tend set.  On return those ranges are
+// consumed.  CLOSEST: candidates are offered to cl in order.  SHADOW: `occluded` is set for owners with a candidate whose
+// hit point is within the light distance (AccelerationStructure.cpp:73-74).
+template <bool SHADOW, bool PRIMARY, bool COUNT>
+CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, uint32_t &tref, const uint32_t tend, Closest &cl,
+                      bool &occluded, uint32_t &n_tris) {
+  const uint32_t lane = lane_id();
+  const uint32_t cnt = pending ? tend - tref : 0u;
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(CRT_FULL_MASK, incl, d);
+    if (lane >= (uint32_t)d) incl += v;
+  }
+  const uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
+  const uint32_t start = incl - cnt;
+  if (cnt) ws.refbase[lane] = tref - start;
+  for (uint32_t base = 0; base < total; base += 32u) {
+    // segment heads of this window: an owner whose range intersects [base, base + 32) marks its first slot in the window
+    const bool in_win = cnt && start < base + 32u && start + cnt > base;
+    const uint32_t hp = (in_win && start > base) ? start - base : 0u;
+    const uint32_t heads = __reduce_or_sync(CRT_FULL_MASK, in_win ? (1u << hp) : 0u);
+    if (in_win) ws.owner[hp] = lane;
+    __syncwarp();
+    const uint32_t g = base + lane;
+    bool hit = false;
+    float t = 0.0f;
+    uint32_t tri = 0, own = 0;
+    if (g < total) {
+      own = ws.owner[31 - __clz(heads & (CRT_FULL_MASK >> (31u - lane)))];  // slot 0 of a window is always a head
+      tri = __ldg(&sc.leaf_refs[ws.refbase[own] + g]);
+      const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
+      const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
+      const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+      const float4 o4 = ws.ro[own], d4 = ws.rd[own];
+      Ray r;
+      r.o = mk(o4.x, o4.y, o4.z);
+      r.d = mk(d4.x, d4.y, d4.z);
+      r.flags = PRIMARY ? 8u : 0u;
+      V3 p;
+      if (COUNT) n_tris++;
+      hit = triangle_test(g0, g1, g2, r, t, p);
+      if (SHADOW) hit = hit && vlen(vsub(p, r.o)) <= o4.w;
+    }
+    // hand the candidates to their owners in slot (= encounter) order
+    uint32_t hm = __ballot_sync(CRT_FULL_MASK, hit);
+    while (hm) {
+      const int l = __ffs(hm) - 1;
+      hm &= hm - 1u;
+      const uint32_t o_l = __shfl_sync(CRT_FULL_MASK, own, l);
+      if (SHADOW) {
+        if (lane == o_l) occluded = true;
+      } else {
+        const uint32_t tri_l = __shfl_sync(CRT_FULL_MASK, tri, l);
+        const float t_l = __shfl_sync(CRT_FULL_MASK, t, l);
+        if (lane == o_l) closest_offer(cl, tri_l, t_l);
+      }
+    }
+    __syncwarp();  // ws.owner is rewritten by the next window
+  }
+  if (cnt) tref = tend;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K2: closest hit.  Replaces RayTracer::trace -> KDTree<ObjectKDTreeSubTree>::intersect -> KDTree<Triangle>::intersect
 // (RayTracer.cpp:453-458, KDTree.cpp:127-166, 48-87).
 //
@@ -105,6 +192,8 @@ CRT_DI bool item_pixel(const Frame &fr, const DScene &sc, uint32_t item, uint32_
 template <bool PRIMARY, bool COUNT, int REFILL, int MODE, bool CULL>
 __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest(const DScene sc, const Frame fr, const Levels lv, const uint32_t level,
                                                 uint32_t *__restrict__ work_counter) {
+  __shared__ WarpShare s_ws[(MODE == 2) ? CRT_TRAV_BLOCK / 32 : 1];
+  WarpShare *ws = &s_ws[(MODE == 2) ? (threadIdx.x >> 5) : 0];
   const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
   const uint32_t node_base = lv.offset[level];
   const uint32_t lane = lane_id();
@@ -145,6 +234,10 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
           closest_begin(cl);
           node = node_base + i;
           active = true;
+          if (MODE == 2) {
+            ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.f);
+            ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
+          }
         }
       }
     }
@@ -152,7 +245,36 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
       if (exhausted) break;
       continue;
     }
-    if (MODE == 0) {
+    if (MODE == 2) {
+      // ---- node phase: one AABB step per iteration for the lanes that need one ----
+      bool need = active && tv.tref == tv.tend;
+      bool to_refill = false;
+      for (;;) {
+        const uint32_t nn = __popc(__ballot_sync(CRT_FULL_MASK, need));
+        if (nn == 0u) break;
+        const uint32_t na = __popc(__ballot_sync(CRT_FULL_MASK, active));
+        if (nn < (uint32_t)CRT_NODE_MIN && na > nn) break;            // few steppers, leaves are waiting: test them
+        if (!exhausted && 32u - na >= (uint32_t)REFILL) {            // enough idle lanes: fetch new rays first
+          to_refill = true;
+          break;
+        }
+        if (need) {
+          const int st = trav_step<false, COUNT, !COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t);
+          if (st == TRAV_DONE) {
+            lv.hit_tri[node] = cl.best_tri;
+            lv.hit_t[node] = cl.best_t;
+            active = false;
+            need = false;
+          } else if (st == TRAV_LEAF) {
+            need = false;
+          }
+        }
+      }
+      if (to_refill) continue;
+      // ---- triangle phase: all pending leaves, packed across the warp ----
+      bool dummy = false;
+      tri_phase<false, PRIMARY, COUNT>(sc, *ws, active && tv.tref != tv.tend, tv.tref, tv.tend, cl, dummy, n_tris);
+    } else if (MODE == 0) {
       // ---- node phase ----
       int st = active ? TRAV_STEP : TRAV_DONE;
       while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
@@ -440,6 +562,8 @@ CRT_DI void shadow_ray_setup(const DScene &sc, const Frame &fr, const V3 P, cons
 template <int COUNT, int REFILL, int MODE, bool CULL>
 __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(const DScene sc, const Frame fr, const Levels lv,
                                                                              uint32_t *__restrict__ work_counter) {
+  __shared__ WarpShare s_ws[(MODE == 2) ? CRT_TRAV_BLOCK / 32 : 1];
+  WarpShare *ws = &s_ws[(MODE == 2) ? (threadIdx.x >> 5) : 0];
   const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];
   const uint32_t total = n_hits * sc.n_lights;
   const uint32_t lane = lane_id();
@@ -471,13 +595,48 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
         occluded = false;
         slot = hit * sc.n_lights + light;
         active = true;
+        if (MODE == 2) {
+          ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, dist);
+          ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
+        }
       }
     }
     if (!__any_sync(CRT_FULL_MASK, active)) {
       if (exhausted) break;
       continue;
     }
-    if (MODE == 0) {
+    if (MODE == 2) {
+      bool need = active && tv.tref == tv.tend;
+      bool to_refill = false;
+      for (;;) {
+        const uint32_t nn = __popc(__ballot_sync(CRT_FULL_MASK, need));
+        if (nn == 0u) break;
+        const uint32_t na = __popc(__ballot_sync(CRT_FULL_MASK, active));
+        if (nn < (uint32_t)CRT_NODE_MIN && na > nn) break;
+        if (!exhausted && 32u - na >= (uint32_t)REFILL) {
+          to_refill = true;
+          break;
+        }
+        if (need) {
+          const int st = trav_step<true, (COUNT != 0), (COUNT != 1), CULL>(tv, sc, ray, n_nodes, t_limit);
+          if (st == TRAV_DONE) {
+            lv.vis[slot] = occluded ? 0 : 1;
+            active = false;
+            need = false;
+          } else if (st == TRAV_LEAF) {
+            need = false;
+          }
+        }
+      }
+      if (to_refill) continue;
+      Closest unused;
+      tri_phase<true, false, (COUNT != 0)>(sc, *ws, active && tv.tref != tv.tend, tv.tref, tv.tend, unused, occluded, n_tris);
+      if (COUNT != 1 && active && occluded) {  // early termination: the rest of the walk cannot change the answer
+        tv.tref = tv.tend = 0;
+        lv.vis[slot] = 0;
+        active = false;
+      }
+    } else if (MODE == 0) {
       int st = active ? TRAV_STEP : TRAV_DONE;
       while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
         if (st == TRAV_STEP) st = trav_step<true, (COUNT != 0), (COUNT != 1), CULL>(tv, sc, ray, n_nodes, t_limit);

@@ -20,7 +20,7 @@ using namespace crtd;
 #define CRT_REFILL 8  // refill a warp when at least this many lanes are idle
 #endif
 #ifndef CRT_LOOP_MODE
-#define CRT_LOOP_MODE 1  // 0 = while-while, 1 = merged loop (crt_kernels.cuh); measured: profiles/r1_tuning.md
+#define CRT_LOOP_MODE 2  // 0 = while-while, 1 = merged loop, 2 = node phase + warp-cooperative triangle phase (crt_kernels.cuh)
 #endif
 
 static thread_local std::string g_error;
