@@ -79,6 +79,9 @@ struct DCamera {
 // exact float helpers
 // ------------------------------------------------------------------------------------------------------------
 #define CRT_DI __device__ __forceinline__
+#ifndef CRT_PREFETCH_SKIP
+#define CRT_PREFETCH_SKIP 0  // tuning: prefetch a node's skip target into L1 as soon as the node arrives
+#endif
 
 CRT_DI float fmul(float a, float b) { return __fmul_rn(a, b); }
 CRT_DI float fadd(float a, float b) { return __fadd_rn(a, b); }
@@ -333,6 +336,74 @@ CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tes
     return TRAV_STEP;
   }
   if (s.below) {  // meshes of this top-level leaf are done: back to the top-level tree
+    s.below = 0u;
+    s.cur = s.resume;
+    s.cend = sc.top_end;
+    return TRAV_STEP;
+  }
+  return TRAV_DONE;
+}
+
+// trav_step split in two for the MODE 2 kernels (crt_kernels.cuh), whose tight node loop only wants the AABB step:
+//   trav_fast   one AABB test for a lane with cur != cend.  Returns true while the lane can take another fast step;
+//               false when a triangle range is pending (tref..tend) or the cursor ran off its tree (trav_slow is due).
+//   trav_slow   the bookkeeping between trees for a lane with cur == cend and no pending triangles: next mesh of the
+//               current top-level leaf, or back to the top-level tree, or TRAV_DONE.
+// Together they perform exactly the state transitions of trav_step.
+template <bool COUNT, bool CULL>
+CRT_DI bool trav_fast(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float t_limit) {
+  const uint32_t idx = s.cur;
+  const float4 lo = __ldg(&sc.nodes[2 * (size_t)idx]);
+  const float4 hi = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
+  const uint32_t a = __float_as_uint(lo.w);
+  const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
+#if CRT_PREFETCH_SKIP
+  // the node after this subtree is visited whatever happens here (visit-all order): start pulling it into L1
+  if (!leaf) asm volatile("prefetch.global.L1 [%0];" ::"l"(&sc.nodes[2 * (size_t)a]));
+#endif
+  if (COUNT) node_tests++;
+  float t0, t1;
+  bool pass = slab_test(lo, hi, r, t0, t1);
+  if (CULL) {
+    const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
+    const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
+    pass = pass && !behind && !beyond;
+  }
+  s.cur = (pass || leaf) ? idx + 1 : a;
+  if (pass && leaf) {
+    const uint32_t first = __float_as_uint(hi.w), last = first + (a & ~CRT_LEAF_FLAG);
+    if (s.below) {
+      s.tref = first;
+      s.tend = last;
+    } else {  // a top-level leaf: remember where to continue, then walk its meshes (trav_slow)
+      s.mref = first;
+      s.mend = last;
+      s.resume = s.cur;
+      s.cur = s.cend;
+      s.below = 1u;
+    }
+    return false;
+  }
+  return s.cur != s.cend;
+}
+template <bool SKIP_REFRACTIVE, bool DEDUP>
+CRT_DI int trav_slow(Trav &s, const DScene &sc) {
+  if (s.mref != s.mend) {
+    const uint32_t m = __ldg(&sc.top_refs[s.mref++]);
+    const DMesh me = sc.meshes[m];
+    bool skip = SKIP_REFRACTIVE && sc.materials[me.material].type == 3u;
+    if (DEDUP && sc.dedup_meshes) {
+      const unsigned long long bit = 1ull << (m & 63u);
+      skip = skip || (s.seen & bit) != 0ull;
+      s.seen |= bit;
+    }
+    if (!skip) {
+      s.cur = me.node_begin;
+      s.cend = me.node_end;
+    }
+    return TRAV_STEP;
+  }
+  if (s.below) {
     s.below = 0u;
     s.cur = s.resume;
     s.cend = sc.top_end;

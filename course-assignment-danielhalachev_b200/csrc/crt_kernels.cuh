@@ -102,9 +102,20 @@ CRT_DI bool item_pixel(const Frame &fr, const DScene &sc, uint32_t item, uint32_
 //                Candidates are handed back to their owners in slot order, i.e. in the reference's encounter order
 //                (a lane has at most one pending leaf), so closest_offer sees exactly the sequence of KDTree.cpp:59-63.
 // ------------------------------------------------------------------------------------------------------------
+#ifndef CRT_TRI_CARRY
+#define CRT_TRI_CARRY 0  // tuning: deal out full 32-slot windows only, the remainder waits for the next triangle phase
+#endif
 #ifndef CRT_NODE_MIN
 #define CRT_NODE_MIN 16  // leave the node phase when fewer lanes than this still need an AABB step (and leaves wait)
 #endif
+
+// Node-phase exit threshold: with `na` lanes active, keep stepping while at least min(CRT_NODE_MIN, na / 2) lanes (but
+// at least one) want an AABB step.  Lanes leave the node phase only by parking (leaf pending / cursor off its tree), so
+// when the loop exits with fewer steppers than that, the triangle phase or trav_slow has work: no livelock.
+CRT_DI uint32_t node_threshold(uint32_t na) {
+  const uint32_t h = na >> 1;
+  return h < 1u ? 1u : (h < (uint32_t)CRT_NODE_MIN ? h : (uint32_t)CRT_NODE_MIN);
+}
 
 struct __align__(16) WarpShare {
   float4 ro[32];         // ray origin of lane i, w = distance to the light (shadow rays)
@@ -117,8 +128,8 @@ struct __align__(16) WarpShare {
 // consumed.  CLOSEST: candidates are offered to cl in order.  SHADOW: `occluded` is set for owners with a candidate whose
 // hit point is within the light distance (AccelerationStructure.cpp:73-74).
 template <bool SHADOW, bool PRIMARY, bool COUNT>
-CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, uint32_t &tref, const uint32_t tend, Closest &cl,
-                      bool &occluded, uint32_t &n_tris) {
+CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, const bool flush, uint32_t &tref, const uint32_t tend,
+                      Closest &cl, bool &occluded, uint32_t &n_tris) {
   const uint32_t lane = lane_id();
   const uint32_t cnt = pending ? tend - tref : 0u;
   uint32_t incl = cnt;
@@ -127,9 +138,13 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, uint3
     const uint32_t v = __shfl_up_sync(CRT_FULL_MASK, incl, d);
     if (lane >= (uint32_t)d) incl += v;
   }
-  const uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
+  uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
   const uint32_t start = incl - cnt;
   if (cnt) ws.refbase[lane] = tref - start;
+#if CRT_TRI_CARRY
+  // full windows only (unless `flush`): the tail of the concatenation stays parked and rides with the next phase
+  if (!flush && total >= 32u) total &= ~31u;
+#endif
   for (uint32_t base = 0; base < total; base += 32u) {
     // segment heads of this window: an owner whose range intersects [base, base + 32) marks its first slot in the window
     const bool in_win = cnt && start < base + 32u && start + cnt > base;
@@ -173,7 +188,10 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, uint3
     }
     __syncwarp();  // ws.owner is rewritten by the next window
   }
-  if (cnt) tref = tend;
+  if (cnt) {
+    const uint32_t done = total > start ? total - start : 0u;  // slots of this owner that were dealt out
+    tref += done < cnt ? done : cnt;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -246,34 +264,28 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
       continue;
     }
     if (MODE == 2) {
-      // ---- node phase: one AABB step per iteration for the lanes that need one ----
-      bool need = active && tv.tref == tv.tend;
-      bool to_refill = false;
+      // ---- between-trees bookkeeping for lanes whose cursor ran off a tree (rare) ----
       for (;;) {
-        const uint32_t nn = __popc(__ballot_sync(CRT_FULL_MASK, need));
-        if (nn == 0u) break;
-        const uint32_t na = __popc(__ballot_sync(CRT_FULL_MASK, active));
-        if (nn < (uint32_t)CRT_NODE_MIN && na > nn) break;            // few steppers, leaves are waiting: test them
-        if (!exhausted && 32u - na >= (uint32_t)REFILL) {            // enough idle lanes: fetch new rays first
-          to_refill = true;
-          break;
-        }
-        if (need) {
-          const int st = trav_step<false, COUNT, !COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t);
-          if (st == TRAV_DONE) {
-            lv.hit_tri[node] = cl.best_tri;
-            lv.hit_t[node] = cl.best_t;
-            active = false;
-            need = false;
-          } else if (st == TRAV_LEAF) {
-            need = false;
-          }
+        const bool slow = active && tv.tref == tv.tend && tv.cur == tv.cend;
+        if (!__any_sync(CRT_FULL_MASK, slow)) break;
+        if (slow && trav_slow<false, !COUNT>(tv, sc) == TRAV_DONE) {
+          lv.hit_tri[node] = cl.best_tri;
+          lv.hit_t[node] = cl.best_t;
+          active = false;
         }
       }
-      if (to_refill) continue;
+      // ---- node phase: one AABB step per iteration while enough lanes want one ----
+      bool need = active && tv.tref == tv.tend;
+      const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
+      while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
+        if (need) need = trav_fast<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t);
+      }
       // ---- triangle phase: all pending leaves, packed across the warp ----
-      bool dummy = false;
-      tri_phase<false, PRIMARY, COUNT>(sc, *ws, active && tv.tref != tv.tend, tv.tref, tv.tend, cl, dummy, n_tris);
+      const bool parked = active && tv.tref != tv.tend;
+      if (__any_sync(CRT_FULL_MASK, parked)) {
+        bool dummy = false;
+        tri_phase<false, PRIMARY, COUNT>(sc, *ws, parked, !__any_sync(CRT_FULL_MASK, need), tv.tref, tv.tend, cl, dummy, n_tris);
+      }
     } else if (MODE == 0) {
       // ---- node phase ----
       int st = active ? TRAV_STEP : TRAV_DONE;
@@ -606,35 +618,28 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
       continue;
     }
     if (MODE == 2) {
-      bool need = active && tv.tref == tv.tend;
-      bool to_refill = false;
       for (;;) {
-        const uint32_t nn = __popc(__ballot_sync(CRT_FULL_MASK, need));
-        if (nn == 0u) break;
-        const uint32_t na = __popc(__ballot_sync(CRT_FULL_MASK, active));
-        if (nn < (uint32_t)CRT_NODE_MIN && na > nn) break;
-        if (!exhausted && 32u - na >= (uint32_t)REFILL) {
-          to_refill = true;
-          break;
-        }
-        if (need) {
-          const int st = trav_step<true, (COUNT != 0), (COUNT != 1), CULL>(tv, sc, ray, n_nodes, t_limit);
-          if (st == TRAV_DONE) {
-            lv.vis[slot] = occluded ? 0 : 1;
-            active = false;
-            need = false;
-          } else if (st == TRAV_LEAF) {
-            need = false;
-          }
+        const bool slow = active && tv.tref == tv.tend && tv.cur == tv.cend;
+        if (!__any_sync(CRT_FULL_MASK, slow)) break;
+        if (slow && trav_slow<true, (COUNT != 1)>(tv, sc) == TRAV_DONE) {
+          lv.vis[slot] = occluded ? 0 : 1;
+          active = false;
         }
       }
-      if (to_refill) continue;
-      Closest unused;
-      tri_phase<true, false, (COUNT != 0)>(sc, *ws, active && tv.tref != tv.tend, tv.tref, tv.tend, unused, occluded, n_tris);
-      if (COUNT != 1 && active && occluded) {  // early termination: the rest of the walk cannot change the answer
-        tv.tref = tv.tend = 0;
-        lv.vis[slot] = 0;
-        active = false;
+      bool need = active && tv.tref == tv.tend;
+      const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
+      while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
+        if (need) need = trav_fast<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit);
+      }
+      const bool parked = active && tv.tref != tv.tend;
+      if (__any_sync(CRT_FULL_MASK, parked)) {
+        Closest unused;
+        tri_phase<true, false, (COUNT != 0)>(sc, *ws, parked, !__any_sync(CRT_FULL_MASK, need), tv.tref, tv.tend, unused, occluded, n_tris);
+        if (COUNT != 1 && active && occluded) {  // early termination: the rest of the walk cannot change the answer
+          tv.tref = tv.tend = 0;
+          lv.vis[slot] = 0;
+          active = false;
+        }
       }
     } else if (MODE == 0) {
       int st = active ? TRAV_STEP : TRAV_DONE;

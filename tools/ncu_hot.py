@@ -1,25 +1,32 @@
 #!/usr/bin/env python3
-"""Top SASS instructions by stall samples from `ncu --page source --csv`.  usage: ncu_hot.py rep [kernel-index] [n]"""
-import csv, io, subprocess, sys
-rep = sys.argv[1]
-which = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-n = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(txt)))
-sections, cur = [], None
-for r in rows:
-    if r and r[0] == "Kernel Name":
-        cur = {"name": r[1], "hdr": None, "rows": []}
-        sections.append(cur)
-    elif cur is not None and cur["hdr"] is None:
-        cur["hdr"] = r
-    elif cur is not None and len(r) >= len(cur["hdr"]) - 2:
-        cur["rows"].append(r)
-s = sections[which]
-idx = {h: i for i, h in enumerate(s["hdr"])}
-data = s["rows"]
-tot = sum(int(r[idx["# Samples"]]) for r in data)
-ti = sum(int(r[idx["Instructions Executed"]]) for r in data)
-print(f"{len(sections)} kernels; [{which}] {s['name'][:80]}: samples {tot}, warp inst {ti}, sass lines {len(data)}")
-for r in sorted(data, key=lambda r: -int(r[idx["# Samples"]]))[:n]:
-    print(r[idx["# Samples"]].rjust(7), r[idx["Instructions Executed"]].rjust(11), r[idx["Avg. Threads Executed"]].rjust(6), " ", r[idx["Source"]][:110])
+"""Per-SASS-instruction view of an `ncu --page source --csv` export: share of executed warp instructions, average active
+threads and stall-sample share.  usage: ncu_hot.py source.csv [min_inst_pct]"""
+import csv
+import sys
+
+
+def main():
+    rows = list(csv.reader(open(sys.argv[1])))
+    thresh = float(sys.argv[2]) if len(sys.argv) > 2 else 0.05
+    hdr = rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    data = [r for r in rows[2:] if len(r) > ix['stall_wait'] and r[0].startswith('0x')]
+    # several launches of one kernel are concatenated: keep the first
+    first = data[0][0]
+    for k in range(1, len(data)):
+        if data[k][0] == first:
+            data = data[:k]
+            break
+    tot_i = sum(int(r[ix['Instructions Executed']]) for r in data)
+    tot_s = sum(int(r[ix['# Samples']]) for r in data)
+    print('sass instructions', len(data), 'executed', tot_i, 'samples', tot_s)
+    for k, r in enumerate(data):
+        i = int(r[ix['Instructions Executed']])
+        s = int(r[ix['# Samples']])
+        if 100 * i / tot_i > thresh or 100 * s / tot_s > 0.5:
+            print(k, r[ix['Source']].strip()[:64].ljust(64), 'inst%5.2f' % (100 * i / tot_i), 'thr', r[ix['Avg. Threads Executed']].rjust(3),
+                  'smp%5.2f' % (100 * s / tot_s), 'lsb', r[ix['stall_long_sb']], 'ssb', r[ix['stall_short_sb']])
+
+
+if __name__ == '__main__':
+    main()
