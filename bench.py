@@ -282,27 +282,37 @@ def ours_arm(args):
         # sequence (a static-camera sequence here, so per-GPU work equals the N = 1 case) and its PPMColor bytes are
         # gathered to rank 0 over NCCL, double-buffered so the gather of frame k overlaps the render of frame k + 1.
         bufs8 = [torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
-        gls = [[torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) for _ in range(world)] for _ in range(2)] if rank == 0 else [None, None]
+        gflat = [torch.zeros((world, H, W, 3), dtype=torch.uint8, device=dev) if rank == 0 else None for _ in range(2)]
+        gls = [[gflat[b][i] for i in range(world)] for b in range(2)] if rank == 0 else [None, None]
+        host8 = [torch.empty((world, H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else [None, None]
         works = [None, None]
+    host_frame = torch.empty((H, W, 3), dtype=torch.float32).pin_memory() if (world > 1 and rank == 0) else None
 
-    def step(k=0):
+    def step(k=0, to_host=False):
+        # to_host (e2e legs, N > 1): the step's result also lands in pinned host memory on rank 0
         if frames_mode:
             b = k & 1
             if works[b] is not None:
                 works[b].wait()
+                if to_host and rank == 0:
+                    host8[b].copy_(gflat[b], non_blocking=True)
             ctx.render_device(cam, opt, d_rgb=frame.data_ptr(), d_rgb8=bufs8[b].data_ptr(), stream=stream)
             works[b] = dist.gather(bufs8[b], gls[b], dst=0, async_op=True)
         elif world > 1:
             sharded.render(cam, max_depth=depth, traversal=args.traversal, frame=frame if rank == 0 else None,
                            frame8=frame8 if rank == 0 else None)
+            if to_host and rank == 0:
+                host_frame.copy_(frame, non_blocking=True)
         else:
             ctx.render_device(cam, opt, d_rgb=frame.data_ptr(), d_rgb8=frame8.data_ptr(), stream=stream)
 
-    def drain():
+    def drain(to_host=False):
         if frames_mode:
             for b in range(2):
                 if works[b] is not None:
                     works[b].wait()
+                    if to_host and rank == 0:
+                        host8[b].copy_(gflat[b], non_blocking=True)
                     works[b] = None
 
     for k in range(max(args.warmup, 3)):
@@ -350,6 +360,24 @@ def ours_arm(args):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
 
+    # N > 1 end to end: the same K steps, with every step's gathered result copied to pinned host memory on rank 0 inside
+    # the timed region (all ranks take part: the gather is a collective); device events, max over ranks
+    e2e_multi_ms = None
+    if world > 1:
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        a.record()
+        for k in range(args.steps):
+            step(k, to_host=True)
+        drain(to_host=True)
+        b2.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([a.elapsed_time(b2)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_multi_ms = float(t.item()) / args.steps
+
     # ray count of one frame: identical every step; with shards, sum over ranks
     rays_local = torch.tensor([kstats[-1]["rays_total"]], dtype=torch.int64, device=dev)
     if world > 1:
@@ -381,7 +409,11 @@ def ours_arm(args):
                "h2d_bytes_per_step": 48 + 40 + 16 * n_rects, "d2h_bytes_per_step": W * H * 12,
                "api": "crtb200_render(host camera/options -> pinned host float RGB)"}
     else:
-        e2e = None
+        e2e = {"value": rays_frame / (e2e_multi_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_multi_ms,
+               "h2d_bytes_per_step": (48 + 40 + 16 * n_rects) * world,
+               "d2h_bytes_per_step": (world * W * H * 3) if frames_mode else W * H * 12,
+               "api": ("crtb200_render_device per rank -> NCCL gather of the PPMColor frames -> pinned host memory on rank 0" if frames_mode
+                       else "crtb200_render_device shard per rank -> NCCL gather -> crtb200_assemble_shards -> pinned host float RGB on rank 0")}
 
     peak, peak_src = measured_hbm_peak()
     roofline = None
@@ -485,6 +517,138 @@ def ours_arm(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# config 5: camera-animation sequence (app/animation.cpp:24-38), frames round-robin over the GPUs
+# ---------------------------------------------------------------------------------------------------------------------
+def animation_arm(args):
+    """A step = the whole F-frame orbit sequence.  Frame f is rendered by rank f % N (scene replicated); after every
+    round of N frames the PPMColor frames are gathered to rank 0 over NCCL, double-buffered so the gather of round r
+    overlaps the render of round r + 1.  value = rays of all F frames / sequence time; e2e adds the copy of every
+    gathered frame to pinned host memory (what the reference's exportPPM consumes)."""
+    import torch
+    import torch.distributed as dist
+
+    crt = importlib.import_module(PKG)
+    scenes = importlib.import_module(PKG + ".scenes")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    torch.cuda.set_device(dev)
+    if rank == 0:
+        scene_file, folder, kw, tex, depth = ensure_scene(args.workload, dict(width=args.width, height=args.height))
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        scene_file, folder, kw, tex, depth = ensure_scene(args.workload, dict(width=args.width, height=args.height))
+    sf = crt.SceneFile(scene_file, folder)
+    flat = sf.flatten()
+    ctx = crt.Context(dev.index)
+    ctx.upload(flat, keepalive=sf)
+    ctx.set_concurrency(args.concurrency)
+    W, H = sf.info.width, sf.info.height
+    F = args.animation
+    center_z = -3.0 if args.workload == "synthetic_10M" else -4.0
+    cams = [crt.Camera.make(p, r) for p, r in scenes.orbit_cameras(F, radius=5.12, center_z=center_z)]
+    rects, n_rects = sf.rects(mode=crt.MODE_B200_WAVEFRONT)
+    opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, traversal=args.traversal)
+    stream = torch.cuda.current_stream().cuda_stream
+    rounds = (F + world - 1) // world
+    frame = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    bufs8 = [torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+    gflat = [torch.zeros((world, H, W, 3), dtype=torch.uint8, device=dev) if rank == 0 else None for _ in range(2)]
+    host8 = [torch.empty((world, H, W, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None for _ in range(2)]
+    works = [None, None]
+
+    # untimed pass: ray count of every frame this rank owns (also the warm-up)
+    rays_mine = 0
+    for f in range(rank, F, world):
+        ctx.render_device(cams[f], opt, d_rgb=frame.data_ptr(), d_rgb8=bufs8[0].data_ptr(), stream=stream)
+        torch.cuda.synchronize()
+        rays_mine += ctx.last_stats()["rays_total"]
+    rays_t = torch.tensor([rays_mine], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
+    rays_seq = int(rays_t.item())
+
+    def finish(b, to_host):
+        if works[b] is not None:
+            if works[b] is not True:
+                works[b].wait()
+            if to_host and rank == 0:
+                host8[b].copy_(gflat[b], non_blocking=True)
+            works[b] = None
+
+    def sequence(to_host):
+        for r in range(rounds):
+            b = r & 1
+            finish(b, to_host)
+            f = r * world + rank
+            if f < F:
+                ctx.render_device(cams[f], opt, d_rgb=frame.data_ptr(), d_rgb8=bufs8[b].data_ptr(), stream=stream)
+            if world > 1:
+                works[b] = dist.gather(bufs8[b], [gflat[b][i] for i in range(world)] if rank == 0 else None, dst=0, async_op=True)
+            else:
+                gflat[b][0].copy_(bufs8[b])
+                works[b] = True
+        finish(0, to_host)
+        finish(1, to_host)
+
+    def timed(to_host):
+        out = []
+        for _ in range(args.steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a.record()
+            sequence(to_host)
+            b.record()
+            torch.cuda.synchronize()
+            out.append(a.elapsed_time(b))
+        t = torch.tensor([sum(out)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / args.steps, out
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        sequence(False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    ms, step_ms = timed(False)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms, _ = timed(True)
+    if rank == 0:
+        launches = 0
+        st = ctx.last_stats()
+        launches = st["kernel_launches"] * F + (rounds if world > 1 else 0)
+        line = {
+            "metric": "Mrays/s (primary+secondary)", "value": rays_seq / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(1, min(args.warmup, 2)) + 1, "ms_per_step": ms, "ms_per_frame": ms / F,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "width": W, "height": H, "triangles": int(sf.info.n_triangles), "max_depth": depth,
+                       "animation_frames": F, "camera_path": "app/animation.cpp orbit, radius 5.12, 360/F degrees per frame",
+                       "traversal": "exact (reference visit-all order)" if args.traversal == 0 else "fast (ordered+culled)",
+                       "parallelism": f"frames round-robin over {world} GPU(s), rgb8 frames gathered to rank 0 (NCCL, overlapped)",
+                       "l2": "every frame has a new camera and streams its queues through L2; scene working set >= L2 for synthetic_10M",
+                       "rays_per_step": rays_seq},
+            "clocks": clocks, "gpu_launches": launches * args.steps, "step_ms": step_ms,
+            "e2e": {"value": rays_seq / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms, "ms_per_frame": e2e_ms / F,
+                    "h2d_bytes_per_step": (48 + 40 + 16 * n_rects) * F, "d2h_bytes_per_step": rounds * world * W * H * 3,
+                    "api": "crtb200_render_device per frame -> NCCL gather -> pinned host PPMColor frames on rank 0"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -499,6 +663,7 @@ def main():
                     help="N > 1: frames = one frame per GPU per step (weak scaling); tiles = one frame split by tiles (strong)")
     ap.add_argument("--concurrency", type=int, default=4, help="chunks of a frame in flight on separate streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--animation", type=int, default=0, help="F > 0: a step is the F-frame orbit animation (config 5), frames round-robin over GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -508,6 +673,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", os.environ.get("MASTER_PORT", "29511"), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    if args.animation > 0:
+        return animation_arm(args)
     return ours_arm(args)
 
 
