@@ -26,10 +26,17 @@ namespace crtd {
 //  tri_geom  3 x float4 per triangle: {v0, n.x} {v1, n.y} {v2, n.z}  (48 B: everything Ray::intersectWithTriangle reads)
 //  tri_shade uint4 per triangle: {i0, i1, i2, mesh}  -- only touched once per ray, at shading time
 // ------------------------------------------------------------------------------------------------------------
+//  wnodes    the same mesh trees collapsed two levels at a time into 4-wide nodes of 128 B = one L2 line (8 x float4):
+//            entry k = {min.x, min.y, min.z, max.x} {max.y, max.z, a, b}; the entries are reference nodes (their exact
+//            boxes), in visiting order: for each child (child[1] first) the child itself when it is a leaf, else the
+//            child's children.  leaf entry: a = 0x80000000 | count, b = first reference; inner entry: a = index of the
+//            wide node of that reference node; absent entry: a = 0xFFFFFFFF.  Every mesh starts with a one-entry wide
+//            node holding its root.  See "wide walk" below for why walking this is exact.
 struct DMesh {
   uint32_t node_begin, node_end;  // [begin, end) in `nodes`
   uint32_t material;
   uint32_t first_triangle;
+  uint32_t wroot;                 // index of the mesh's one-entry root wide node in `wnodes`, CRT_INVALID for an empty tree
 };
 struct DMaterial {
   uint32_t type, smooth, texture;
@@ -52,6 +59,7 @@ struct DLight {
 
 struct DScene {
   const float4 *nodes;
+  const float4 *wnodes;
   const uint32_t *leaf_refs;
   const uint32_t *top_refs;
   const float4 *tri_geom;
@@ -79,6 +87,9 @@ struct DCamera {
 // exact float helpers
 // ------------------------------------------------------------------------------------------------------------
 #define CRT_DI __device__ __forceinline__
+#ifndef CRT_TRAV_BLOCK
+#define CRT_TRAV_BLOCK 256      // threads per CTA of the persistent traversal kernels
+#endif
 #ifndef CRT_PREFETCH_SKIP
 #define CRT_PREFETCH_SKIP 0  // tuning: prefetch a node's skip target into L1 as soon as the node arrives
 #endif
@@ -407,6 +418,177 @@ CRT_DI int trav_slow(Trav &s, const DScene &sc) {
     s.below = 0u;
     s.cur = s.resume;
     s.cend = sc.top_end;
+    return TRAV_STEP;
+  }
+  return TRAV_DONE;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Wide walk (MODE 3).  The reference visits a leaf iff the slab test passes for the leaf AND all its ancestors
+// (KDTree.cpp:53-72).  Its child boxes are the exact halves of the parent box (BoundingBox.h:60-69: one plane replaced by
+// min + (max - min) / 2, which lies in [min, max] in binary32), and BoundingBox::hasIntersection is monotone in every
+// plane under round-to-nearest: moving min down or max up can only lower t0 / raise t1 (or widen the containment test
+// of a parallel axis), and a NaN never rejects.  So "leaf passes" implies "every ancestor passes": the visited leaves
+// are exactly the leaves whose OWN box passes, in tree order.  Any hierarchy over the same leaves in the same order
+// whose inner tests never reject a passing leaf enumerates the same candidates in the same order; the 4-wide nodes use
+// reference boxes for every entry, so an inner entry rejects only what the reference rejects at that node.
+// crtb200_upload_scene verifies the nesting for the uploaded trees and falls back to the binary walk otherwise.
+// The walk needs a stack of (wide node, remaining entries): one 32-bit word per level in shared memory.
+// ------------------------------------------------------------------------------------------------------------
+#define CRT_WIDE_STACK 16  // levels; upload checks the collapsed depth of every tree against it
+
+struct TravW {
+  uint32_t top;           // cursor in the top-level (binary, skip-linked) tree
+  uint32_t resume;        // top-level cursor to continue from once the current leaf's meshes are done
+  uint32_t mref, mend;    // cursor in the current top-level leaf's mesh list
+  uint32_t below;         // 1 while working below a top-level leaf
+  unsigned long long seen;
+  uint32_t wcur;          // current wide node, CRT_INVALID when not inside a mesh tree
+  uint32_t mask;          // entries of wcur that passed and are still to be taken (bits 0..3)
+  uint32_t sp;            // stack depth
+  uint32_t tref, tend;    // pending triangle range
+};
+CRT_DI void travw_begin(TravW &s, const DScene &sc) {
+  s.top = sc.top_begin;
+  s.resume = sc.top_end;
+  s.mref = s.mend = 0;
+  s.below = 0;
+  s.seen = 0ull;
+  s.wcur = CRT_INVALID;
+  s.mask = 0;
+  s.sp = 0;
+  s.tref = s.tend = 0;
+}
+
+// slab tests of the (up to) four entries of wide node w -> pass mask.  The common ray (finite, no axis-parallel
+// component: slab_test's fast path) gets straight-line code: all eight 16-byte loads of the 128-byte node are issued
+// before the first use and the four tests are independent instruction streams for the scheduler.
+template <bool CULL>
+CRT_DI uint32_t wide_test(const DScene &sc, const uint32_t w, const Ray &r, const float t_limit) {
+  const float4 *p = sc.wnodes + 8 * (size_t)w;
+  uint32_t m = 0;
+  if (r.flags & CRT_RAY_SLOW_MASK) {
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+      const float4 q0 = __ldg(p + 2 * k), q1 = __ldg(p + 2 * k + 1);
+      float t0, t1;
+      bool pass = slab_test_exact(make_float4(q0.x, q0.y, q0.z, 0.f), make_float4(q0.w, q1.x, q1.y, 0.f), r, t0, t1);
+      if (CULL) {
+        const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
+        const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
+        pass = pass && !behind && !beyond;
+      }
+      pass = pass && __float_as_uint(q1.z) != CRT_INVALID;
+      m |= pass ? (1u << k) : 0u;
+    }
+    return m;
+  }
+  float4 q[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) q[k] = __ldg(p + k);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float4 q0 = q[2 * k], q1 = q[2 * k + 1];
+    const float ax = fmul(fsub(q0.x, r.o.x), r.inv.x), bx = fmul(fsub(q0.w, r.o.x), r.inv.x);
+    const float ay = fmul(fsub(q0.y, r.o.y), r.inv.y), by = fmul(fsub(q1.x, r.o.y), r.inv.y);
+    const float az = fmul(fsub(q0.z, r.o.z), r.inv.z), bz = fmul(fsub(q1.y, r.o.z), r.inv.z);
+    const float t0 = fmaxf(fmaxf(fmaxf(-CRT_FLT_MAX, fminf(ax, bx)), fminf(ay, by)), fminf(az, bz));
+    const float t1 = fminf(fminf(fminf(CRT_FLT_MAX, fmaxf(ax, bx)), fmaxf(ay, by)), fmaxf(az, bz));
+    bool pass = !(t0 > t1);
+    if (CULL) {
+      const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
+      const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
+      pass = pass && !behind && !beyond;
+    }
+    pass = pass && __float_as_uint(q1.z) != CRT_INVALID;
+    m |= pass ? (1u << k) : 0u;
+  }
+  return m;
+}
+
+// One step inside a mesh tree for a lane with wcur valid and no pending triangles: take the next passing entry of the
+// current wide node (popping the stack when the node is used up); a leaf entry parks the lane with its triangle range,
+// an inner entry is descended into and its four entries are tested.  Returns true while the lane can take another step.
+template <bool CULL>
+CRT_DI bool travw_fast(TravW &s, const DScene &sc, const Ray &r, uint32_t *stack, const float t_limit) {
+  if (s.mask == 0u) {
+    if (s.sp == 0u) {  // mesh tree finished
+      s.wcur = CRT_INVALID;
+      return false;
+    }
+    const uint32_t e = stack[(--s.sp) * CRT_TRAV_BLOCK];
+    s.wcur = e >> 4;
+    s.mask = e & 15u;  // never 0: only nodes with entries left are pushed
+  }
+  const uint32_t k = (uint32_t)__ffs((int)s.mask) - 1u;
+  s.mask &= s.mask - 1u;
+  const float4 q1 = __ldg(sc.wnodes + 8 * (size_t)s.wcur + 2 * k + 1);
+  const uint32_t a = __float_as_uint(q1.z), b = __float_as_uint(q1.w);
+  if (a & CRT_LEAF_FLAG) {
+    s.tref = b;
+    s.tend = b + (a & ~CRT_LEAF_FLAG);
+    return false;
+  }
+  if (s.mask) stack[(s.sp++) * CRT_TRAV_BLOCK] = (s.wcur << 4) | s.mask;
+  s.wcur = a;
+  s.mask = wide_test<CULL>(sc, a, r, t_limit);
+  return true;
+}
+
+// Everything outside the mesh trees for a lane with wcur invalid and no pending triangles: top-level tree steps, the
+// mesh list of a top-level leaf, the root test of the next mesh.  Same order of events as trav_step.
+template <bool SKIP_REFRACTIVE, bool CULL>
+CRT_DI int travw_slow(TravW &s, const DScene &sc, const Ray &r, const float t_limit) {
+  if (!s.below && s.top != sc.top_end) {
+    const uint32_t idx = s.top;
+    const float4 lo = __ldg(&sc.nodes[2 * (size_t)idx]);
+    const float4 hi = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
+    const uint32_t a = __float_as_uint(lo.w);
+    const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
+    float t0, t1;
+    bool pass = slab_test(lo, hi, r, t0, t1);
+    if (CULL) {
+      const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
+      const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
+      pass = pass && !behind && !beyond;
+    }
+    s.top = (pass || leaf) ? idx + 1 : a;
+    if (pass && leaf) {
+      s.mref = __float_as_uint(hi.w);
+      s.mend = s.mref + (a & ~CRT_LEAF_FLAG);
+      s.resume = s.top;
+      s.below = 1u;
+    }
+    return TRAV_STEP;
+  }
+  if (s.mref != s.mend) {
+    const uint32_t m = __ldg(&sc.top_refs[s.mref++]);
+    const DMesh me = sc.meshes[m];
+    bool skip = (SKIP_REFRACTIVE && sc.materials[me.material].type == 3u) || me.wroot == CRT_INVALID;
+    if (sc.dedup_meshes) {
+      const unsigned long long bit = 1ull << (m & 63u);
+      skip = skip || (s.seen & bit) != 0ull;
+      s.seen |= bit;
+    }
+    if (!skip) {
+      // the root's own box (KDTree.cpp:53-57) = entry 0 of the mesh's root wide node
+      const float4 q0 = __ldg(sc.wnodes + 8 * (size_t)me.wroot), q1 = __ldg(sc.wnodes + 8 * (size_t)me.wroot + 1);
+      float t0, t1;
+      bool pass = slab_test(make_float4(q0.x, q0.y, q0.z, 0.f), make_float4(q0.w, q1.x, q1.y, 0.f), r, t0, t1);
+      if (CULL) {
+        const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
+        const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
+        pass = pass && !behind && !beyond;
+      }
+      s.sp = 0u;
+      s.mask = pass ? 1u : 0u;
+      if (pass) s.wcur = me.wroot;
+    }
+    return TRAV_STEP;
+  }
+  if (s.below) {
+    s.below = 0u;
+    s.top = s.resume;
     return TRAV_STEP;
   }
   return TRAV_DONE;

@@ -19,9 +19,6 @@
 namespace crtd {
 
 #define CRT_FULL_MASK 0xFFFFFFFFu
-#ifndef CRT_TRAV_BLOCK
-#define CRT_TRAV_BLOCK 256      // threads per CTA of the persistent traversal kernels
-#endif
 #ifndef CRT_TRAV_MIN_BLOCKS
 #define CRT_TRAV_MIN_BLOCKS 4   // resident CTAs per SM the register allocation is bounded for
 #endif
@@ -102,6 +99,24 @@ CRT_DI bool item_pixel(const Frame &fr, const DScene &sc, uint32_t item, uint32_
 //                Candidates are handed back to their owners in slot order, i.e. in the reference's encounter order
 //                (a lane has at most one pending leaf), so closest_offer sees exactly the sequence of KDTree.cpp:59-63.
 // ------------------------------------------------------------------------------------------------------------
+// CRT_PHASE_CLOCKS (debug builds for tools/ only): per-warp clock64 time spent in the refill / between-trees / node /
+// triangle phases of the MODE 2 kernels, plus iteration counts, summed into stats[8 + 8 * kernel + i] and printed by
+// crtb200_core.cu after every frame.
+#ifndef CRT_PHASE_CLOCKS
+#define CRT_PHASE_CLOCKS 0
+#endif
+#if CRT_PHASE_CLOCKS
+#define CRT_PC_DECL long long pc_t = clock64(); unsigned long long pc_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define CRT_PC_MARK(i) { const long long n_ = clock64(); pc_acc[i] += (unsigned long long)(n_ - pc_t); pc_t = n_; }
+#define CRT_PC_COUNT(i, v) { pc_acc[i] += (v); }
+#define CRT_PC_FLUSH(base) { if (lane_id() == 0) for (int i_ = 0; i_ < 8; i_++) atomicAdd(&lv.stats[(base) + i_], pc_acc[i_]); }
+#else
+#define CRT_PC_DECL
+#define CRT_PC_MARK(i)
+#define CRT_PC_COUNT(i, v)
+#define CRT_PC_FLUSH(base)
+#endif
+
 #ifndef CRT_TRI_CARRY
 #define CRT_TRI_CARRY 0  // tuning: deal out full 32-slot windows only, the remainder waits for the next triangle phase
 #endif
@@ -225,7 +240,10 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
   ray.flags = 0;
   trav_begin(tv, sc);
   closest_begin(cl);
+  CRT_PC_DECL
   for (;;) {
+    CRT_PC_MARK(4)
+    CRT_PC_COUNT(7, 1)
     const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !active);
     if (!exhausted && __popc(idle) >= REFILL) {
       const uint32_t want = __popc(idle);
@@ -264,6 +282,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
       continue;
     }
     if (MODE == 2) {
+      CRT_PC_MARK(0)
       // ---- between-trees bookkeeping for lanes whose cursor ran off a tree (rare) ----
       for (;;) {
         const bool slow = active && tv.tref == tv.tend && tv.cur == tv.cend;
@@ -274,18 +293,23 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
           active = false;
         }
       }
+      CRT_PC_MARK(1)
       // ---- node phase: one AABB step per iteration while enough lanes want one ----
       bool need = active && tv.tref == tv.tend;
       const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
       while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
+        CRT_PC_COUNT(5, 1)
         if (need) need = trav_fast<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t);
       }
+      CRT_PC_MARK(2)
       // ---- triangle phase: all pending leaves, packed across the warp ----
       const bool parked = active && tv.tref != tv.tend;
       if (__any_sync(CRT_FULL_MASK, parked)) {
         bool dummy = false;
+        CRT_PC_COUNT(6, 1)
         tri_phase<false, PRIMARY, COUNT>(sc, *ws, parked, !__any_sync(CRT_FULL_MASK, need), tv.tref, tv.tend, cl, dummy, n_tris);
       }
+      CRT_PC_MARK(3)
     } else if (MODE == 0) {
       // ---- node phase ----
       int st = active ? TRAV_STEP : TRAV_DONE;
@@ -335,6 +359,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
       }
     }
   }
+  CRT_PC_FLUSH(8)
   if (COUNT) {
     unsigned long long a = n_nodes, b = n_tris;
 #pragma unroll
@@ -587,7 +612,10 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
   ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
   ray.flags = 0;
   trav_begin(tv, sc);
+  CRT_PC_DECL
   for (;;) {
+    CRT_PC_MARK(4)
+    CRT_PC_COUNT(7, 1)
     const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !active);
     if (!exhausted && __popc(idle) >= REFILL) {
       const uint32_t want = __popc(idle);
@@ -618,6 +646,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
       continue;
     }
     if (MODE == 2) {
+      CRT_PC_MARK(0)
       for (;;) {
         const bool slow = active && tv.tref == tv.tend && tv.cur == tv.cend;
         if (!__any_sync(CRT_FULL_MASK, slow)) break;
@@ -626,13 +655,17 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
           active = false;
         }
       }
+      CRT_PC_MARK(1)
       bool need = active && tv.tref == tv.tend;
       const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
       while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
+        CRT_PC_COUNT(5, 1)
         if (need) need = trav_fast<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit);
       }
+      CRT_PC_MARK(2)
       const bool parked = active && tv.tref != tv.tend;
       if (__any_sync(CRT_FULL_MASK, parked)) {
+        CRT_PC_COUNT(6, 1)
         Closest unused;
         tri_phase<true, false, (COUNT != 0)>(sc, *ws, parked, !__any_sync(CRT_FULL_MASK, need), tv.tref, tv.tend, unused, occluded, n_tris);
         if (COUNT != 1 && active && occluded) {  // early termination: the rest of the walk cannot change the answer
@@ -641,6 +674,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
           active = false;
         }
       }
+      CRT_PC_MARK(3)
     } else if (MODE == 0) {
       int st = active ? TRAV_STEP : TRAV_DONE;
       while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
@@ -701,6 +735,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
       }
     }
   }
+  CRT_PC_FLUSH(16)
   if (COUNT) {
     unsigned long long a = n_nodes, b = n_tris;
 #pragma unroll
@@ -711,6 +746,163 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
     if (lane == 0) {
       atomicAdd(&lv.stats[6], a);
       atomicAdd(&lv.stats[7], b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2 / K3 on the 4-wide layout (MODE 3, the default when the uploaded trees nest; crt_device.cuh "wide walk").  Same
+// round structure as MODE 2 -- refill, between-trees bookkeeping, thresholded node phase, warp-cooperative triangle
+// phase -- but a node-phase step descends one wide node (four reference boxes from one 128-byte line), which cuts the
+// chain of dependent loads per ray ~3.5x and gives the four slab tests of a step to the scheduler as independent work.
+// No counters here: the counting modes measure the reference's binary visit-all walk and run the MODE 2 kernels.
+// ------------------------------------------------------------------------------------------------------------
+template <bool PRIMARY, int REFILL, bool CULL>
+__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest_w(const DScene sc, const Frame fr, const Levels lv,
+                                                                                const uint32_t level,
+                                                                                uint32_t *__restrict__ work_counter) {
+  __shared__ WarpShare s_ws[CRT_TRAV_BLOCK / 32];
+  __shared__ uint32_t s_stack[CRT_WIDE_STACK * CRT_TRAV_BLOCK];
+  WarpShare *ws = &s_ws[threadIdx.x >> 5];
+  uint32_t *stack = s_stack + threadIdx.x;
+  const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
+  const uint32_t node_base = lv.offset[level];
+  const uint32_t lane = lane_id();
+  bool active = false, exhausted = false;
+  uint32_t node = 0, n_tris = 0;
+  Ray ray;
+  TravW tv;
+  Closest cl;
+  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
+  ray.flags = 0;
+  travw_begin(tv, sc);
+  closest_begin(cl);
+  for (;;) {
+    const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !active);
+    if (!exhausted && __popc(idle) >= REFILL) {
+      const uint32_t want = __popc(idle);
+      uint32_t start = 0;
+      if (lane == 0) start = atomicAdd(work_counter, want);
+      start = __shfl_sync(CRT_FULL_MASK, start, 0);
+      if (start + want >= total) exhausted = true;
+      const uint32_t i = start + __popc(idle & lanemask_lt());
+      if (!active && i < total) {
+        bool valid = true;
+        if (PRIMARY) {
+          uint32_t row, col;
+          valid = item_pixel(fr, sc, fr.item_begin + i, row, col);
+          if (valid) primary_ray(fr.cam, sc.width, sc.height, row, col, ray.o, ray.d);
+        } else {
+          const float4 o = lv.ray_o[node_base - lv.offset[1] + i];
+          const float4 d = lv.ray_d[node_base - lv.offset[1] + i];
+          ray.o = mk(o.x, o.y, o.z);
+          ray.d = mk(d.x, d.y, d.z);
+        }
+        if (valid) {
+          ray_prepare(ray, PRIMARY);
+          travw_begin(tv, sc);
+          closest_begin(cl);
+          node = node_base + i;
+          active = true;
+          ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.f);
+          ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
+        }
+      }
+    }
+    if (!__any_sync(CRT_FULL_MASK, active)) {
+      if (exhausted) break;
+      continue;
+    }
+    for (;;) {  // between-trees bookkeeping
+      const bool slow = active && tv.tref == tv.tend && tv.wcur == CRT_INVALID;
+      if (!__any_sync(CRT_FULL_MASK, slow)) break;
+      if (slow && travw_slow<false, CULL>(tv, sc, ray, cl.min_t) == TRAV_DONE) {
+        lv.hit_tri[node] = cl.best_tri;
+        lv.hit_t[node] = cl.best_t;
+        active = false;
+      }
+    }
+    bool need = active && tv.tref == tv.tend;
+    const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
+    while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
+      if (need) need = travw_fast<CULL>(tv, sc, ray, stack, cl.min_t);
+    }
+    const bool parked = active && tv.tref != tv.tend;
+    if (__any_sync(CRT_FULL_MASK, parked)) {
+      bool dummy = false;
+      tri_phase<false, PRIMARY, false>(sc, *ws, parked, !__any_sync(CRT_FULL_MASK, need), tv.tref, tv.tend, cl, dummy, n_tris);
+    }
+  }
+}
+
+template <int REFILL, bool CULL>
+__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_w(const DScene sc, const Frame fr, const Levels lv,
+                                                                               uint32_t *__restrict__ work_counter) {
+  __shared__ WarpShare s_ws[CRT_TRAV_BLOCK / 32];
+  __shared__ uint32_t s_stack[CRT_WIDE_STACK * CRT_TRAV_BLOCK];
+  WarpShare *ws = &s_ws[threadIdx.x >> 5];
+  uint32_t *stack = s_stack + threadIdx.x;
+  const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];
+  const uint32_t total = n_hits * sc.n_lights;
+  const uint32_t lane = lane_id();
+  bool active = false, exhausted = false, occluded = false;
+  uint32_t slot = 0, n_tris = 0;
+  float dist = 0.0f, t_limit = 0.0f;
+  Ray ray;
+  TravW tv;
+  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
+  ray.flags = 0;
+  travw_begin(tv, sc);
+  for (;;) {
+    const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !active);
+    if (!exhausted && __popc(idle) >= REFILL) {
+      const uint32_t want = __popc(idle);
+      uint32_t start = 0;
+      if (lane == 0) start = atomicAdd(work_counter, want);
+      start = __shfl_sync(CRT_FULL_MASK, start, 0);
+      if (start + want >= total) exhausted = true;
+      const uint32_t i = start + __popc(idle & lanemask_lt());
+      if (!active && i < total) {
+        const uint32_t light = i / n_hits, hit = i - light * n_hits;
+        const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
+        float contrib;
+        shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
+        ray_prepare(ray, false);
+        travw_begin(tv, sc);
+        t_limit = fadd(fmul(dist, 1.0001f), 1e-4f);  // CULL only
+        occluded = false;
+        slot = hit * sc.n_lights + light;
+        active = true;
+        ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, dist);
+        ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
+      }
+    }
+    if (!__any_sync(CRT_FULL_MASK, active)) {
+      if (exhausted) break;
+      continue;
+    }
+    for (;;) {
+      const bool slow = active && tv.tref == tv.tend && tv.wcur == CRT_INVALID;
+      if (!__any_sync(CRT_FULL_MASK, slow)) break;
+      if (slow && travw_slow<true, CULL>(tv, sc, ray, t_limit) == TRAV_DONE) {
+        lv.vis[slot] = 1;  // an occluded ray never gets here: it retires in the triangle phase
+        active = false;
+      }
+    }
+    bool need = active && tv.tref == tv.tend;
+    const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
+    while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
+      if (need) need = travw_fast<CULL>(tv, sc, ray, stack, t_limit);
+    }
+    const bool parked = active && tv.tref != tv.tend;
+    if (__any_sync(CRT_FULL_MASK, parked)) {
+      Closest unused;
+      tri_phase<true, false, false>(sc, *ws, parked, !__any_sync(CRT_FULL_MASK, need), tv.tref, tv.tend, unused, occluded, n_tris);
+      if (active && occluded) {  // any-hit: the rest of the walk cannot change the answer
+        tv.tref = tv.tend = 0;
+        lv.vis[slot] = 0;
+        active = false;
+      }
     }
   }
 }

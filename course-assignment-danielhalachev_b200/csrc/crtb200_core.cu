@@ -75,7 +75,10 @@ struct crtb200_ctx {
 
   // scene
   DScene sc{};
-  DevBuf<float4> nodes, tri_geom, vtx_normal;
+  DevBuf<float4> nodes, wnodes, tri_geom, vtx_normal;
+  bool wide_ok = false;      // the 4-wide layout is usable (trees nest and are shallow enough)
+  bool use_wide = false;     // CRT_LAYOUT=wide: walk the 4-wide layout (MODE 3 kernels).  Measured equal to slightly slower
+                             // than the binary walk on every workload (profiles/r1_tuning.md), so it is opt-in
   DevBuf<uint32_t> leaf_refs, top_refs;
   DevBuf<uint4> tri_shade;
   DevBuf<float2> vtx_uv;
@@ -120,7 +123,7 @@ struct crtb200_ctx {
   uint32_t cap_depth = 0xFFFFFFFFu;
   uint32_t cap_sets = 0;
 
-  int blocks_closest = 0, blocks_shadow = 0;
+  int blocks_closest = 0, blocks_shadow = 0, blocks_closest_w = 0, blocks_shadow_w = 0;
   crtb200_stats last{};
   bool last_pending = false;
 };
@@ -166,10 +169,15 @@ int crtb200_create(int device, crtb200_ctx **out) {
   c->blocks_closest = std::max(1, occ) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest_w<true, CRT_REFILL, false>, CRT_TRAV_BLOCK, 0);
+  c->blocks_closest_w = std::max(1, occ) * c->sm_count;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_w<CRT_REFILL, false>, CRT_TRAV_BLOCK, 0);
+  c->blocks_shadow_w = std::max(1, occ) * c->sm_count;
   if (const char *env = getenv("CRT_BLOCKS_PER_SM")) {  // tuning only (tools/): resident persistent CTAs per SM
     const int b = atoi(env);
-    if (b > 0) c->blocks_closest = c->blocks_shadow = b * c->sm_count;
+    if (b > 0) c->blocks_closest = c->blocks_shadow = c->blocks_closest_w = c->blocks_shadow_w = b * c->sm_count;
   }
+  if (const char *env = getenv("CRT_LAYOUT")) c->use_wide = std::string(env) == "wide";
   *out = c;
   return CRTB200_OK;
 }
@@ -178,7 +186,7 @@ int crtb200_destroy(crtb200_ctx *c) {
   if (!c) return CRTB200_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->nodes.release(); c->tri_geom.release(); c->vtx_normal.release(); c->leaf_refs.release(); c->top_refs.release();
+  c->nodes.release(); c->wnodes.release(); c->tri_geom.release(); c->vtx_normal.release(); c->leaf_refs.release(); c->top_refs.release();
   c->tri_shade.release(); c->vtx_uv.release(); c->meshes.release(); c->materials.release(); c->textures.release();
   c->texels.release(); c->lights.release(); c->frame.release(); c->frame8.release(); c->hits.release();
   c->mask.release();
@@ -280,6 +288,97 @@ static bool relayout_tree(const crtb200_kdnode *nodes, uint32_t n, uint32_t out_
   return true;
 }
 
+// ---- host flattener H1b: reference tree -> 4-wide nodes (crt_device.cuh "wide walk") ---------------------------
+// Entry order inside a wide node = the reference's visiting order: child[1] (or its children) before child[0] (or its
+// children).  `ok` goes false when a child box is not contained plane-by-plane in its parent's (then the walk would
+// not be equivalent to the reference's) or when the collapsed tree is deeper than the device stack.
+struct WideBuild {
+  const crtb200_kdnode *nodes;
+  uint32_t ref_base;
+  std::vector<float4> *out;
+  bool ok;
+};
+static void wide_put(std::vector<float4> &out, uint32_t w, int k, const crtb200_kdnode &nd, uint32_t a, uint32_t b) {
+  float fa, fb;
+  std::memcpy(&fa, &a, 4);
+  std::memcpy(&fb, &b, 4);
+  out[8 * (size_t)w + 2 * k] = make_float4(nd.box_min[0], nd.box_min[1], nd.box_min[2], nd.box_max[0]);
+  out[8 * (size_t)w + 2 * k + 1] = make_float4(nd.box_max[1], nd.box_max[2], fa, fb);
+}
+static bool box_nested(const crtb200_kdnode &parent, const crtb200_kdnode &child) {
+  for (int k = 0; k < 3; k++)
+    if (!(child.box_min[k] >= parent.box_min[k]) || !(child.box_max[k] <= parent.box_max[k]) || !(child.box_min[k] <= child.box_max[k]))
+      return false;
+  return true;
+}
+static uint32_t wide_new(std::vector<float4> &out) {
+  const uint32_t w = (uint32_t)(out.size() / 8);
+  float inv;
+  const uint32_t bits = CRT_INVALID;
+  std::memcpy(&inv, &bits, 4);
+  out.resize(out.size() + 8, make_float4(0.f, 0.f, 0.f, 0.f));
+  for (int k = 0; k < 4; k++) out[8 * (size_t)w + 2 * k + 1].z = inv;  // absent
+  return w;
+}
+// wide node for the children of reference inner node i
+static uint32_t wide_build(WideBuild &wb, uint32_t i, uint32_t level) {
+  std::vector<float4> &out = *wb.out;
+  const uint32_t w = wide_new(out);
+  if (level >= CRT_WIDE_STACK) {
+    wb.ok = false;
+    return w;
+  }
+  uint32_t e[4];
+  int n = 0;
+  const crtb200_kdnode &p = wb.nodes[i];
+  for (int side = 1; side >= 0; side--) {
+    const uint32_t ch = p.child[side];
+    if (ch == CRTB200_INVALID) continue;
+    const crtb200_kdnode &cn = wb.nodes[ch];
+    if (!box_nested(p, cn)) wb.ok = false;
+    if (cn.leaf_count) {
+      e[n++] = ch;
+    } else {
+      for (int s2 = 1; s2 >= 0; s2--) {
+        const uint32_t g = cn.child[s2];
+        if (g == CRTB200_INVALID) continue;
+        if (!box_nested(cn, wb.nodes[g])) wb.ok = false;
+        e[n++] = g;
+      }
+    }
+  }
+  for (int k = 0; k < n && wb.ok; k++) {
+    const crtb200_kdnode &nd = wb.nodes[e[k]];
+    uint32_t a, b = 0;
+    if (nd.leaf_count) {
+      a = CRT_LEAF_FLAG | nd.leaf_count;
+      b = wb.ref_base + nd.leaf_start;
+    } else {
+      a = wide_build(wb, e[k], level + 1);
+    }
+    wide_put(out, w, k, nd, a, b);  // `out` may have grown: index, not reference
+  }
+  return w;
+}
+// returns the mesh's root wide node (one entry: the reference root), CRT_INVALID for an empty tree
+static uint32_t wide_build_mesh(WideBuild &wb, uint32_t n_nodes) {
+  if (n_nodes == 0) return CRT_INVALID;
+  std::vector<float4> &out = *wb.out;
+  const uint32_t w = wide_new(out);
+  const crtb200_kdnode &root = wb.nodes[0];
+  for (int k = 0; k < 3; k++)
+    if (!(root.box_min[k] <= root.box_max[k])) wb.ok = false;
+  uint32_t a, b = 0;
+  if (root.leaf_count) {
+    a = CRT_LEAF_FLAG | root.leaf_count;
+    b = wb.ref_base + root.leaf_start;
+  } else {
+    a = wide_build(wb, 0, 1);
+  }
+  wide_put(out, w, 0, wb.nodes[0], a, b);
+  return w;
+}
+
 int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   if (!c || !s) return fail(CRTB200_ERR_ARG, "null argument");
   if (s->abi_version != CRTB200_ABI_VERSION) return fail(CRTB200_ERR_ARG, "crtb200_scene.abi_version mismatch");
@@ -318,7 +417,8 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
     shade[t] = make_uint4(iv[0], iv[1], iv[2], tri_mesh[t]);
   }
   // trees: mesh trees first, top-level tree last, one node array
-  std::vector<float4> nodes;
+  std::vector<float4> nodes, wnodes;
+  bool wide_ok = c->use_wide;  // the 4-wide copy of the trees is only built when it will be walked
   std::vector<uint32_t> refs(s->n_mesh_leaf_refs);
   std::vector<DMesh> meshes(s->n_meshes);
   uint32_t node_cursor = 0;
@@ -338,7 +438,13 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
     meshes[m].node_end = node_cursor + placed;
     meshes[m].material = me.material;
     meshes[m].first_triangle = me.first_triangle;
+    meshes[m].wroot = CRT_INVALID;
     node_cursor += placed;
+    if (wide_ok) {  // relayout_tree has validated the tree's shape
+      WideBuild wb{s->mesh_nodes + me.first_node, me.first_leaf_ref, &wnodes, true};
+      meshes[m].wroot = wide_build_mesh(wb, me.n_nodes);
+      wide_ok = wb.ok && wnodes.size() / 8 < (1u << 28);
+    }
   }
   for (uint32_t k = 0; k < s->n_top_leaf_refs; k++)
     if (s->top_leaf_refs[k] >= s->n_meshes) return fail(CRTB200_ERR_SCENE, "top-level leaf reference out of range");
@@ -401,6 +507,9 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   std::vector<uint32_t> top_refs(s->top_leaf_refs, s->top_leaf_refs + s->n_top_leaf_refs);
 
   CUDA_TRY(c->nodes.upload(nodes));
+  if (!wide_ok) wnodes.clear();
+  CUDA_TRY(c->wnodes.upload(wnodes));
+  c->wide_ok = wide_ok;
   CUDA_TRY(c->leaf_refs.upload(refs));
   CUDA_TRY(c->top_refs.upload(top_refs));
   CUDA_TRY(c->tri_geom.upload(geom));
@@ -412,10 +521,11 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   CUDA_TRY(c->textures.upload(texs));
   CUDA_TRY(c->texels.upload(texels));
   CUDA_TRY(c->lights.upload(lights));
-  c->scene_bytes = nodes.size() * 16 + refs.size() * 4 + geom.size() * 16 + shade.size() * 16 + vn.size() * 16;
+  c->scene_bytes = nodes.size() * 16 + wnodes.size() * 16 + refs.size() * 4 + geom.size() * 16 + shade.size() * 16 + vn.size() * 16;
 
   DScene &d = c->sc;
   d.nodes = c->nodes.p;
+  d.wnodes = c->wnodes.p;
   d.leaf_refs = c->leaf_refs.p;
   d.top_refs = c->top_refs.p;
   d.tri_geom = c->tri_geom.p;
@@ -440,7 +550,7 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   CUDA_TRY(cudaMemset(c->frame.p, 0, px * 3 * sizeof(float)));  // colorBuffer starts at (0,0,0), RayTracer.cpp:47-50
   CUDA_TRY(c->frame8.ensure(px * 3));
   CUDA_TRY(cudaMemset(c->frame8.p, 0, px * 3));
-  CUDA_TRY(c->stats_dev.ensure(8));
+  CUDA_TRY(c->stats_dev.ensure(24));
   c->mask_valid = false;
   c->cap_items = 0;
   c->have_scene = true;
@@ -578,6 +688,15 @@ static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const 
     k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
 }
 
+template <bool CULL>
+static void launch_closest_w(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, uint32_t *work,
+                             cudaStream_t st) {
+  if (primary)
+    k_closest_w<true, CRT_REFILL, CULL><<<c->blocks_closest_w, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
+  else
+    k_closest_w<false, CRT_REFILL, CULL><<<c->blocks_closest_w, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
+}
+
 // Host destinations of crtb200_render: each chunk's band of rows is copied back on the chunk's own stream right after
 // its k_store, so the device->host copy of band k overlaps the traversal of the other chunks.
 struct HostOut {
@@ -598,6 +717,8 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   if (o->traversal == 1 && o->count_work == 1)
     return fail(CRTB200_ERR_ARG, "count_work = 1 counts the reference's visit-all work and needs traversal = 0");
   const bool cull = o->traversal == 1;
+  // opt-in 4-wide walk (CRT_LAYOUT=wide); the counting modes always measure the reference's binary visit-all walk
+  const bool wide = c->use_wide && c->wide_ok && o->count_work == 0;
   const uint32_t shard_count = o->shard_count ? o->shard_count : 1;
   if (o->shard_index >= shard_count) return fail(CRTB200_ERR_ARG, "shard_index >= shard_count");
   int rc = plan_mask(c, o);
@@ -625,7 +746,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   const uint32_t levels = secondary ? o->max_depth + 1 : 1;
   const int grid_simple = c->sm_count * 8;
 
-  CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 8 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 24 * sizeof(unsigned long long), st));
   c->kev_used = 0;
   c->kev_kind.clear();
   if (timed) CUDA_TRY(cudaEventRecord(c->ev[0], st));
@@ -648,7 +769,11 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
         cudaEventRecord(next_event(c), qs);
         c->kev_kind.push_back(0);
       }
-      if (o->count_work && cull)
+      if (wide && cull)
+        launch_closest_w<true>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
+      else if (wide)
+        launch_closest_w<false>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
+      else if (o->count_work && cull)
         launch_closest<true, true>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
       else if (o->count_work)
         launch_closest<true, false>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
@@ -665,7 +790,11 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       c->kev_kind.push_back(1);
     }
     uint32_t *swork = q.work.p + CRT_MAX_LEVELS;
-    if (o->count_work == 1)
+    if (wide && cull)
+      k_shadow_w<CRT_REFILL, true><<<c->blocks_shadow_w, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+    else if (wide)
+      k_shadow_w<CRT_REFILL, false><<<c->blocks_shadow_w, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+    else if (o->count_work == 1)
       k_shadow<1, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else if (o->count_work == 2 && cull)
       k_shadow<2, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
@@ -705,8 +834,17 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
 }
 
 static int collect_stats(crtb200_ctx *c, bool timed) {
-  unsigned long long st[8];
+  unsigned long long st[24];
   CUDA_TRY(cudaMemcpy(st, c->stats_dev.p, sizeof(st), cudaMemcpyDeviceToHost));
+#if CRT_PHASE_CLOCKS
+  for (int k = 0; k < 2; k++) {
+    const unsigned long long *p = st + 8 + 8 * k;
+    const double tot = (double)(p[0] + p[1] + p[2] + p[3] + p[4]);
+    fprintf(stderr, "[phase clocks] %s: refill %.1f%% slow %.1f%% node %.1f%% tri %.1f%% other %.1f%% | node iterations %llu, tri phases %llu, rounds %llu\n",
+            k ? "k_shadow " : "k_closest", 100.0 * p[0] / tot, 100.0 * p[1] / tot, 100.0 * p[2] / tot, 100.0 * p[3] / tot, 100.0 * p[4] / tot,
+            p[5], p[6], p[7]);
+  }
+#endif
   c->last.rays_primary = st[0];
   c->last.rays_shadow = st[1];
   c->last.rays_reflection = st[2];

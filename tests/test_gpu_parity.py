@@ -179,3 +179,68 @@ def test_dedup_does_less_work_than_visit_all_with_same_pixels(gpu, loaded, crt):
     b, _, _, real = gpu.render(sf.camera(), crt.make_options(count_work=2))
     assert same_f32(a, b).all()
     assert real["node_tests"] < visit_all["node_tests"] and real["triangle_tests"] < visit_all["triangle_tests"]
+
+
+@pytest.mark.parametrize("name", list(SMALL_SCENES))
+def test_production_path_matches_golden(name, gpu, loaded, crt):
+    """count_work = 0 is what bench.py times: any-hit shadow rays, one walk per mesh, MODE 2 loops (thresholded node
+    phase + warp-cooperative triangle phase).  Same bar as the counting mode: bit-identical to the reference fixtures."""
+    sf, flat, rects, n = loaded[name]
+    gpu.upload(flat, keepalive=sf)
+    rgb, rgb8, hits, st = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n), want_rgb8=True, want_hits=True)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cov = _covered(sf, rects, n)
+    assert np.array_equal(hits["mesh"][cov], g["hits"]["mesh"][cov]) and np.array_equal(hits["triangle"][cov], g["hits"]["triangle"][cov])
+    h = cov & (g["hits"]["mesh"] >= 0)
+    assert same_f32(hits["t"][h], g["hits"]["t"][h]).all()
+    _assert_pixels(name, rgb, g["rgb"], rgb8, g["ppm"])
+    assert [st["rays_primary"], st["rays_shadow"], st["rays_reflection"], st["rays_refraction"]] == list(g["rays"])
+
+
+@pytest.fixture(scope="module")
+def gpu_wide(built):
+    """A context that walks the opt-in 4-wide layout (CRT_LAYOUT is read by crtb200_create)."""
+    os.environ["CRT_LAYOUT"] = "wide"
+    try:
+        ctx = built.Context(0)
+    finally:
+        del os.environ["CRT_LAYOUT"]
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", list(SMALL_SCENES))
+def test_wide_layout_matches_golden(name, gpu_wide, loaded, crt):
+    """The 4-wide collapse of the reference trees (crt_device.cuh "wide walk") enumerates the same candidates in the same
+    order: hit ids, t and float RGB bit-identical to the reference fixtures, NaN-ray scene included."""
+    sf, flat, rects, n = loaded[name]
+    gpu_wide.upload(flat, keepalive=sf)
+    for traversal in (0, 1):
+        if traversal == 1 and name == "degenerate_uv":
+            continue
+        rgb, rgb8, hits, st = gpu_wide.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=traversal),
+                                              want_rgb8=True, want_hits=True)
+        g = np.load(os.path.join(GOLDEN, name + ".npz"))
+        cov = _covered(sf, rects, n)
+        assert np.array_equal(hits["mesh"][cov], g["hits"]["mesh"][cov]) and np.array_equal(hits["triangle"][cov], g["hits"]["triangle"][cov])
+        _assert_pixels(name, rgb, g["rgb"], rgb8, g["ppm"])
+        assert [st["rays_primary"], st["rays_shadow"], st["rays_reflection"], st["rays_refraction"]] == list(g["rays"])
+
+
+def test_wide_layout_falls_back_when_boxes_do_not_nest(gpu_wide, built, scene_dir, ob, crt):
+    """The wide walk is only equivalent to the reference's when every child box lies inside its parent's.  A caller may
+    upload any tree through the C ABI: shrink one inner box so its children stick out -> the library must keep walking
+    the binary layout, i.e. still agree with the oracle run on the very same (odd) tree."""
+    sf = built.SceneFile("hw14_small.crtscene", scene_dir)
+    flat = sf.flatten()
+    s = flat.contents
+    big = max(range(s.n_meshes), key=lambda m: s.meshes[m].n_nodes)
+    root = s.mesh_nodes[s.meshes[big].first_node]
+    assert root.leaf_count == 0
+    root.box_min[0] += 0.25 * (root.box_max[0] - root.box_min[0])  # children keep the old min.x: no longer nested
+    gpu_wide.upload(flat, keepalive=sf)
+    rgb, _, hits, st = gpu_wide.render(sf.camera(), crt.make_options(), want_hits=True)
+    o_rgb, o_hits, o_st = ob.render(flat, sf.camera(), crt.make_options())
+    assert np.array_equal(hits["mesh"], o_hits["mesh"]) and np.array_equal(hits["triangle"], o_hits["triangle"])
+    assert same_f32(rgb, o_rgb).all()
+    assert st["rays_total"] == o_st["rays_total"]
