@@ -75,11 +75,21 @@ struct crtb200_ctx {
 
   // scene
   DScene sc{};
-  DevBuf<float4> nodes, wnodes, tri_geom, vtx_normal;
+  // nodes / leaf_refs / tri_geom (everything the traversal kernels chase) live in ONE allocation so that a single L2
+  // access-policy window can mark them persisting: the ~1 GB of ray / hit / colour queues a 4K frame streams through
+  // the 126 MB L2 then stops evicting the scene between and during the traversal kernels
+  DevBuf<uint8_t> arena;
+  float4 *nodes_p = nullptr, *tri_geom_p = nullptr;
+  uint32_t *leaf_refs_p = nullptr;
+  size_t arena_used = 0;
+  size_t l2_persist_max = 0, l2_window_max = 0;
+  int l2_persist = 0;  // CRT_L2_PERSIST: 0 off (default, measured best), 1 arena persisting / rest of it streaming, 2 arena persisting / normal, 3 nodes only
+  size_t nodes_bytes = 0;
+  DevBuf<float4> wnodes, vtx_normal;
   bool wide_ok = false;      // the 4-wide layout is usable (trees nest and are shallow enough)
   bool use_wide = false;     // CRT_LAYOUT=wide: walk the 4-wide layout (MODE 3 kernels).  Measured equal to slightly slower
                              // than the binary walk on every workload (profiles/r1_tuning.md), so it is opt-in
-  DevBuf<uint32_t> leaf_refs, top_refs;
+  DevBuf<uint32_t> top_refs;
   DevBuf<uint4> tri_shade;
   DevBuf<float2> vtx_uv;
   DevBuf<DMesh> meshes;
@@ -178,6 +188,14 @@ int crtb200_create(int device, crtb200_ctx **out) {
     if (b > 0) c->blocks_closest = c->blocks_shadow = c->blocks_closest_w = c->blocks_shadow_w = b * c->sm_count;
   }
   if (const char *env = getenv("CRT_LAYOUT")) c->use_wide = std::string(env) == "wide";
+  if (const char *env = getenv("CRT_L2_PERSIST")) c->l2_persist = atoi(env);
+  c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
+  c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
+  if (c->l2_persist && c->l2_persist_max)
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_max);  // best effort: a refusal only loses the hint
+  if (getenv("CRT_VERBOSE"))
+    fprintf(stderr, "[crtb200] %s: %d SMs, L2 %d MiB, persisting L2 max %zu MiB, access-policy window max %zu MiB, persist %s\n", prop.name,
+            prop.multiProcessorCount, prop.l2CacheSize >> 20, c->l2_persist_max >> 20, c->l2_window_max >> 20, c->l2_persist ? "on" : "off");
   *out = c;
   return CRTB200_OK;
 }
@@ -186,7 +204,7 @@ int crtb200_destroy(crtb200_ctx *c) {
   if (!c) return CRTB200_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->nodes.release(); c->wnodes.release(); c->tri_geom.release(); c->vtx_normal.release(); c->leaf_refs.release(); c->top_refs.release();
+  c->arena.release(); c->wnodes.release(); c->vtx_normal.release(); c->top_refs.release();
   c->tri_shade.release(); c->vtx_uv.release(); c->meshes.release(); c->materials.release(); c->textures.release();
   c->texels.release(); c->lights.release(); c->frame.release(); c->frame8.release(); c->hits.release();
   c->mask.release();
@@ -506,13 +524,24 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   }
   std::vector<uint32_t> top_refs(s->top_leaf_refs, s->top_leaf_refs + s->n_top_leaf_refs);
 
-  CUDA_TRY(c->nodes.upload(nodes));
+  {
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t b_nodes = al(nodes.size() * sizeof(float4)), b_refs = al(refs.size() * sizeof(uint32_t)),
+                 b_geom = al(geom.size() * sizeof(float4));
+    c->arena_used = b_nodes + b_refs + b_geom;
+    c->nodes_bytes = b_nodes;
+    CUDA_TRY(c->arena.ensure(std::max<size_t>(c->arena_used, 256)));
+    c->nodes_p = reinterpret_cast<float4 *>(c->arena.p);
+    c->leaf_refs_p = reinterpret_cast<uint32_t *>(c->arena.p + b_nodes);
+    c->tri_geom_p = reinterpret_cast<float4 *>(c->arena.p + b_nodes + b_refs);
+    if (!nodes.empty()) CUDA_TRY(cudaMemcpy(c->nodes_p, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    if (!refs.empty()) CUDA_TRY(cudaMemcpy(c->leaf_refs_p, refs.data(), refs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!geom.empty()) CUDA_TRY(cudaMemcpy(c->tri_geom_p, geom.data(), geom.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  }
   if (!wide_ok) wnodes.clear();
   CUDA_TRY(c->wnodes.upload(wnodes));
   c->wide_ok = wide_ok;
-  CUDA_TRY(c->leaf_refs.upload(refs));
   CUDA_TRY(c->top_refs.upload(top_refs));
-  CUDA_TRY(c->tri_geom.upload(geom));
   CUDA_TRY(c->tri_shade.upload(shade));
   CUDA_TRY(c->vtx_normal.upload(vn));
   if (!uv.empty()) CUDA_TRY(c->vtx_uv.upload(uv));
@@ -524,11 +553,11 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   c->scene_bytes = nodes.size() * 16 + wnodes.size() * 16 + refs.size() * 4 + geom.size() * 16 + shade.size() * 16 + vn.size() * 16;
 
   DScene &d = c->sc;
-  d.nodes = c->nodes.p;
+  d.nodes = c->nodes_p;
   d.wnodes = c->wnodes.p;
-  d.leaf_refs = c->leaf_refs.p;
+  d.leaf_refs = c->leaf_refs_p;
   d.top_refs = c->top_refs.p;
-  d.tri_geom = c->tri_geom.p;
+  d.tri_geom = c->tri_geom_p;
   d.tri_shade = c->tri_shade.p;
   d.vtx_normal = c->vtx_normal.p;
   d.vtx_uv = uv.empty() ? nullptr : c->vtx_uv.p;
@@ -579,6 +608,21 @@ static uint32_t branching_sum(const crtb200_ctx *c, uint32_t max_depth, uint64_t
   return (uint32_t)std::min<uint64_t>(sum, 0xFFFFFFFFull);
 }
 
+// Marks the scene arena as L2-persisting for the kernels of `st` (one access-policy window per stream).  When the arena
+// is larger than the persisting carve-out, hitRatio makes a matching fraction of its lines persist instead of thrashing.
+static void apply_l2_window(crtb200_ctx *c, cudaStream_t st) {
+  if (!c->l2_persist || !c->l2_persist_max || !c->l2_window_max || !c->arena_used) return;
+  cudaStreamAttrValue v{};
+  const size_t bytes = std::min(c->l2_persist == 3 ? c->nodes_bytes : c->arena_used, c->l2_window_max);
+  v.accessPolicyWindow.base_ptr = c->arena.p;
+  v.accessPolicyWindow.num_bytes = bytes;
+  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_persist_max / (double)bytes);
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = c->l2_persist == 1 ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+  cudaGetLastError();  // a hint: never an error of the render
+}
+
 static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth, uint32_t row_items, bool pipelined) {
   uint64_t per_level[CRT_MAX_LEVELS] = {0};
   branching_sum(c, max_depth, per_level);
@@ -607,6 +651,7 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
   for (uint32_t k = 0; k < n_sets; k++) {
     crtb200_ctx::QueueSet &q = c->sets[k];
     if (!q.stream) CUDA_TRY(cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking));
+    apply_l2_window(c, q.stream);
     if (!q.done) CUDA_TRY(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
     uint64_t total = 0;
     for (uint32_t l = 0; l <= max_depth; l++) {
