@@ -90,6 +90,9 @@ struct DCamera {
 #ifndef CRT_TRAV_BLOCK
 #define CRT_TRAV_BLOCK 256      // threads per CTA of the persistent traversal kernels
 #endif
+#ifndef CRT_NODE_PAIR
+#define CRT_NODE_PAIR 1  // MODE 2 node phase: test nodes idx and idx + 1 together (trav_fast2)
+#endif
 #ifndef CRT_PREFETCH_SKIP
 #define CRT_PREFETCH_SKIP 0  // tuning: prefetch a node's skip target into L1 as soon as the node arrives
 #endif
@@ -397,6 +400,54 @@ CRT_DI bool trav_fast(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_te
   }
   return s.cur != s.cend;
 }
+// trav_fast for two consecutive nodes at once (CRT_NODE_PAIR).  Node idx + 1 is the next node of the walk whenever
+// node idx passes or is a leaf -- about 56 % of the steps on the 1 M-triangle scene -- so its box is loaded and tested
+// together with node idx's: two independent load + ALU chains per iteration instead of one, and 1.5x fewer iterations
+// of a loop whose iteration time is the latency of the slowest lane's load.  When node idx fails (an inner node) the
+// second test is simply discarded; testing a node the reference would not have reached cannot change the walk,
+// because only the pass / fail of nodes that ARE reached is acted on.
+template <bool COUNT, bool CULL>
+CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float t_limit) {
+  const uint32_t idx = s.cur;
+  const bool has2 = idx + 1u != s.cend;
+  const uint32_t jdx = has2 ? idx + 1u : idx;
+  const float4 lo0 = __ldg(&sc.nodes[2 * (size_t)idx]), hi0 = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
+  const float4 lo1 = __ldg(&sc.nodes[2 * (size_t)jdx]), hi1 = __ldg(&sc.nodes[2 * (size_t)jdx + 1]);
+  float t00, t01, t10, t11;
+  bool pass0 = slab_test(lo0, hi0, r, t00, t01);
+  bool pass1 = slab_test(lo1, hi1, r, t10, t11);
+  if (CULL) {
+    const float lim = fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
+    pass0 = pass0 && !(t01 < -(1e-5f * (fabsf(t00) + fabsf(t01)))) && !(t00 > lim);
+    pass1 = pass1 && !(t11 < -(1e-5f * (fabsf(t10) + fabsf(t11)))) && !(t10 > lim);
+  }
+  const uint32_t a0 = __float_as_uint(lo0.w), a1 = __float_as_uint(lo1.w);
+  const bool leaf0 = (a0 & CRT_LEAF_FLAG) != 0u, leaf1 = (a1 & CRT_LEAF_FLAG) != 0u;
+  if (COUNT) node_tests++;
+  // which of the two nodes decides where the walk goes: the second one iff the first is stepped over (inner + pass, or a
+  // failing leaf) and a second one exists
+  const bool second = has2 && (pass0 != leaf0);
+  if (COUNT && second) node_tests++;
+  const uint32_t a = second ? a1 : a0, b = __float_as_uint(second ? hi1.w : hi0.w), at = second ? idx + 1u : idx;
+  const bool pass = second ? pass1 : pass0, leaf = second ? leaf1 : leaf0;
+  s.cur = (pass || leaf) ? at + 1u : a;
+  if (pass && leaf) {
+    const uint32_t first = b, last = first + (a & ~CRT_LEAF_FLAG);
+    if (s.below) {
+      s.tref = first;
+      s.tend = last;
+    } else {
+      s.mref = first;
+      s.mend = last;
+      s.resume = s.cur;
+      s.cur = s.cend;
+      s.below = 1u;
+    }
+    return false;
+  }
+  return s.cur != s.cend;
+}
+
 template <bool SKIP_REFRACTIVE, bool DEDUP>
 CRT_DI int trav_slow(Trav &s, const DScene &sc) {
   if (s.mref != s.mend) {

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
       const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
       while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
         CRT_PC_COUNT(5, 1)
-        if (need) need = trav_fast<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t);
+        if (need) need = CRT_NODE_PAIR ? trav_fast2<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t) : trav_fast<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t);
       }
       CRT_PC_MARK(2)
       // ---- triangle phase: all pending leaves, packed across the warp ----
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
       const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
       while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
         CRT_PC_COUNT(5, 1)
-        if (need) need = trav_fast<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit);
+        if (need) need = CRT_NODE_PAIR ? trav_fast2<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit) : trav_fast<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit);
       }
       CRT_PC_MARK(2)
       const bool parked = active && tv.tref != tv.tend;
