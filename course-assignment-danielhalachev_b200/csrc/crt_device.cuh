@@ -278,6 +278,7 @@ struct Trav {
   uint32_t tref, tend;    // cursor in the current mesh leaf's triangle list
   uint32_t below;         // 1 while working below a top-level leaf (mesh list / mesh trees)
   unsigned long long seen;  // meshes already traversed for this ray (scenes with <= 64 meshes)
+  uint32_t leaf;          // node index of the pending leaf (trav_fast2): encounter-order key for split walks
 };
 CRT_DI void trav_begin(Trav &s, const DScene &sc) {
   s.cur = sc.top_begin;
@@ -287,6 +288,7 @@ CRT_DI void trav_begin(Trav &s, const DScene &sc) {
   s.tref = s.tend = 0;
   s.below = 0;
   s.seen = 0ull;
+  s.leaf = 0;
 }
 
 // One traversal micro-step.  Returns 0 = keep stepping, 1 = a triangle list is pending (tref..tend), 2 = traversal
@@ -398,7 +400,7 @@ CRT_DI bool trav_fast(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_te
     }
     return false;
   }
-  return s.cur != s.cend;
+  return s.cur < s.cend;  // '<': a skip link may jump past the end of a range that was split off (k_*_s kernels)
 }
 // trav_fast for two consecutive nodes at once (CRT_NODE_PAIR).  Node idx + 1 is the next node of the walk whenever
 // node idx passes or is a leaf -- about 56 % of the steps on the 1 M-triangle scene -- so its box is loaded and tested
@@ -409,7 +411,7 @@ CRT_DI bool trav_fast(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_te
 template <bool COUNT, bool CULL>
 CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float t_limit) {
   const uint32_t idx = s.cur;
-  const bool has2 = idx + 1u != s.cend;
+  const bool has2 = idx + 1u < s.cend;
   const uint32_t jdx = has2 ? idx + 1u : idx;
   const float4 lo0 = __ldg(&sc.nodes[2 * (size_t)idx]), hi0 = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
   const float4 lo1 = __ldg(&sc.nodes[2 * (size_t)jdx]), hi1 = __ldg(&sc.nodes[2 * (size_t)jdx + 1]);
@@ -443,9 +445,10 @@ CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_t
       s.cur = s.cend;
       s.below = 1u;
     }
+    s.leaf = at;
     return false;
   }
-  return s.cur != s.cend;
+  return s.cur < s.cend;
 }
 
 template <bool SKIP_REFRACTIVE, bool DEDUP>

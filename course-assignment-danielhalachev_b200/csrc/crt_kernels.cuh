@@ -106,11 +106,32 @@ CRT_DI bool item_pixel(const Frame &fr, const DScene &sc, uint32_t item, uint32_
 #define CRT_PHASE_CLOCKS 0
 #endif
 #if CRT_PHASE_CLOCKS
-#define CRT_PC_DECL long long pc_t = clock64(); unsigned long long pc_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+CRT_DI unsigned long long crt_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ unsigned long long g_warp_rec[2][8192][6];  // per warp: start, end (globaltimer ns), rounds, node iterations, time after dry, stolen
+__device__ unsigned long long g_tail[2][2];
+__device__ unsigned long long g_iter_hist[2][32];  // debug: rays by floor(log2(node-phase iterations + 1)), [0] closest [1] shadow
+#define CRT_PC_RAY_DONE(k, it) { atomicAdd(&g_iter_hist[k][31 - __clz((int)(it) + 1)], 1ull); }
+#define CRT_PC_DECL long long pc_t = clock64(); unsigned long long pc_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const unsigned long long pc_g0 = crt_globaltimer(); \
+  long long pc_tail_t = 0; unsigned long long pc_tail_time = 0, pc_tail_lanes = 0;
+// after the work queue is exhausted: wall time of the warp's remaining life and busy-lane x time within it
+#define CRT_PC_TAIL(exh, act) { if (exh) { const long long n_ = clock64(); if (pc_tail_t) { pc_tail_time += (unsigned long long)(n_ - pc_tail_t); \
+  pc_tail_lanes += (unsigned long long)(n_ - pc_tail_t) * __popc(__ballot_sync(CRT_FULL_MASK, act)); } pc_tail_t = n_; } }
 #define CRT_PC_MARK(i) { const long long n_ = clock64(); pc_acc[i] += (unsigned long long)(n_ - pc_t); pc_t = n_; }
 #define CRT_PC_COUNT(i, v) { pc_acc[i] += (v); }
-#define CRT_PC_FLUSH(base) { if (lane_id() == 0) for (int i_ = 0; i_ < 8; i_++) atomicAdd(&lv.stats[(base) + i_], pc_acc[i_]); }
+#define CRT_PC_FLUSH(base) { if (lane_id() == 0) { for (int i_ = 0; i_ < 8; i_++) atomicAdd(&lv.stats[(base) + i_], pc_acc[i_]); \
+    const unsigned long long g1_ = crt_globaltimer(); const int kb_ = 24 + ((base) - 8) / 2; /* 24.. closest, 28.. shadow */ \
+    atomicAdd(&lv.stats[kb_], g1_ - pc_g0); atomicAdd(&lv.stats[kb_ + 1], 1ull); atomicMax(&lv.stats[kb_ + 2], g1_); \
+    atomicMin(&lv.stats[kb_ + 3], pc_g0 ? pc_g0 : 1ull); \
+    atomicAdd(&g_tail[((base) - 8) / 8][0], pc_tail_time); atomicAdd(&g_tail[((base) - 8) / 8][1], pc_tail_lanes); \
+    const uint32_t w_ = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; if (w_ < 8192u) { unsigned long long *r_ = g_warp_rec[((base) - 8) / 8][w_]; \
+      r_[0] = pc_g0; r_[1] = g1_; r_[2] = pc_acc[7]; r_[3] = pc_acc[5]; r_[4] = pc_tail_time; r_[5] = pc_acc[6]; } } }
 #else
+#define CRT_PC_TAIL(exh, act)
+#define CRT_PC_RAY_DONE(k, it)
 #define CRT_PC_DECL
 #define CRT_PC_MARK(i)
 #define CRT_PC_COUNT(i, v)
@@ -232,6 +253,9 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
   const uint32_t lane = lane_id();
   bool active = false, exhausted = false;
   uint32_t node = 0, n_nodes = 0, n_tris = 0;
+#if CRT_PHASE_CLOCKS
+  uint32_t ray_iters = 0;
+#endif
   Ray ray;
   Trav tv;
   Closest cl;
@@ -270,6 +294,9 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
           closest_begin(cl);
           node = node_base + i;
           active = true;
+#if CRT_PHASE_CLOCKS
+          ray_iters = 0;
+#endif
           if (MODE == 2) {
             ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.f);
             ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
@@ -283,6 +310,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
     }
     if (MODE == 2) {
       CRT_PC_MARK(0)
+      CRT_PC_TAIL(exhausted, active)
       // ---- between-trees bookkeeping for lanes whose cursor ran off a tree (rare) ----
       for (;;) {
         const bool slow = active && tv.tref == tv.tend && tv.cur == tv.cend;
@@ -291,6 +319,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
           lv.hit_tri[node] = cl.best_tri;
           lv.hit_t[node] = cl.best_t;
           active = false;
+          CRT_PC_RAY_DONE(0, ray_iters)
         }
       }
       CRT_PC_MARK(1)
@@ -299,6 +328,9 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
       const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
       while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
         CRT_PC_COUNT(5, 1)
+#if CRT_PHASE_CLOCKS
+        if (need) ray_iters++;
+#endif
         if (need) need = CRT_NODE_PAIR ? trav_fast2<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t) : trav_fast<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t);
       }
       CRT_PC_MARK(2)
@@ -606,6 +638,9 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
   const uint32_t lane = lane_id();
   bool active = false, exhausted = false, occluded = false;
   uint32_t slot = 0, n_nodes = 0, n_tris = 0;
+#if CRT_PHASE_CLOCKS
+  uint32_t ray_iters = 0;
+#endif
   float dist = 0.0f, t_limit = 0.0f;
   Ray ray;
   Trav tv;
@@ -635,6 +670,9 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
         occluded = false;
         slot = hit * sc.n_lights + light;
         active = true;
+#if CRT_PHASE_CLOCKS
+        ray_iters = 0;
+#endif
         if (MODE == 2) {
           ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, dist);
           ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
@@ -647,12 +685,14 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
     }
     if (MODE == 2) {
       CRT_PC_MARK(0)
+      CRT_PC_TAIL(exhausted, active)
       for (;;) {
         const bool slow = active && tv.tref == tv.tend && tv.cur == tv.cend;
         if (!__any_sync(CRT_FULL_MASK, slow)) break;
         if (slow && trav_slow<true, (COUNT != 1)>(tv, sc) == TRAV_DONE) {
           lv.vis[slot] = occluded ? 0 : 1;
           active = false;
+          CRT_PC_RAY_DONE(1, ray_iters)
         }
       }
       CRT_PC_MARK(1)
@@ -660,6 +700,9 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
       const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
       while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
         CRT_PC_COUNT(5, 1)
+#if CRT_PHASE_CLOCKS
+        if (need) ray_iters++;
+#endif
         if (need) need = CRT_NODE_PAIR ? trav_fast2<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit) : trav_fast<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit);
       }
       CRT_PC_MARK(2)
@@ -672,6 +715,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
           tv.tref = tv.tend = 0;
           lv.vis[slot] = 0;
           active = false;
+          CRT_PC_RAY_DONE(1, ray_iters)
         }
       }
       CRT_PC_MARK(3)
@@ -905,6 +949,442 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2 / K3 with range stealing (the default for the timed path when the uploaded trees nest).
+//
+// Problem (profiles/r1_tuning.md, "tails"): a ray is walked by one lane, and 2-3 % of the rays need 256-1000 node-phase
+// iterations of ~1 us each.  Once the work queue is dry a warp is down to ~11 busy lanes and the kernel ends when the
+// last such ray does: 20-27 % of the kernel span at 4K on one GPU, and almost all of it when a frame is sharded 8 ways.
+//
+// Cure: the nesting property (crt_device.cuh "wide walk") makes ANY node index a valid place to start a sub-walk -- a
+// walk over nodes [m, e) finds exactly the passing leaves in [m, e), in order, whatever happened before m.  So, after
+// the queue has run dry, a lane whose cursor still has a long way to go hands the upper half [mid, cend) of its range
+// to an idle lane of its warp ("helper"), repeatedly, until everybody is busy.  Exactness of the result:
+//   shadow   the answer is an OR over candidates: helpers raise ws.occ[ray]; order is irrelevant.
+//   closest  the reference keeps "the first candidate unless a later one has strictly smaller t".  Every helper range
+//            lies after its donor's own remaining range in encounter order and inside the same mesh tree, so the owner
+//            (i) finishes its own part sequentially, (ii) waits at the end of that mesh tree until its helpers are done,
+//            (iii) folds their candidates in as if they had come next: helper candidates are reduced order-independently
+//            with the key (leaf node index, position in leaf) = encounter order: first candidate = minimal key,
+//            best = minimal (t, key) over candidates with t < inf.  Only then does the owner go on to the next mesh.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef CRT_MIN_SPLIT
+#define CRT_MIN_SPLIT 64  // nodes: ranges shorter than this are not split
+#endif
+#ifndef CRT_LONG_ITERS
+#define CRT_LONG_ITERS 96  // a walk becomes a donor once it has taken this many node-phase iterations
+#endif
+#ifndef CRT_SPLIT_SPAN
+#define CRT_SPLIT_SPAN 2048  // a donor keeps at most this many nodes ahead of its cursor (the work of a ray clusters near it)
+#endif
+
+struct __align__(16) WarpShareS {
+  float4 ro[32], rd[32];   // ray table (origin + w = light distance for shadow rays, direction), indexed by ray = owner lane
+  uint32_t refbase[32], owner[32];
+  uint32_t rayof[32];      // lane -> ray it is walking (itself, or the owner it helps)
+  uint32_t pend[32];       // ray -> helper ranges still being walked
+  uint32_t occ[32];        // shadow: ray is occluded
+  float best_t[32];        // closest: candidates found by the helpers of a ray since its last fold
+  uint32_t best_tri[32], first_tri[32];
+  float first_t[32];
+  unsigned long long best_key[32], first_key[32];
+};
+
+CRT_DI void acc_reset(WarpShareS &ws, uint32_t ray) {
+  ws.best_t[ray] = __int_as_float(0x7f800000);
+  ws.best_tri[ray] = CRT_INVALID;
+  ws.best_key[ray] = ~0ull;
+  ws.first_tri[ray] = CRT_INVALID;
+  ws.first_key[ray] = ~0ull;
+  ws.first_t[ray] = 0.0f;
+}
+// one candidate of a helper range (executed by one lane at a time)
+CRT_DI void acc_offer(WarpShareS &ws, uint32_t ray, uint32_t tri, float t, unsigned long long key) {
+  if (key < ws.first_key[ray]) {
+    ws.first_key[ray] = key;
+    ws.first_tri[ray] = tri;
+    ws.first_t[ray] = t;
+  }
+  const float bt = ws.best_t[ray];
+  if (t < __int_as_float(0x7f800000) && (t < bt || (!(bt < t) && key < ws.best_key[ray]))) {
+    ws.best_t[ray] = t;
+    ws.best_tri[ray] = tri;
+    ws.best_key[ray] = key;
+  }
+}
+// the owner folds its helpers' candidates in as the continuation of its own sequence (KDTree.cpp:75-86 semantics)
+CRT_DI void acc_fold(WarpShareS &ws, uint32_t ray, Closest &cl) {
+  const uint32_t ft = ws.first_tri[ray];
+  if (ft == CRT_INVALID) return;
+  if (cl.best_tri == CRT_INVALID) {
+    cl.best_tri = ft;
+    cl.best_t = ws.first_t[ray];
+  }
+  const float bt = ws.best_t[ray];
+  if (ws.best_tri[ray] != CRT_INVALID && bt < cl.min_t) {
+    cl.min_t = bt;
+    cl.best_t = bt;
+    cl.best_tri = ws.best_tri[ray];
+  }
+  acc_reset(ws, ray);
+}
+
+// tri_phase for the stealing kernels: the ray of a parked lane is ws.rayof[lane]; candidates of a helper go to the
+// owner's accumulator (closest) / occlusion flag (shadow) instead of the parking lane's registers.
+template <bool SHADOW, bool PRIMARY>
+CRT_DI void tri_phase_s(const DScene &sc, WarpShareS &ws, const bool pending, uint32_t &tref, const uint32_t tend, const bool helper,
+                        const uint32_t jown, const uint32_t leafnode, Closest &cl) {
+  const uint32_t lane = lane_id();
+  const uint32_t cnt = pending ? tend - tref : 0u;
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(CRT_FULL_MASK, incl, d);
+    if (lane >= (uint32_t)d) incl += v;
+  }
+  const uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
+  const uint32_t start = incl - cnt;
+  if (cnt) ws.refbase[lane] = tref - start;
+  for (uint32_t base = 0; base < total; base += 32u) {
+    const bool in_win = cnt && start < base + 32u && start + cnt > base;
+    const uint32_t hp = (in_win && start > base) ? start - base : 0u;
+    const uint32_t heads = __reduce_or_sync(CRT_FULL_MASK, in_win ? (1u << hp) : 0u);
+    if (in_win) ws.owner[hp] = lane;
+    __syncwarp();
+    const uint32_t g = base + lane;
+    bool hit = false;
+    float t = 0.0f;
+    uint32_t tri = 0, own = 0;
+    if (g < total) {
+      own = ws.owner[31 - __clz(heads & (CRT_FULL_MASK >> (31u - lane)))];
+      tri = __ldg(&sc.leaf_refs[ws.refbase[own] + g]);
+      const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
+      const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
+      const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+      const uint32_t ri = ws.rayof[own];
+      const float4 o4 = ws.ro[ri], d4 = ws.rd[ri];
+      Ray r;
+      r.o = mk(o4.x, o4.y, o4.z);
+      r.d = mk(d4.x, d4.y, d4.z);
+      r.flags = PRIMARY ? 8u : 0u;
+      V3 p;
+      hit = triangle_test(g0, g1, g2, r, t, p);
+      if (SHADOW) hit = hit && vlen(vsub(p, r.o)) <= o4.w;
+    }
+    uint32_t hm = __ballot_sync(CRT_FULL_MASK, hit);
+    while (hm) {
+      const int l = __ffs(hm) - 1;
+      hm &= hm - 1u;
+      const uint32_t o_l = __shfl_sync(CRT_FULL_MASK, own, l);
+      if (SHADOW) {
+        if (lane == o_l) ws.occ[jown] = 1u;
+      } else {
+        const uint32_t tri_l = __shfl_sync(CRT_FULL_MASK, tri, l);
+        const float t_l = __shfl_sync(CRT_FULL_MASK, t, l);
+        if (lane == o_l) {
+          if (helper)
+            acc_offer(ws, jown, tri_l, t_l, ((unsigned long long)leafnode << 32) | (unsigned long long)(base + (uint32_t)l - start));
+          else
+            closest_offer(cl, tri_l, t_l);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (cnt) tref = tend;
+}
+
+// Donation step (warp-uniform; only called once the work queue is dry).  job: 0 = nothing to walk, 1 = own ray,
+// 2 = helper range.  The i-th lane without a job takes the upper half of the i-th splittable range.
+CRT_DI void steal_step(WarpShareS &ws, Trav &tv, uint32_t &job, uint32_t &jown, uint32_t &iters, bool &took) {
+  const uint32_t lane = lane_id();
+  const bool avail = job == 0u;
+  const bool donor = job != 0u && iters >= (uint32_t)CRT_LONG_ITERS && tv.tref == tv.tend && tv.below != 0u && tv.cur < tv.cend &&
+                     (tv.cend - tv.cur) >= (uint32_t)CRT_MIN_SPLIT;
+  const uint32_t am = __ballot_sync(CRT_FULL_MASK, avail), dm = __ballot_sync(CRT_FULL_MASK, donor);
+  const int n = min(__popc(am), __popc(dm));
+  took = false;
+  if (n == 0) return;
+  const int ra = __popc(am & lanemask_lt()), rd = __popc(dm & lanemask_lt());
+  const bool give = donor && rd < n, take = avail && ra < n;
+  const uint32_t half = (tv.cend - tv.cur) >> 1;
+  const uint32_t mid = tv.cur + (half < (uint32_t)CRT_SPLIT_SPAN ? half : (uint32_t)CRT_SPLIT_SPAN);
+  const int partner = take ? (int)__fns(dm, 0, ra + 1) : (int)lane;
+  const uint32_t p_mid = __shfl_sync(CRT_FULL_MASK, mid, partner);
+  const uint32_t p_end = __shfl_sync(CRT_FULL_MASK, tv.cend, partner);
+  const uint32_t p_own = __shfl_sync(CRT_FULL_MASK, jown, partner);
+  if (give) {
+    tv.cend = mid;
+    atomicAdd(&ws.pend[jown], 1u);
+  }
+  if (take) {
+    job = 2u;
+    jown = p_own;
+    tv.cur = p_mid;
+    tv.cend = p_end;
+    tv.below = 1u;
+    tv.tref = tv.tend = 0u;
+    ws.rayof[lane] = p_own;
+    iters = (uint32_t)CRT_LONG_ITERS;  // part of a long walk: splittable straight away
+    took = true;
+  }
+}
+
+template <bool PRIMARY, int REFILL, bool CULL>
+__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest_s(const DScene sc, const Frame fr, const Levels lv,
+                                                                                const uint32_t level,
+                                                                                uint32_t *__restrict__ work_counter) {
+  __shared__ WarpShareS s_ws[CRT_TRAV_BLOCK / 32];
+  WarpShareS *ws = &s_ws[threadIdx.x >> 5];
+  const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
+  const uint32_t node_base = lv.offset[level];
+  const uint32_t lane = lane_id();
+  bool has_ray = false, exhausted = false, dirty = false;  // dirty: `ray` / tv.below hold a helped ray's state, not the own ray's
+  uint32_t job = 0, jown = lane, node = 0, own_below = 0, iters = 0;
+  Ray ray;
+  Trav tv;
+  Closest cl;
+  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
+  ray.flags = 0;
+  trav_begin(tv, sc);
+  tv.tref = tv.tend = 0;
+  closest_begin(cl);
+  ws->pend[lane] = 0u;
+  ws->rayof[lane] = lane;
+  acc_reset(*ws, lane);
+  __syncwarp();
+  CRT_PC_DECL
+  for (;;) {
+    CRT_PC_MARK(4)
+    CRT_PC_COUNT(7, 1)
+    CRT_PC_TAIL(exhausted, job != 0u)
+    __syncwarp();  // pend / occ / accumulators written by other lanes last round
+    const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !has_ray && job == 0u);
+    if (!exhausted && __popc(idle) >= REFILL) {
+      const uint32_t want = __popc(idle);
+      uint32_t start = 0;
+      if (lane == 0) start = atomicAdd(work_counter, want);
+      start = __shfl_sync(CRT_FULL_MASK, start, 0);
+      if (start + want >= total) exhausted = true;
+      const uint32_t i = start + __popc(idle & lanemask_lt());
+      if (!has_ray && job == 0u && i < total) {
+        bool valid = true;
+        if (PRIMARY) {
+          uint32_t row, col;
+          valid = item_pixel(fr, sc, fr.item_begin + i, row, col);
+          if (valid) primary_ray(fr.cam, sc.width, sc.height, row, col, ray.o, ray.d);
+        } else {
+          const float4 o = lv.ray_o[node_base - lv.offset[1] + i];
+          const float4 d = lv.ray_d[node_base - lv.offset[1] + i];
+          ray.o = mk(o.x, o.y, o.z);
+          ray.d = mk(d.x, d.y, d.z);
+        }
+        if (valid) {
+          ray_prepare(ray, PRIMARY);
+          trav_begin(tv, sc);
+          closest_begin(cl);
+          node = node_base + i;
+          has_ray = true;
+          job = 1u;
+          jown = lane;
+          iters = 0u;
+          dirty = false;
+          ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.f);
+          ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
+          ws->rayof[lane] = lane;
+        }
+      }
+    }
+    if (!__any_sync(CRT_FULL_MASK, has_ray || job != 0u)) {
+      if (exhausted) break;
+      continue;
+    }
+    // an owner that paused at the end of a mesh tree resumes once its helpers are done
+    if (has_ray && job == 0u && ws->pend[lane] == 0u) {
+      job = 1u;
+      jown = lane;
+      ws->rayof[lane] = lane;
+      if (dirty) {
+        const float4 o = ws->ro[lane], d = ws->rd[lane];
+        ray.o = mk(o.x, o.y, o.z);
+        ray.d = mk(d.x, d.y, d.z);
+        ray_prepare(ray, PRIMARY);
+        tv.below = own_below;
+        dirty = false;
+      }
+      tv.cur = tv.cend = 0u;
+      tv.tref = tv.tend = 0u;
+    }
+    // ---- ranges that ran out: helpers retire, owners fold their helpers' candidates and do the between-trees step ----
+    for (;;) {
+      const bool fin = job != 0u && tv.tref == tv.tend && tv.cur >= tv.cend;
+      if (!__any_sync(CRT_FULL_MASK, fin)) break;
+      if (fin) {
+        if (job == 2u) {
+          atomicSub(&ws->pend[jown], 1u);
+          job = 0u;
+        } else if (ws->pend[lane] != 0u) {
+          job = 0u;  // pause: helpers of this ray are still walking the rest of this mesh tree
+          own_below = tv.below;
+        } else {
+          acc_fold(*ws, lane, cl);
+          if (trav_slow<false, true>(tv, sc) == TRAV_DONE) {
+            lv.hit_tri[node] = cl.best_tri;
+            lv.hit_t[node] = cl.best_t;
+            has_ray = false;
+            job = 0u;
+          }
+        }
+      }
+    }
+    {
+      bool took;
+      steal_step(*ws, tv, job, jown, iters, took);
+      CRT_PC_COUNT(6, __popc(__ballot_sync(CRT_FULL_MASK, took)))
+      if (took) {
+        const float4 o = ws->ro[jown], d = ws->rd[jown];
+        ray.o = mk(o.x, o.y, o.z);
+        ray.d = mk(d.x, d.y, d.z);
+        ray_prepare(ray, PRIMARY);
+        dirty = true;
+      }
+    }
+    CRT_PC_MARK(1)
+    // ---- node phase ----
+    bool need = job != 0u && tv.tref == tv.tend && tv.cur < tv.cend;
+    const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, job != 0u)));
+    uint32_t dummy_count = 0;
+    while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
+      CRT_PC_COUNT(5, 1)
+      iters++;
+      if (need) need = trav_fast2<false, CULL>(tv, sc, ray, dummy_count, job == 1u ? cl.min_t : __int_as_float(0x7f800000));
+    }
+    CRT_PC_MARK(2)
+    // ---- triangle phase ----
+    const bool parked = job != 0u && tv.tref != tv.tend;
+    if (__any_sync(CRT_FULL_MASK, parked)) tri_phase_s<false, PRIMARY>(sc, *ws, parked, tv.tref, tv.tend, job == 2u, jown, tv.leaf, cl);
+    CRT_PC_MARK(3)
+  }
+  CRT_PC_FLUSH(8)
+}
+
+template <int REFILL, bool CULL>
+__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_s(const DScene sc, const Frame fr, const Levels lv,
+                                                                               uint32_t *__restrict__ work_counter) {
+  __shared__ WarpShareS s_ws[CRT_TRAV_BLOCK / 32];
+  WarpShareS *ws = &s_ws[threadIdx.x >> 5];
+  const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];
+  const uint32_t total = n_hits * sc.n_lights;
+  const uint32_t lane = lane_id();
+  bool has_ray = false, exhausted = false, dirty = false, own_done = false;
+  uint32_t job = 0, jown = lane, slot = 0, own_below = 0, iters = 0;
+  float t_limit = 0.0f, own_limit = 0.0f;
+  Ray ray;
+  Trav tv;
+  Closest unused;
+  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
+  ray.flags = 0;
+  trav_begin(tv, sc);
+  tv.tref = tv.tend = 0;
+  ws->pend[lane] = 0u;
+  ws->occ[lane] = 0u;
+  ws->rayof[lane] = lane;
+  __syncwarp();
+  CRT_PC_DECL
+  for (;;) {
+    CRT_PC_MARK(4)
+    CRT_PC_COUNT(7, 1)
+    CRT_PC_TAIL(exhausted, job != 0u)
+    __syncwarp();  // pend / occ / accumulators written by other lanes last round
+    const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !has_ray && job == 0u);
+    if (!exhausted && __popc(idle) >= REFILL) {
+      const uint32_t want = __popc(idle);
+      uint32_t start = 0;
+      if (lane == 0) start = atomicAdd(work_counter, want);
+      start = __shfl_sync(CRT_FULL_MASK, start, 0);
+      if (start + want >= total) exhausted = true;
+      const uint32_t i = start + __popc(idle & lanemask_lt());
+      if (!has_ray && job == 0u && i < total) {
+        const uint32_t light = i / n_hits, hit = i - light * n_hits;
+        const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
+        float contrib, dist;
+        shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
+        ray_prepare(ray, false);
+        trav_begin(tv, sc);
+        t_limit = own_limit = fadd(fmul(dist, 1.0001f), 1e-4f);  // CULL only
+        slot = hit * sc.n_lights + light;
+        has_ray = true;
+        own_done = false;
+        job = 1u;
+        jown = lane;
+        iters = 0u;
+        dirty = false;
+        ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, dist);
+        ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
+        ws->rayof[lane] = lane;
+        ws->occ[lane] = 0u;
+      }
+    }
+    if (!__any_sync(CRT_FULL_MASK, has_ray || job != 0u)) {
+      if (exhausted) break;
+      continue;
+    }
+    // any-hit: a ray somebody found occluded needs no more walking, by its owner or by its helpers
+    if (job != 0u && ws->occ[jown] != 0u) {
+      if (job == 2u) atomicSub(&ws->pend[jown], 1u);
+      else own_done = true;
+      job = 0u;
+      tv.tref = tv.tend = 0u;
+    }
+    // an owner whose own walk is over retires once its helpers are done
+    if (has_ray && job == 0u && own_done && ws->pend[lane] == 0u) {
+      lv.vis[slot] = ws->occ[lane] ? 0 : 1;
+      has_ray = false;
+    }
+    for (;;) {
+      const bool fin = job != 0u && tv.tref == tv.tend && tv.cur >= tv.cend;
+      if (!__any_sync(CRT_FULL_MASK, fin)) break;
+      if (fin) {
+        if (job == 2u) {
+          atomicSub(&ws->pend[jown], 1u);
+          job = 0u;
+        } else if (trav_slow<true, true>(tv, sc) == TRAV_DONE) {
+          own_done = true;  // retires above, next round, when no helper of this ray is left
+          job = 0u;
+        }
+      }
+    }
+    {
+      bool took;
+      steal_step(*ws, tv, job, jown, iters, took);
+      CRT_PC_COUNT(6, __popc(__ballot_sync(CRT_FULL_MASK, took)))
+      if (took) {
+        const float4 o = ws->ro[jown], d = ws->rd[jown];
+        ray.o = mk(o.x, o.y, o.z);
+        ray.d = mk(d.x, d.y, d.z);
+        ray_prepare(ray, false);
+        t_limit = fadd(fmul(o.w, 1.0001f), 1e-4f);
+        dirty = true;
+      }
+    }
+    CRT_PC_MARK(1)
+    bool need = job != 0u && tv.tref == tv.tend && tv.cur < tv.cend;
+    const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, job != 0u)));
+    uint32_t dummy_count = 0;
+    while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
+      CRT_PC_COUNT(5, 1)
+      iters++;
+      if (need) need = trav_fast2<false, CULL>(tv, sc, ray, dummy_count, t_limit);
+    }
+    CRT_PC_MARK(2)
+    const bool parked = job != 0u && tv.tref != tv.tend;
+    if (__any_sync(CRT_FULL_MASK, parked)) tri_phase_s<true, false>(sc, *ws, parked, tv.tref, tv.tend, job == 2u, jown, tv.leaf, unused);
+    CRT_PC_MARK(3)
+  }
+  CRT_PC_FLUSH(16)
+  (void)dirty; (void)own_below; (void)own_limit;
 }
 
 // K3b: the light loop of RayTracer::calculateDiffusion (RayTracer.cpp:308-330): per diffuse hit, walk the lights IN

@@ -86,6 +86,8 @@ struct crtb200_ctx {
   int l2_persist = 0;  // CRT_L2_PERSIST: 0 off (default, measured best), 1 arena persisting / rest of it streaming, 2 arena persisting / normal, 3 nodes only
   size_t nodes_bytes = 0;
   DevBuf<float4> wnodes, vtx_normal;
+  bool nested_ok = false;    // every child box of the uploaded mesh trees lies inside its parent's (crt_device.cuh "wide walk")
+  bool use_steal = false;    // CRT_STEAL=1: range-stealing kernels k_*_s (exact, parity green, but measured slower: profiles/r1_tuning.md)
   bool wide_ok = false;      // the 4-wide layout is usable (trees nest and are shallow enough)
   bool use_wide = false;     // CRT_LAYOUT=wide: walk the 4-wide layout (MODE 3 kernels).  Measured equal to slightly slower
                              // than the binary walk on every workload (profiles/r1_tuning.md), so it is opt-in
@@ -133,7 +135,7 @@ struct crtb200_ctx {
   uint32_t cap_depth = 0xFFFFFFFFu;
   uint32_t cap_sets = 0;
 
-  int blocks_closest = 0, blocks_shadow = 0, blocks_closest_w = 0, blocks_shadow_w = 0;
+  int blocks_closest = 0, blocks_shadow = 0, blocks_closest_w = 0, blocks_shadow_w = 0, blocks_closest_s = 0, blocks_shadow_s = 0;
   crtb200_stats last{};
   bool last_pending = false;
 };
@@ -183,12 +185,18 @@ int crtb200_create(int device, crtb200_ctx **out) {
   c->blocks_closest_w = std::max(1, occ) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_w<CRT_REFILL, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_shadow_w = std::max(1, occ) * c->sm_count;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest_s<true, CRT_REFILL, false>, CRT_TRAV_BLOCK, 0);
+  c->blocks_closest_s = std::max(1, occ) * c->sm_count;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_s<CRT_REFILL, false>, CRT_TRAV_BLOCK, 0);
+  c->blocks_shadow_s = std::max(1, occ) * c->sm_count;
   if (const char *env = getenv("CRT_BLOCKS_PER_SM")) {  // tuning only (tools/): resident persistent CTAs per SM
     const int b = atoi(env);
-    if (b > 0) c->blocks_closest = c->blocks_shadow = c->blocks_closest_w = c->blocks_shadow_w = b * c->sm_count;
+    if (b > 0)
+      c->blocks_closest = c->blocks_shadow = c->blocks_closest_w = c->blocks_shadow_w = c->blocks_closest_s = c->blocks_shadow_s = b * c->sm_count;
   }
   if (const char *env = getenv("CRT_LAYOUT")) c->use_wide = std::string(env) == "wide";
   if (const char *env = getenv("CRT_L2_PERSIST")) c->l2_persist = atoi(env);
+  if (const char *env = getenv("CRT_STEAL")) c->use_steal = atoi(env) != 0;
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
   c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
   if (c->l2_persist && c->l2_persist_max)
@@ -436,6 +444,7 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   }
   // trees: mesh trees first, top-level tree last, one node array
   std::vector<float4> nodes, wnodes;
+  bool nested_ok = true;
   bool wide_ok = c->use_wide;  // the 4-wide copy of the trees is only built when it will be walked
   std::vector<uint32_t> refs(s->n_mesh_leaf_refs);
   std::vector<DMesh> meshes(s->n_meshes);
@@ -458,6 +467,14 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
     meshes[m].first_triangle = me.first_triangle;
     meshes[m].wroot = CRT_INVALID;
     node_cursor += placed;
+    for (uint32_t k = 0; k < me.n_nodes && nested_ok; k++) {  // relayout_tree has validated the child indices
+      const crtb200_kdnode &p = s->mesh_nodes[me.first_node + k];
+      for (int k3 = 0; k3 < 3; k3++)
+        if (!(p.box_min[k3] <= p.box_max[k3])) nested_ok = false;
+      if (p.leaf_count) continue;
+      for (int side = 0; side < 2; side++)
+        if (p.child[side] != CRTB200_INVALID && !box_nested(p, s->mesh_nodes[me.first_node + p.child[side]])) nested_ok = false;
+    }
     if (wide_ok) {  // relayout_tree has validated the tree's shape
       WideBuild wb{s->mesh_nodes + me.first_node, me.first_leaf_ref, &wnodes, true};
       meshes[m].wroot = wide_build_mesh(wb, me.n_nodes);
@@ -541,6 +558,7 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   if (!wide_ok) wnodes.clear();
   CUDA_TRY(c->wnodes.upload(wnodes));
   c->wide_ok = wide_ok;
+  c->nested_ok = nested_ok;
   CUDA_TRY(c->top_refs.upload(top_refs));
   CUDA_TRY(c->tri_shade.upload(shade));
   CUDA_TRY(c->vtx_normal.upload(vn));
@@ -579,7 +597,7 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   CUDA_TRY(cudaMemset(c->frame.p, 0, px * 3 * sizeof(float)));  // colorBuffer starts at (0,0,0), RayTracer.cpp:47-50
   CUDA_TRY(c->frame8.ensure(px * 3));
   CUDA_TRY(cudaMemset(c->frame8.p, 0, px * 3));
-  CUDA_TRY(c->stats_dev.ensure(24));
+  CUDA_TRY(c->stats_dev.ensure(32));
   c->mask_valid = false;
   c->cap_items = 0;
   c->have_scene = true;
@@ -633,7 +651,10 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
   uint32_t n_sets = std::max<uint32_t>(1, std::min<uint32_t>(c->concurrency, (shard_items + 65535u) / 65536u));
   // measured (profiles/r1_tuning.md): overlapping chunks only pays when band copies to the host ride along; the
   // persistent kernels already fill the GPU, extra chunks just add launches and tails
-  if (!pipelined) n_sets = 1;
+  if (!pipelined) {
+    n_sets = 1;
+    if (const char *env = getenv("CRT_DEVICE_CHUNKS")) n_sets = std::max(1, std::min<int>(atoi(env), (int)std::min<uint32_t>(16u, (shard_items + 65535u) / 65536u)));
+  }
   uint64_t items = c->queue_budget / (bytes_per_node * sum * n_sets);
   items &= ~31ull;
   if (items < 32 * 64) return fail(CRTB200_ERR_MEMORY, "queue budget too small for one chunk at this ray depth");
@@ -734,6 +755,15 @@ static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const 
 }
 
 template <bool CULL>
+static void launch_closest_s(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, uint32_t *work,
+                             cudaStream_t st) {
+  if (primary)
+    k_closest_s<true, CRT_REFILL, CULL><<<c->blocks_closest_s, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
+  else
+    k_closest_s<false, CRT_REFILL, CULL><<<c->blocks_closest_s, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
+}
+
+template <bool CULL>
 static void launch_closest_w(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, uint32_t *work,
                              cudaStream_t st) {
   if (primary)
@@ -764,6 +794,8 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   const bool cull = o->traversal == 1;
   // opt-in 4-wide walk (CRT_LAYOUT=wide); the counting modes always measure the reference's binary visit-all walk
   const bool wide = c->use_wide && c->wide_ok && o->count_work == 0;
+  // range stealing needs the nesting property too; the counting modes keep the plain kernels (they count the reference's walk)
+  const bool steal = !wide && c->use_steal && c->nested_ok && o->count_work == 0;
   const uint32_t shard_count = o->shard_count ? o->shard_count : 1;
   if (o->shard_index >= shard_count) return fail(CRTB200_ERR_ARG, "shard_index >= shard_count");
   int rc = plan_mask(c, o);
@@ -791,7 +823,11 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   const uint32_t levels = secondary ? o->max_depth + 1 : 1;
   const int grid_simple = c->sm_count * 8;
 
-  CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 24 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 32 * sizeof(unsigned long long), st));
+#if CRT_PHASE_CLOCKS
+  CUDA_TRY(cudaMemsetAsync(c->stats_dev.p + 27, 0xFF, sizeof(unsigned long long), st));  // atomicMin slots
+  CUDA_TRY(cudaMemsetAsync(c->stats_dev.p + 31, 0xFF, sizeof(unsigned long long), st));
+#endif
   c->kev_used = 0;
   c->kev_kind.clear();
   if (timed) CUDA_TRY(cudaEventRecord(c->ev[0], st));
@@ -814,7 +850,11 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
         cudaEventRecord(next_event(c), qs);
         c->kev_kind.push_back(0);
       }
-      if (wide && cull)
+      if (steal && cull)
+        launch_closest_s<true>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
+      else if (steal)
+        launch_closest_s<false>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
+      else if (wide && cull)
         launch_closest_w<true>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
       else if (wide)
         launch_closest_w<false>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
@@ -835,7 +875,11 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       c->kev_kind.push_back(1);
     }
     uint32_t *swork = q.work.p + CRT_MAX_LEVELS;
-    if (wide && cull)
+    if (steal && cull)
+      k_shadow_s<CRT_REFILL, true><<<c->blocks_shadow_s, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+    else if (steal)
+      k_shadow_s<CRT_REFILL, false><<<c->blocks_shadow_s, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+    else if (wide && cull)
       k_shadow_w<CRT_REFILL, true><<<c->blocks_shadow_w, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else if (wide)
       k_shadow_w<CRT_REFILL, false><<<c->blocks_shadow_w, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
@@ -879,15 +923,50 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
 }
 
 static int collect_stats(crtb200_ctx *c, bool timed) {
-  unsigned long long st[24];
+  unsigned long long st[32];
   CUDA_TRY(cudaMemcpy(st, c->stats_dev.p, sizeof(st), cudaMemcpyDeviceToHost));
 #if CRT_PHASE_CLOCKS
   for (int k = 0; k < 2; k++) {
     const unsigned long long *p = st + 8 + 8 * k;
     const double tot = (double)(p[0] + p[1] + p[2] + p[3] + p[4]);
-    fprintf(stderr, "[phase clocks] %s: refill %.1f%% slow %.1f%% node %.1f%% tri %.1f%% other %.1f%% | node iterations %llu, tri phases %llu, rounds %llu\n",
+    fprintf(stderr, "[phase clocks] %s: refill %.1f%% slow %.1f%% node %.1f%% tri %.1f%% other %.1f%% | node iterations %llu, tri phases (MODE 2) / ranges stolen (k_*_s) %llu, rounds %llu\n",
             k ? "k_shadow " : "k_closest", 100.0 * p[0] / tot, 100.0 * p[1] / tot, 100.0 * p[2] / tot, 100.0 * p[3] / tot, 100.0 * p[4] / tot,
             p[5], p[6], p[7]);
+    {
+      unsigned long long hist[2][32];
+      cudaMemcpyFromSymbol(hist, g_iter_hist, sizeof(hist));
+      fprintf(stderr, "[phase clocks] %s rays by log2(node iterations + 1) (cumulative over frames):", k ? "k_shadow " : "k_closest");
+      for (int b = 0; b < 20; b++) fprintf(stderr, " %llu", hist[k][b]);
+      fprintf(stderr, "\n");
+    }
+    {
+      unsigned long long tail[2][2];
+      cudaMemcpyFromSymbol(tail, g_tail, sizeof(tail));
+      const double clk = (double)(p[0] + p[1] + p[2] + p[3] + p[4]);
+      fprintf(stderr, "[phase clocks] %s after the queue ran dry (cumulative): %.1f%% of warp time, %.1f of 32 lanes busy on average\n", k ? "k_shadow " : "k_closest",
+              100.0 * (double)tail[k][0] / clk, tail[k][0] ? (double)tail[k][1] / (double)tail[k][0] : 0.0);
+    }
+    if (getenv("CRT_WARP_DUMP")) {
+      static unsigned long long rec[2][8192][6];
+      cudaMemcpyFromSymbol(rec, g_warp_rec, sizeof(rec));
+      unsigned long long t0 = ~0ull;
+      for (int w = 0; w < 8192; w++) if (rec[k][w][1] && rec[k][w][0] < t0) t0 = rec[k][w][0];
+      std::vector<std::pair<unsigned long long, int>> ends;
+      for (int w = 0; w < 8192; w++) if (rec[k][w][1]) ends.push_back({rec[k][w][1] - t0, w});
+      std::sort(ends.begin(), ends.end());
+      fprintf(stderr, "[warp dump] %s: %zu warps; end-time percentiles (us): p10 %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f\n", k ? "k_shadow " : "k_closest", ends.size(),
+              ends[ends.size() / 10].first * 1e-3, ends[ends.size() / 2].first * 1e-3, ends[ends.size() * 9 / 10].first * 1e-3,
+              ends[ends.size() * 99 / 100].first * 1e-3, ends.back().first * 1e-3);
+      for (size_t i = ends.size() >= 6 ? ends.size() - 6 : 0; i < ends.size(); i++) {
+        const unsigned long long *r = rec[k][ends[i].second];
+        fprintf(stderr, "[warp dump]   warp %d: start %.0f us end %.0f us rounds %llu node-iterations %llu clk-after-dry %llu stolen %llu\n", ends[i].second,
+                (r[0] - t0) * 1e-3, (r[1] - t0) * 1e-3, r[2], r[3], r[4], r[5]);
+      }
+    }
+    const unsigned long long *g = st + 24 + 4 * k;  // sum of warp lifetimes, warps, last end, first start (globaltimer ns)
+    if (g[1])
+      fprintf(stderr, "[phase clocks] %s: %llu warps, mean warp lifetime %.1f us, kernel span %.1f us (first warp start -> last warp end; one launch per frame only)\n",
+              k ? "k_shadow " : "k_closest", g[1], 1e-3 * (double)g[0] / (double)g[1], 1e-3 * (double)(g[2] - g[3]));
   }
 #endif
   c->last.rays_primary = st[0];

@@ -244,3 +244,50 @@ def test_wide_layout_falls_back_when_boxes_do_not_nest(gpu_wide, built, scene_di
     assert np.array_equal(hits["mesh"], o_hits["mesh"]) and np.array_equal(hits["triangle"], o_hits["triangle"])
     assert same_f32(rgb, o_rgb).all()
     assert st["rays_total"] == o_st["rays_total"]
+
+
+@pytest.fixture(scope="module")
+def gpu_steal(built):
+    """A context that runs the opt-in range-stealing kernels k_closest_s / k_shadow_s (CRT_STEAL is read by crtb200_create)."""
+    os.environ["CRT_STEAL"] = "1"
+    try:
+        ctx = built.Context(0)
+    finally:
+        del os.environ["CRT_STEAL"]
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", list(SMALL_SCENES))
+def test_range_stealing_matches_golden(name, gpu_steal, loaded, crt):
+    """Long walks hand the far part of their node range to idle lanes of the warp (crt_kernels.cuh, k_*_s): helper
+    candidates are folded back in encounter order, so hit ids, t and float RGB stay bit-identical to the reference."""
+    sf, flat, rects, n = loaded[name]
+    gpu_steal.upload(flat, keepalive=sf)
+    rgb, rgb8, hits, st = gpu_steal.render(sf.camera(), crt.make_options(rects=rects, n_rects=n), want_rgb8=True, want_hits=True)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cov = _covered(sf, rects, n)
+    assert np.array_equal(hits["mesh"][cov], g["hits"]["mesh"][cov]) and np.array_equal(hits["triangle"][cov], g["hits"]["triangle"][cov])
+    h = cov & (g["hits"]["mesh"] >= 0)
+    assert same_f32(hits["t"][h], g["hits"]["t"][h]).all()
+    _assert_pixels(name, rgb, g["rgb"], rgb8, g["ppm"])
+    assert [st["rays_primary"], st["rays_shadow"], st["rays_reflection"], st["rays_refraction"]] == list(g["rays"])
+
+
+def test_range_stealing_full_size_equals_default(gpu, gpu_steal, built):
+    """1920x1080 room with 196 608-triangle mirror and glass spheres (thousands of long walks, depth 5): the stealing
+    kernels and the default kernels must agree bit for bit on hits and colours."""
+    import importlib
+    bench_mod = importlib.import_module("bench")
+    f, folder, kw, tex, depth = bench_mod.ensure_scene("hw11_room_128", {})
+    sf = built.SceneFile(f, folder)
+    flat = sf.flatten()
+    outs = []
+    for ctx in (gpu, gpu_steal):
+        ctx.upload(flat, keepalive=sf)
+        rgb, _, hits, st = ctx.render(sf.camera(), built.make_options(max_depth=depth), want_hits=True)
+        outs.append((rgb, hits, st))
+    assert np.array_equal(outs[0][1]["triangle"], outs[1][1]["triangle"]) and np.array_equal(outs[0][1]["mesh"], outs[1][1]["mesh"])
+    assert same_f32(outs[0][1]["t"], outs[1][1]["t"]).all()
+    assert same_f32(outs[0][0], outs[1][0]).all()
+    assert outs[0][2]["rays_total"] == outs[1][2]["rays_total"]
