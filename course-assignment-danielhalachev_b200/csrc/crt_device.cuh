@@ -408,8 +408,11 @@ CRT_DI bool trav_fast(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_te
 // of a loop whose iteration time is the latency of the slowest lane's load.  When node idx fails (an inner node) the
 // second test is simply discarded; testing a node the reference would not have reached cannot change the walk,
 // because only the pass / fail of nodes that ARE reached is acted on.
-template <bool COUNT, bool CULL>
-CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float t_limit) {
+// HINT (k_*_s kernels): when node idx passes and has two children, the subtree of the child visited second,
+// [sibling, a0), is work this walk will come back to.  `hint` remembers the outermost such sibling still ahead of the
+// cursor: the place where the walk can be cut with real work on both sides (steal_step).
+template <bool COUNT, bool CULL, bool HINT = false>
+CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float t_limit, uint32_t *hint = nullptr) {
   const uint32_t idx = s.cur;
   const bool has2 = idx + 1u < s.cend;
   const uint32_t jdx = has2 ? idx + 1u : idx;
@@ -430,6 +433,10 @@ CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_t
   // failing leaf) and a second one exists
   const bool second = has2 && (pass0 != leaf0);
   if (COUNT && second) node_tests++;
+  if (HINT) {
+    const uint32_t sib = leaf1 ? idx + 2u : a1;  // first node after the subtree of idx + 1
+    if (has2 && pass0 && !leaf0 && *hint <= idx && sib < a0 && a0 - sib >= 16u && a0 <= s.cend) *hint = sib;
+  }
   const uint32_t a = second ? a1 : a0, b = __float_as_uint(second ? hi1.w : hi0.w), at = second ? idx + 1u : idx;
   const bool pass = second ? pass1 : pass0, leaf = second ? leaf1 : leaf0;
   s.cur = (pass || leaf) ? at + 1u : a;

@@ -971,13 +971,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
 //            best = minimal (t, key) over candidates with t < inf.  Only then does the owner go on to the next mesh.
 // ------------------------------------------------------------------------------------------------------------
 #ifndef CRT_MIN_SPLIT
-#define CRT_MIN_SPLIT 64  // nodes: ranges shorter than this are not split
-#endif
-#ifndef CRT_LONG_ITERS
-#define CRT_LONG_ITERS 96  // a walk becomes a donor once it has taken this many node-phase iterations
-#endif
-#ifndef CRT_SPLIT_SPAN
-#define CRT_SPLIT_SPAN 2048  // a donor keeps at most this many nodes ahead of its cursor (the work of a ray clusters near it)
+#define CRT_MIN_SPLIT 16  // nodes: a donated range is at least this long
 #endif
 
 struct __align__(16) WarpShareS {
@@ -1096,27 +1090,27 @@ CRT_DI void tri_phase_s(const DScene &sc, WarpShareS &ws, const bool pending, ui
   if (cnt) tref = tend;
 }
 
-// Donation step (warp-uniform; only called once the work queue is dry).  job: 0 = nothing to walk, 1 = own ray,
-// 2 = helper range.  The i-th lane without a job takes the upper half of the i-th splittable range.
-CRT_DI void steal_step(WarpShareS &ws, Trav &tv, uint32_t &job, uint32_t &jown, uint32_t &iters, bool &took) {
+// Donation step (warp-uniform, every round).  job: 0 = nothing to walk, 1 = own ray, 2 = helper range.  A walk with a
+// pending sibling subtree ahead of its cursor (`hint`, trav_fast2) can be cut there: it keeps [cur, hint) and the i-th
+// lane without a job takes [hint, cend) of the i-th such walk.
+CRT_DI void steal_step(WarpShareS &ws, Trav &tv, uint32_t &job, uint32_t &jown, uint32_t &hint, bool &took) {
   const uint32_t lane = lane_id();
   const bool avail = job == 0u;
-  const bool donor = job != 0u && iters >= (uint32_t)CRT_LONG_ITERS && tv.tref == tv.tend && tv.below != 0u && tv.cur < tv.cend &&
-                     (tv.cend - tv.cur) >= (uint32_t)CRT_MIN_SPLIT;
+  const bool donor = job != 0u && tv.tref == tv.tend && tv.below != 0u && hint > tv.cur && hint < tv.cend &&
+                     (tv.cend - hint) >= (uint32_t)CRT_MIN_SPLIT;
   const uint32_t am = __ballot_sync(CRT_FULL_MASK, avail), dm = __ballot_sync(CRT_FULL_MASK, donor);
   const int n = min(__popc(am), __popc(dm));
   took = false;
   if (n == 0) return;
   const int ra = __popc(am & lanemask_lt()), rd = __popc(dm & lanemask_lt());
   const bool give = donor && rd < n, take = avail && ra < n;
-  const uint32_t half = (tv.cend - tv.cur) >> 1;
-  const uint32_t mid = tv.cur + (half < (uint32_t)CRT_SPLIT_SPAN ? half : (uint32_t)CRT_SPLIT_SPAN);
   const int partner = take ? (int)__fns(dm, 0, ra + 1) : (int)lane;
-  const uint32_t p_mid = __shfl_sync(CRT_FULL_MASK, mid, partner);
+  const uint32_t p_mid = __shfl_sync(CRT_FULL_MASK, hint, partner);
   const uint32_t p_end = __shfl_sync(CRT_FULL_MASK, tv.cend, partner);
   const uint32_t p_own = __shfl_sync(CRT_FULL_MASK, jown, partner);
   if (give) {
-    tv.cend = mid;
+    tv.cend = hint;
+    hint = 0u;
     atomicAdd(&ws.pend[jown], 1u);
   }
   if (take) {
@@ -1127,7 +1121,7 @@ CRT_DI void steal_step(WarpShareS &ws, Trav &tv, uint32_t &job, uint32_t &jown, 
     tv.below = 1u;
     tv.tref = tv.tend = 0u;
     ws.rayof[lane] = p_own;
-    iters = (uint32_t)CRT_LONG_ITERS;  // part of a long walk: splittable straight away
+    hint = 0u;
     took = true;
   }
 }
@@ -1142,7 +1136,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
   const uint32_t node_base = lv.offset[level];
   const uint32_t lane = lane_id();
   bool has_ray = false, exhausted = false, dirty = false;  // dirty: `ray` / tv.below hold a helped ray's state, not the own ray's
-  uint32_t job = 0, jown = lane, node = 0, own_below = 0, iters = 0;
+  uint32_t job = 0, jown = lane, node = 0, own_below = 0, hint = 0;
   Ray ray;
   Trav tv;
   Closest cl;
@@ -1189,7 +1183,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
           has_ray = true;
           job = 1u;
           jown = lane;
-          iters = 0u;
+          hint = 0u;
           dirty = false;
           ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.f);
           ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
@@ -1230,6 +1224,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
           own_below = tv.below;
         } else {
           acc_fold(*ws, lane, cl);
+          hint = 0u;  // node indices of the next tree are unrelated
           if (trav_slow<false, true>(tv, sc) == TRAV_DONE) {
             lv.hit_tri[node] = cl.best_tri;
             lv.hit_t[node] = cl.best_t;
@@ -1241,7 +1236,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
     }
     {
       bool took;
-      steal_step(*ws, tv, job, jown, iters, took);
+      steal_step(*ws, tv, job, jown, hint, took);
       CRT_PC_COUNT(6, __popc(__ballot_sync(CRT_FULL_MASK, took)))
       if (took) {
         const float4 o = ws->ro[jown], d = ws->rd[jown];
@@ -1258,8 +1253,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
     uint32_t dummy_count = 0;
     while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
       CRT_PC_COUNT(5, 1)
-      iters++;
-      if (need) need = trav_fast2<false, CULL>(tv, sc, ray, dummy_count, job == 1u ? cl.min_t : __int_as_float(0x7f800000));
+      if (need) need = trav_fast2<false, CULL, true>(tv, sc, ray, dummy_count, job == 1u ? cl.min_t : __int_as_float(0x7f800000), &hint);
     }
     CRT_PC_MARK(2)
     // ---- triangle phase ----
@@ -1279,7 +1273,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
   const uint32_t total = n_hits * sc.n_lights;
   const uint32_t lane = lane_id();
   bool has_ray = false, exhausted = false, dirty = false, own_done = false;
-  uint32_t job = 0, jown = lane, slot = 0, own_below = 0, iters = 0;
+  uint32_t job = 0, jown = lane, slot = 0, own_below = 0, hint = 0;
   float t_limit = 0.0f, own_limit = 0.0f;
   Ray ray;
   Trav tv;
@@ -1319,7 +1313,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
         own_done = false;
         job = 1u;
         jown = lane;
-        iters = 0u;
+        hint = 0u;
         dirty = false;
         ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, dist);
         ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
@@ -1350,15 +1344,18 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
         if (job == 2u) {
           atomicSub(&ws->pend[jown], 1u);
           job = 0u;
-        } else if (trav_slow<true, true>(tv, sc) == TRAV_DONE) {
-          own_done = true;  // retires above, next round, when no helper of this ray is left
-          job = 0u;
+        } else {
+          hint = 0u;  // node indices of the next tree are unrelated
+          if (trav_slow<true, true>(tv, sc) == TRAV_DONE) {
+            own_done = true;  // retires above, next round, when no helper of this ray is left
+            job = 0u;
+          }
         }
       }
     }
     {
       bool took;
-      steal_step(*ws, tv, job, jown, iters, took);
+      steal_step(*ws, tv, job, jown, hint, took);
       CRT_PC_COUNT(6, __popc(__ballot_sync(CRT_FULL_MASK, took)))
       if (took) {
         const float4 o = ws->ro[jown], d = ws->rd[jown];
@@ -1375,8 +1372,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
     uint32_t dummy_count = 0;
     while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
       CRT_PC_COUNT(5, 1)
-      iters++;
-      if (need) need = trav_fast2<false, CULL>(tv, sc, ray, dummy_count, t_limit);
+      if (need) need = trav_fast2<false, CULL, true>(tv, sc, ray, dummy_count, t_limit, &hint);
     }
     CRT_PC_MARK(2)
     const bool parked = job != 0u && tv.tref != tv.tend;
