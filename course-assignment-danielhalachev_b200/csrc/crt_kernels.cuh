@@ -5,6 +5,8 @@
 //   K4/K5 k_shade                   per-hit: barycentrics, smooth normal, texture sample, material switch,
 //                                   reflect / refract + Fresnel, compaction of children into the next level's queue
 //   K3  k_shadow                    persistent any-hit traversal, one (diffuse hit, light) pair per lane -> visibility
+//       k_closest_w / k_shadow_w    opt-in (CRT_LAYOUT=wide): the same walks over the 4-wide collapse of the trees
+//       k_closest_s / k_shadow_s    opt-in (CRT_STEAL=1): long walks hand pending sibling subtrees to idle lanes
 //   K3b k_accumulate                in-order light sum per diffuse hit
 //   K6  k_resolve                   bottom-up combine of the ray tree in the reference's expression order
 //   K7  k_store                     level-0 colours -> framebuffer (f32 + PPMColor u8)
@@ -237,17 +239,20 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, const
 // Persistent warps, one ray per lane.  Every loop below has a WARP-UNIFORM trip count (its condition is a vote), so the
 // 32 lanes stay converged under independent thread scheduling; per-lane work is predicated.  (A first version with
 // per-lane `while (active)` loops ran at 1.8-5 active threads per instruction: ncu profiles/r1a.)  One outer round =
-//   refill    when >= REFILL lanes are idle, one atomicAdd per warp hands them the next rays of the global cursor
-//   node phase   every lane steps its stack-free KD walk until it reaches a leaf or the end of the tree
-//   leaf phase   every lane tests the triangles of its pending leaf
+//   refill        when >= REFILL lanes are idle, one atomicAdd per warp hands them the next rays of the global cursor
+//   between trees trav_slow for lanes whose cursor ran off a tree (next mesh of the top-level leaf / back to the top level)
+//   node phase    trav_fast2: lanes that need an AABB step take one (two consecutive nodes at once) per iteration while
+//                 at least node_threshold() lanes do; a lane that reaches a leaf parks with its triangle range pending
+//   tri phase     tri_phase: the parked ranges, packed across the warp
+// MODE: 2 = this loop.  (0 = while-while and 1 = merged single loop were the round-1 predecessors; their measurements are
+// in profiles/r1_tuning.md, their code is gone.)
 // ------------------------------------------------------------------------------------------------------------
-// MODE 0: while-while (node phase to the next leaf, then leaf phase).  MODE 1: merged loop -- per iteration a lane does
-// one AABB step or one triangle test, whichever it needs (better when lanes reach leaves at very different times).
 template <bool PRIMARY, bool COUNT, int REFILL, int MODE, bool CULL>
 __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest(const DScene sc, const Frame fr, const Levels lv, const uint32_t level,
                                                 uint32_t *__restrict__ work_counter) {
-  __shared__ WarpShare s_ws[(MODE == 2) ? CRT_TRAV_BLOCK / 32 : 1];
-  WarpShare *ws = &s_ws[(MODE == 2) ? (threadIdx.x >> 5) : 0];
+  static_assert(MODE == 2, "only loop mode 2 is implemented");
+  __shared__ WarpShare s_ws[CRT_TRAV_BLOCK / 32];
+  WarpShare *ws = &s_ws[threadIdx.x >> 5];
   const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
   const uint32_t node_base = lv.offset[level];
   const uint32_t lane = lane_id();
@@ -342,53 +347,6 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
         tri_phase<false, PRIMARY, COUNT>(sc, *ws, parked, !__any_sync(CRT_FULL_MASK, need), tv.tref, tv.tend, cl, dummy, n_tris);
       }
       CRT_PC_MARK(3)
-    } else if (MODE == 0) {
-      // ---- node phase ----
-      int st = active ? TRAV_STEP : TRAV_DONE;
-      while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
-        if (st == TRAV_STEP) st = trav_step<false, COUNT, !COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t);
-      }
-      if (active && st == TRAV_DONE) {
-        lv.hit_tri[node] = cl.best_tri;
-        lv.hit_t[node] = cl.best_t;
-        active = false;
-      }
-      // ---- leaf phase ----
-      while (__any_sync(CRT_FULL_MASK, tv.tref != tv.tend)) {
-        if (tv.tref != tv.tend) {
-          const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
-          const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
-          const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
-          const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
-          float t;
-          V3 p;
-          if (COUNT) n_tris++;
-          if (triangle_test(g0, g1, g2, ray, t, p)) closest_offer(cl, tri, t);
-        }
-      }
-    } else {
-      // ---- merged loop: runs until REFILL lanes have retired (or all, once the queue is exhausted) ----
-      bool running = active;
-      const int quota = exhausted ? 0 : 32 - REFILL;  // keep going while more than `quota` lanes still run
-      while (__popc(__ballot_sync(CRT_FULL_MASK, running)) > quota) {
-        if (running) {
-          if (tv.tref != tv.tend) {
-            const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
-            const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
-            const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
-            const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
-            float t;
-            V3 p;
-            if (COUNT) n_tris++;
-            if (triangle_test(g0, g1, g2, ray, t, p)) closest_offer(cl, tri, t);
-          } else if (trav_step<false, COUNT, !COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t) == TRAV_DONE) {
-            lv.hit_tri[node] = cl.best_tri;
-            lv.hit_t[node] = cl.best_t;
-            active = false;
-            running = false;
-          }
-        }
-      }
     }
   }
   CRT_PC_FLUSH(8)
@@ -631,8 +589,9 @@ CRT_DI void shadow_ray_setup(const DScene &sc, const Frame &fr, const V3 P, cons
 template <int COUNT, int REFILL, int MODE, bool CULL>
 __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(const DScene sc, const Frame fr, const Levels lv,
                                                                              uint32_t *__restrict__ work_counter) {
-  __shared__ WarpShare s_ws[(MODE == 2) ? CRT_TRAV_BLOCK / 32 : 1];
-  WarpShare *ws = &s_ws[(MODE == 2) ? (threadIdx.x >> 5) : 0];
+  static_assert(MODE == 2, "only loop mode 2 is implemented");
+  __shared__ WarpShare s_ws[CRT_TRAV_BLOCK / 32];
+  WarpShare *ws = &s_ws[threadIdx.x >> 5];
   const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];
   const uint32_t total = n_hits * sc.n_lights;
   const uint32_t lane = lane_id();
@@ -719,64 +678,6 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
         }
       }
       CRT_PC_MARK(3)
-    } else if (MODE == 0) {
-      int st = active ? TRAV_STEP : TRAV_DONE;
-      while (__any_sync(CRT_FULL_MASK, st == TRAV_STEP)) {
-        if (st == TRAV_STEP) st = trav_step<true, (COUNT != 0), (COUNT != 1), CULL>(tv, sc, ray, n_nodes, t_limit);
-      }
-      if (active && st == TRAV_DONE) {
-        lv.vis[slot] = occluded ? 0 : 1;
-        active = false;
-      }
-      while (__any_sync(CRT_FULL_MASK, tv.tref != tv.tend)) {
-        if (tv.tref != tv.tend) {
-          const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
-          const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
-          const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
-          const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
-          float t;
-          V3 p;
-          if (COUNT) n_tris++;
-          // (hitPoint - ray.origin).length() <= distanceToLight                   AccelerationStructure.cpp:73-74
-          if (triangle_test(g0, g1, g2, ray, t, p) && vlen(vsub(p, ray.o)) <= dist) {
-            occluded = true;
-            if (COUNT != 1) {  // early termination: the rest of the walk cannot change the answer
-              tv.tref = tv.tend = 0;
-              lv.vis[slot] = 0;
-              active = false;
-            }
-          }
-        }
-      }
-    } else {
-      bool running = active;
-      const int quota = exhausted ? 0 : 32 - REFILL;
-      while (__popc(__ballot_sync(CRT_FULL_MASK, running)) > quota) {
-        if (running) {
-          if (tv.tref != tv.tend) {
-            const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
-            const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
-            const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
-            const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
-            float t;
-            V3 p;
-            if (COUNT) n_tris++;
-            if (triangle_test(g0, g1, g2, ray, t, p) && vlen(vsub(p, ray.o)) <= dist) {
-              occluded = true;
-              if (COUNT != 1) {
-                tv.tref = tv.tend = 0;
-                lv.vis[slot] = 0;
-                active = false;
-                running = false;
-              }
-            }
-          } else if (trav_step<true, (COUNT != 0), (COUNT != 1), CULL>(tv, sc, ray, n_nodes, t_limit) == TRAV_DONE) {
-            lv.vis[slot] = occluded ? 0 : 1;
-            active = false;
-            running = false;
-          }
-        }
-      }
     }
   }
   CRT_PC_FLUSH(16)
