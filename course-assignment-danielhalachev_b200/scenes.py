@@ -349,6 +349,44 @@ def degenerate_uv_scene(width=240, height=135, buckets=1):
     return s
 
 
+def many_meshes(width=128, height=72, count=70, buckets=24):
+    """Edge case: more than 64 meshes (the per-ray visited-mesh bitmask of the CUDA core is off, every listing of a mesh in
+    a top-level leaf is traversed again, like the reference does) -- `count` small tilted quads on a grid in front of a
+    back wall, one mirror among them, two lights."""
+    objs = [_obj(1, *quad((-4, -3, -7), (4, -3, -7), (4, 3, -7), (-4, 3, -7)))]
+    cols = 10
+    for k in range(count - 1):
+        cx = -2.7 + 0.6 * (k % cols)
+        cy = -1.8 + 0.55 * (k // cols)
+        z = -3.0 - 0.25 * ((k * 7) % 9)
+        dz = 0.05 * ((k % 5) - 2)
+        objs.append(_obj(2 if k == 17 else 0, *quad((cx - 0.25, cy - 0.2, z + dz), (cx + 0.25, cy - 0.2, z - dz),
+                                                     (cx + 0.25, cy + 0.2, z - dz), (cx - 0.25, cy + 0.2, z + dz))))
+    return {
+        "settings": _settings([0.05, 0.1, 0.2], width, height, buckets),
+        "camera": {"matrix": IDENTITY, "position": [0.0, 0.0, 0.0]},
+        "lights": [{"intensity": 60, "position": [0.0, 2.0, -1.0]}, {"intensity": 30, "position": [-2.0, -1.0, 0.0]}],
+        "materials": [{"type": "diffuse", "albedo": [0.8, 0.5, 0.2], "smooth_shading": False},
+                      {"type": "diffuse", "albedo": [0.6, 0.6, 0.6], "smooth_shading": False},
+                      {"type": "reflective", "albedo": [0.9, 0.9, 0.9], "smooth_shading": False}],
+        "objects": objs,
+    }
+
+
+def no_lights(width=64, height=36, buckets=1):
+    """Edge case: an empty light list (diffuse surfaces come out (0,0,0), misses the background) on a 1-bucket grid."""
+    s = hw07_scene0(width, height, 0, buckets)
+    s["lights"] = []
+    return s
+
+
+def empty_scene(width=32, height=18, buckets=1):
+    """Edge case: no objects at all -- every pixel is the background colour, no shadow rays."""
+    s = hw07_scene0(width, height, 0, buckets)
+    s["objects"] = []
+    return s
+
+
 def orbit_cameras(frames: int, radius: float = 5.12, center_z: float = -3.0):
     """Camera path of app/animation.cpp:24-38 with DEG_CHANGE = 360/frames, evaluated in binary32 like the
     reference (M_PIf for the orbit, 22/7 inside Camera::pan, Camera.cpp:10-12,39-48)."""
@@ -381,6 +419,9 @@ CONFIGS = {
     "hw14_dragon_class": lambda **kw: hw14_dragon_class(**kw),
     "synthetic_10M": lambda **kw: synthetic_10m(**kw),
     "degenerate_uv": lambda **kw: degenerate_uv_scene(**kw),
+    "many_meshes": lambda **kw: many_meshes(**kw),
+    "no_lights": lambda **kw: no_lights(**kw),
+    "empty_scene": lambda **kw: empty_scene(**kw),
 }
 
 

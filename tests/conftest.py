@@ -19,6 +19,11 @@ SMALL_SCENES = {
     "hw14_small": dict(builder="hw14_dragon_class", kw=dict(width=192, height=108, sphere_n=24, buckets=24), tex=False),
     "degenerate_uv": dict(builder="degenerate_uv", kw=dict(width=48, height=27, buckets=1), tex=False),
     "uncovered": dict(builder="hw11_room", kw=dict(width=100, height=70, sphere_n=4, buckets=24), tex=False),
+    # > 64 meshes (no per-ray mesh de-duplication), a mirror among them; no lights at all; a 1x1 image; no objects
+    "many_meshes": dict(builder="many_meshes", kw=dict(width=128, height=72, count=70, buckets=24), tex=False),
+    "no_lights": dict(builder="no_lights", kw=dict(width=64, height=36, buckets=1), tex=False),
+    "one_pixel": dict(builder="hw07_scene0", kw=dict(width=1, height=1, buckets=1), tex=False),
+    "empty_scene": dict(builder="empty_scene", kw=dict(width=32, height=18, buckets=1), tex=False),
 }
 
 
