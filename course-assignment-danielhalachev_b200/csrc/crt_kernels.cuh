@@ -930,7 +930,7 @@ CRT_DI void acc_fold(WarpShareS &ws, uint32_t ray, Closest &cl) {
 // owner's accumulator (closest) / occlusion flag (shadow) instead of the parking lane's registers.
 template <bool SHADOW, bool PRIMARY>
 CRT_DI void tri_phase_s(const DScene &sc, WarpShareS &ws, const bool pending, uint32_t &tref, const uint32_t tend, const bool helper,
-                        const uint32_t jown, const uint32_t leafnode, Closest &cl) {
+                        const uint32_t jown, const uint32_t leafnode, Closest &cl, bool &occluded) {
   const uint32_t lane = lane_id();
   const uint32_t cnt = pending ? tend - tref : 0u;
   uint32_t incl = cnt;
@@ -974,7 +974,10 @@ CRT_DI void tri_phase_s(const DScene &sc, WarpShareS &ws, const bool pending, ui
       hm &= hm - 1u;
       const uint32_t o_l = __shfl_sync(CRT_FULL_MASK, own, l);
       if (SHADOW) {
-        if (lane == o_l) ws.occ[jown] = 1u;
+        if (lane == o_l) {
+          ws.occ[jown] = 1u;
+          occluded = true;
+        }
       } else {
         const uint32_t tri_l = __shfl_sync(CRT_FULL_MASK, tri, l);
         const float t_l = __shfl_sync(CRT_FULL_MASK, t, l);
@@ -1096,8 +1099,11 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
       if (exhausted) break;
       continue;
     }
+    // Donations only start once the work queue is dry (before that an idle lane is better used on a fresh ray), so
+    // helpers, paused owners and pending counters only exist in the tail: the bulk of the kernel skips their checks.
+    const bool tail = exhausted;
     // an owner that paused at the end of a mesh tree resumes once its helpers are done
-    if (has_ray && job == 0u && ws->pend[lane] == 0u) {
+    if (tail && has_ray && job == 0u && ws->pend[lane] == 0u) {
       job = 1u;
       jown = lane;
       ws->rayof[lane] = lane;
@@ -1120,11 +1126,11 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
         if (job == 2u) {
           atomicSub(&ws->pend[jown], 1u);
           job = 0u;
-        } else if (ws->pend[lane] != 0u) {
+        } else if (tail && ws->pend[lane] != 0u) {
           job = 0u;  // pause: helpers of this ray are still walking the rest of this mesh tree
           own_below = tv.below;
         } else {
-          acc_fold(*ws, lane, cl);
+          if (tail) acc_fold(*ws, lane, cl);
           hint = 0u;  // node indices of the next tree are unrelated
           if (trav_slow<false, true>(tv, sc) == TRAV_DONE) {
             lv.hit_tri[node] = cl.best_tri;
@@ -1135,7 +1141,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
         }
       }
     }
-    {
+    if (tail) {
       bool took;
       steal_step(*ws, tv, job, jown, hint, took);
       CRT_PC_COUNT(6, __popc(__ballot_sync(CRT_FULL_MASK, took)))
@@ -1159,7 +1165,8 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
     CRT_PC_MARK(2)
     // ---- triangle phase ----
     const bool parked = job != 0u && tv.tref != tv.tend;
-    if (__any_sync(CRT_FULL_MASK, parked)) tri_phase_s<false, PRIMARY>(sc, *ws, parked, tv.tref, tv.tend, job == 2u, jown, tv.leaf, cl);
+    bool unused_occ = false;
+    if (__any_sync(CRT_FULL_MASK, parked)) tri_phase_s<false, PRIMARY>(sc, *ws, parked, tv.tref, tv.tend, job == 2u, jown, tv.leaf, cl, unused_occ);
     CRT_PC_MARK(3)
   }
   CRT_PC_FLUSH(8)
@@ -1173,7 +1180,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
   const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];
   const uint32_t total = n_hits * sc.n_lights;
   const uint32_t lane = lane_id();
-  bool has_ray = false, exhausted = false, dirty = false, own_done = false;
+  bool has_ray = false, exhausted = false, dirty = false, own_done = false, occluded = false;
   uint32_t job = 0, jown = lane, slot = 0, own_below = 0, hint = 0;
   float t_limit = 0.0f, own_limit = 0.0f;
   Ray ray;
@@ -1226,15 +1233,18 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
       if (exhausted) break;
       continue;
     }
-    // any-hit: a ray somebody found occluded needs no more walking, by its owner or by its helpers
-    if (job != 0u && ws->occ[jown] != 0u) {
+    const bool tail = exhausted;  // see k_closest_s
+    // any-hit: a ray somebody found occluded needs no more walking, by its owner or by its helpers.
+    // Before the tail the only finder is the owner itself (register flag `occluded`).
+    if (job != 0u && (occluded || (tail && ws->occ[jown] != 0u))) {
       if (job == 2u) atomicSub(&ws->pend[jown], 1u);
       else own_done = true;
       job = 0u;
+      occluded = false;
       tv.tref = tv.tend = 0u;
     }
     // an owner whose own walk is over retires once its helpers are done
-    if (has_ray && job == 0u && own_done && ws->pend[lane] == 0u) {
+    if (has_ray && job == 0u && own_done && (!tail || ws->pend[lane] == 0u)) {
       lv.vis[slot] = ws->occ[lane] ? 0 : 1;
       has_ray = false;
     }
@@ -1254,7 +1264,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
         }
       }
     }
-    {
+    if (tail) {
       bool took;
       steal_step(*ws, tv, job, jown, hint, took);
       CRT_PC_COUNT(6, __popc(__ballot_sync(CRT_FULL_MASK, took)))
@@ -1277,7 +1287,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
     }
     CRT_PC_MARK(2)
     const bool parked = job != 0u && tv.tref != tv.tend;
-    if (__any_sync(CRT_FULL_MASK, parked)) tri_phase_s<true, false>(sc, *ws, parked, tv.tref, tv.tend, job == 2u, jown, tv.leaf, unused);
+    if (__any_sync(CRT_FULL_MASK, parked)) tri_phase_s<true, false>(sc, *ws, parked, tv.tref, tv.tend, job == 2u, jown, tv.leaf, unused, occluded);
     CRT_PC_MARK(3)
   }
   CRT_PC_FLUSH(16)
