@@ -671,7 +671,7 @@ def main():
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--parallelism", default="frames", choices=["frames", "tiles"],
                     help="N > 1: frames = one frame per GPU per step (weak scaling); tiles = one frame split by tiles (strong)")
-    ap.add_argument("--concurrency", type=int, default=4, help="chunks of a frame in flight on separate streams")
+    ap.add_argument("--concurrency", type=int, default=6, help="chunks of a frame in flight on separate streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--animation", type=int, default=0, help="F > 0: a step is the F-frame orbit animation (config 5), frames round-robin over GPUs")
     args = ap.parse_args()

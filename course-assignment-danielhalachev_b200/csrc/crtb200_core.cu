@@ -128,7 +128,7 @@ struct crtb200_ctx {
     }
   };
   std::vector<QueueSet> sets;
-  uint32_t concurrency = 4;
+  uint32_t concurrency = 6;  // chunks of a host-bound frame in flight (tools/e2e_time.py: 4.93 ms at 6 vs 5.09 at 4 for the 4K frame)
   cudaEvent_t fork_ev = nullptr;
   DevBuf<unsigned long long> stats_dev;
   uint32_t cap_items = 0;
@@ -660,7 +660,9 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
   if (items < 32 * 64) return fail(CRTB200_ERR_MEMORY, "queue budget too small for one chunk at this ray depth");
   // one chunk per set when it fits; two per set when the bands are copied back to the host as they finish, so the
   // copy of one band overlaps the traversal of the next
-  const uint32_t parts = n_sets * ((pipelined && n_sets > 1) ? 2u : 1u);
+  uint32_t per_set = (pipelined && n_sets > 1) ? 2u : 1u;
+  if (const char *env = getenv("CRT_HOST_CHUNKS_PER_SET")) per_set = (uint32_t)std::max(1, std::min(8, atoi(env)));  // tools: e2e tuning
+  const uint32_t parts = n_sets * per_set;
   uint64_t even = ((uint64_t)shard_items + parts - 1) / parts;
   even = ((even + row_items - 1) / row_items) * row_items;
   items = std::min<uint64_t>(items, even);
