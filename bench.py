@@ -289,6 +289,13 @@ def ours_arm(args):
         host8 = [torch.empty((world, H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else [None, None]
         works = [None, None]
     host_frame = torch.empty((H, W, 3), dtype=torch.float32).pin_memory() if (world > 1 and rank == 0) else None
+    copy_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+
+    def to_host_async(dst, src):
+        # device -> pinned host on a side stream, so rank 0's copy engine works while its SMs render the next frame
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):
+            dst.copy_(src, non_blocking=True)
 
     def step(k=0, to_host=False):
         # to_host (e2e legs, N > 1): the step's result also lands in pinned host memory on rank 0
@@ -297,8 +304,10 @@ def ours_arm(args):
             if works[b] is not None:
                 works[b].wait()
                 if to_host and rank == 0:
-                    host8[b].copy_(gflat[b], non_blocking=True)
+                    to_host_async(host8[b], gflat[b])
             ctx.render_device(cam, opt, d_rgb=frame.data_ptr(), d_rgb8=bufs8[b].data_ptr(), stream=stream)
+            if to_host and rank == 0:
+                torch.cuda.current_stream().wait_stream(copy_stream)  # gflat[b] is about to be overwritten by the gather
             works[b] = dist.gather(bufs8[b], gls[b], dst=0, async_op=True)
         elif world > 1:
             sharded.render(cam, max_depth=depth, traversal=args.traversal, frame=frame if rank == 0 else None,
@@ -314,8 +323,10 @@ def ours_arm(args):
                 if works[b] is not None:
                     works[b].wait()
                     if to_host and rank == 0:
-                        host8[b].copy_(gflat[b], non_blocking=True)
+                        to_host_async(host8[b], gflat[b])
                     works[b] = None
+            if to_host and rank == 0:
+                torch.cuda.current_stream().wait_stream(copy_stream)
 
     for k in range(max(args.warmup, 3)):
         step(k)
@@ -584,12 +595,16 @@ def animation_arm(args):
         dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
     rays_seq = int(rays_t.item())
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def finish(b, to_host):
         if works[b] is not None:
             if works[b] is not True:
                 works[b].wait()
-            if to_host and rank == 0:
-                host8[b].copy_(gflat[b], non_blocking=True)
+            if to_host and rank == 0:  # side stream: the copy engine works while the SMs render the next round
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(copy_stream):
+                    host8[b].copy_(gflat[b], non_blocking=True)
             works[b] = None
 
     def sequence(to_host):
@@ -599,6 +614,8 @@ def animation_arm(args):
             f = r * world + rank
             if f < F:
                 ctx.render_device(cams[f], opt, d_rgb=frame.data_ptr(), d_rgb8=bufs8[b].data_ptr(), stream=stream)
+            if to_host and rank == 0:
+                torch.cuda.current_stream().wait_stream(copy_stream)  # gflat[b] is about to be overwritten
             if world > 1:
                 works[b] = dist.gather(bufs8[b], [gflat[b][i] for i in range(world)] if rank == 0 else None, dst=0, async_op=True)
             else:
@@ -606,6 +623,8 @@ def animation_arm(args):
                 works[b] = True
         finish(0, to_host)
         finish(1, to_host)
+        if to_host and rank == 0:
+            torch.cuda.current_stream().wait_stream(copy_stream)
 
     def timed(to_host):
         out = []
