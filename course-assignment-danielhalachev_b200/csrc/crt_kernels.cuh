@@ -34,6 +34,7 @@ struct Frame {
   uint32_t item_begin;                // first level-0 work item of this chunk (shard-local numbering)
   uint32_t n_items0;                  // level-0 work items in this chunk
   uint32_t max_depth;
+  uint32_t resolve;                   // 1 when the frame has secondary levels: k_resolve will read the combine records
   float shadow_bias, reflection_bias, refraction_bias;
 };
 
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(256) k_shade(const DScene sc, const Frame fr, 
       }
       lv.comb[node] = make_uint4(kind, cbase, kind == COMB_REFLECT ? mat_index : cbase + 1, __float_as_uint(fresnel));
     } else {
-      lv.comb[node] = make_uint4(COMB_FINAL, 0, 0, 0);
+      if (fr.resolve) lv.comb[node] = make_uint4(COMB_FINAL, 0, 0, 0);  // diffuse-only frames never read it (16 B / ray saved)
       if (want_diffuse) {
         float4 *q = lv.dq + 3 * (size_t)dslot;
         q[0] = make_float4(P.x, P.y, P.z, __uint_as_float(node));

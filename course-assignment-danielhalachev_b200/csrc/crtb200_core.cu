@@ -815,6 +815,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   fr.shard_count = shard_count;
   fr.mask = c->mask_needed ? c->mask.p : nullptr;
   fr.max_depth = o->max_depth;
+  fr.resolve = (c->has_reflective || c->has_refractive) ? 1u : 0u;
   fr.shadow_bias = o->shadow_bias;
   fr.reflection_bias = o->reflection_bias;
   fr.refraction_bias = o->refraction_bias;
