@@ -50,6 +50,11 @@ struct Levels {
   uint32_t *counts;   // [CRT_MAX_LEVELS] rays per level; [CRT_MAX_LEVELS] = diffuse queue length
   unsigned long long *stats;  // [0..3] rays by type, [4],[5] closest node / triangle tests, [6],[7] shadow
   uint32_t offset[CRT_MAX_LEVELS + 1];
+  // long shadow walks (k_shadow_long): a walk that has taken more than long_budget node-phase iterations is suspended
+  // into ovf[] (2 x uint4 per record) and finished by a whole warp; long_budget = 0 switches this off
+  uint4 *ovf;
+  uint32_t *ovf_ctl;  // [0] records written, [1] records taken
+  uint32_t ovf_cap, long_budget;
 };
 
 enum { COMB_FINAL = 0, COMB_REFLECT = 1, COMB_FRESNEL = 2, COMB_COPY = 3 };
@@ -597,7 +602,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
   const uint32_t total = n_hits * sc.n_lights;
   const uint32_t lane = lane_id();
   bool active = false, exhausted = false, occluded = false;
-  uint32_t slot = 0, n_nodes = 0, n_tris = 0;
+  uint32_t slot = 0, n_nodes = 0, n_tris = 0, walk_iters = 0;
 #if CRT_PHASE_CLOCKS
   uint32_t ray_iters = 0;
 #endif
@@ -630,6 +635,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
         occluded = false;
         slot = hit * sc.n_lights + light;
         active = true;
+        walk_iters = 0;
 #if CRT_PHASE_CLOCKS
         ray_iters = 0;
 #endif
@@ -664,6 +670,18 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
         if (need) ray_iters++;
 #endif
         if (need) need = CRT_NODE_PAIR ? trav_fast2<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit) : trav_fast<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit);
+        if (COUNT == 0 && lv.long_budget) {
+          // a walk past its iteration budget, still inside a mesh tree: hand the rest to k_shadow_long (one warp per ray)
+          if (need && ++walk_iters > lv.long_budget && tv.below) {
+            const uint32_t r = atomicAdd(&lv.ovf_ctl[0], 1u);
+            if (r < lv.ovf_cap) {
+              lv.ovf[2 * (size_t)r] = make_uint4(slot, tv.cur, tv.cend, tv.resume);
+              lv.ovf[2 * (size_t)r + 1] = make_uint4(tv.mref, tv.mend, (uint32_t)tv.seen, (uint32_t)(tv.seen >> 32));
+              active = false;
+              need = false;
+            }
+          }
+        }
       }
       CRT_PC_MARK(2)
       const bool parked = active && tv.tref != tv.tend;
@@ -1293,6 +1311,176 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
   }
   CRT_PC_FLUSH(16)
   (void)dirty; (void)own_below; (void)own_limit;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3 second pass: one WARP per long shadow walk (records written by k_shadow when a walk exceeds lv.long_budget).
+//
+// By the nesting property (crt_device.cuh "wide walk") only a leaf's own box decides whether its triangles are tested,
+// and a shadow ray's answer is an OR over candidates, so the remaining node range [cur, cend) of the suspended walk can
+// be covered in any order.  The warp keeps a LIFO of (node, end of the enclosing range) entries in shared memory:
+// popping (j, limit) loads node j, pushes its next sibling (the first node after j's subtree, if that is still below
+// limit) and, when j's box passes, its first child (j + 1, end of j's subtree).  After a short ramp 32 boxes are tested
+// per iteration instead of one; passing leaves of an iteration are tested together, 32 triangles at a time.  The rest
+// of the ray's itinerary (the remaining meshes of the top-level leaf, the rest of the top-level tree) follows, every
+// mesh tree walked the same way.  The first occluder ends the record.
+// ------------------------------------------------------------------------------------------------------------
+#define CRT_LONG_CAP 2048   // LIFO entries per warp
+#define CRT_LONG_WARPS 2    // warps per CTA (16 KB of LIFO each)
+struct __align__(16) WarpLong {
+  uint2 stack[CRT_LONG_CAP];
+  uint32_t refbase[32], owner[32];
+};
+
+// walks nodes [begin, end) for one ray with the whole warp; true = an occluder within `dist` was found
+template <bool CULL>
+CRT_DI bool long_walk_shadow(const DScene &sc, WarpLong &wl, const Ray &ray, const float dist, const float t_limit, const uint32_t begin,
+                             const uint32_t end) {
+  const uint32_t lane = lane_id();
+  uint32_t sp = 0;
+  if (begin < end) {
+    if (lane == 0) wl.stack[0] = make_uint2(begin, end);
+    sp = 1;
+  }
+  __syncwarp();
+  while (sp) {
+    // pop up to 32 entries; close to capacity fall back to one at a time (a depth-first walk grows by at most one entry per step)
+    const uint32_t n = (CRT_LONG_CAP - sp < 128u) ? 1u : (sp < 32u ? sp : 32u);
+    const bool have = lane < n;
+    uint2 e = make_uint2(0u, 0u);
+    if (have) e = wl.stack[sp - 1u - lane];
+    sp -= n;
+    __syncwarp();
+    bool push_sib = false, push_child = false, leaf_hit = false;
+    uint32_t endj = 0, a = 0, first = 0;
+    if (have) {
+      const float4 lo = __ldg(&sc.nodes[2 * (size_t)e.x]), hi = __ldg(&sc.nodes[2 * (size_t)e.x + 1]);
+      a = __float_as_uint(lo.w);
+      const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
+      endj = leaf ? e.x + 1u : a;
+      push_sib = endj < e.y;
+      float t0, t1;
+      bool pass = slab_test(lo, hi, ray, t0, t1);
+      if (CULL) {
+        const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
+        const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
+        pass = pass && !behind && !beyond;
+      }
+      push_child = pass && !leaf && e.x + 1u < endj;
+      leaf_hit = pass && leaf;
+      first = __float_as_uint(hi.w);
+    }
+    // pushes: sibling below child, so the child's subtree is taken first (depth-first keeps the LIFO short)
+    const uint32_t cnt = (push_sib ? 1u : 0u) + (push_child ? 1u : 0u);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(CRT_FULL_MASK, incl, d);
+      if (lane >= (uint32_t)d) incl += v;
+    }
+    const uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
+    uint32_t at = sp + incl - cnt;
+    if (push_sib) wl.stack[at++] = make_uint2(endj, e.y);
+    if (push_child) wl.stack[at] = make_uint2(e.x + 1u, endj);
+    sp += total;
+    __syncwarp();
+    // triangles of the leaves that passed in this iteration, packed across the warp (cf. tri_phase)
+    if (__any_sync(CRT_FULL_MASK, leaf_hit)) {
+      const uint32_t tcnt = leaf_hit ? (a & ~CRT_LEAF_FLAG) : 0u;
+      uint32_t tincl = tcnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(CRT_FULL_MASK, tincl, d);
+        if (lane >= (uint32_t)d) tincl += v;
+      }
+      const uint32_t ttotal = __shfl_sync(CRT_FULL_MASK, tincl, 31);
+      const uint32_t tstart = tincl - tcnt;
+      if (tcnt) wl.refbase[lane] = first - tstart;
+      for (uint32_t base = 0; base < ttotal; base += 32u) {
+        const bool in_win = tcnt && tstart < base + 32u && tstart + tcnt > base;
+        const uint32_t hp = (in_win && tstart > base) ? tstart - base : 0u;
+        const uint32_t heads = __reduce_or_sync(CRT_FULL_MASK, in_win ? (1u << hp) : 0u);
+        if (in_win) wl.owner[hp] = lane;
+        __syncwarp();
+        const uint32_t g = base + lane;
+        bool hit = false;
+        if (g < ttotal) {
+          const uint32_t own = wl.owner[31 - __clz(heads & (CRT_FULL_MASK >> (31u - lane)))];
+          const uint32_t tri = __ldg(&sc.leaf_refs[wl.refbase[own] + g]);
+          const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
+          const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
+          const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+          float t;
+          V3 p;
+          hit = triangle_test(g0, g1, g2, ray, t, p) && vlen(vsub(p, ray.o)) <= dist;
+        }
+        if (__any_sync(CRT_FULL_MASK, hit)) return true;
+        __syncwarp();
+      }
+    }
+  }
+  return false;
+}
+
+template <bool CULL>
+__global__ void __launch_bounds__(32 * CRT_LONG_WARPS) k_shadow_long(const DScene sc, const Frame fr, const Levels lv) {
+  __shared__ WarpLong s_wl[CRT_LONG_WARPS];
+  WarpLong &wl = s_wl[threadIdx.x >> 5];
+  const uint32_t lane = lane_id();
+  const uint32_t n_rec = min(lv.ovf_ctl[0], lv.ovf_cap);
+  for (;;) {
+    uint32_t r = 0;
+    if (lane == 0) r = atomicAdd(&lv.ovf_ctl[1], 1u);
+    r = __shfl_sync(CRT_FULL_MASK, r, 0);
+    if (r >= n_rec) break;
+    const uint4 r0 = lv.ovf[2 * (size_t)r], r1 = lv.ovf[2 * (size_t)r + 1];
+    const uint32_t slot = r0.x;
+    const uint32_t hit = slot / sc.n_lights, light = slot - hit * sc.n_lights;
+    const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
+    Ray ray;
+    float dist, contrib;
+    shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
+    ray_prepare(ray, false);
+    const float t_limit = fadd(fmul(dist, 1.0001f), 1e-4f);
+    // the rest of the suspended mesh tree, then the rest of the itinerary (trav_step's order of events, warp-uniform)
+    bool occluded = long_walk_shadow<CULL>(sc, wl, ray, dist, t_limit, r0.y, r0.z);
+    uint32_t top = r0.w, mref = r1.x, mend = r1.y;
+    unsigned long long seen = (unsigned long long)r1.z | ((unsigned long long)r1.w << 32);
+    bool below = true;
+    while (!occluded) {
+      if (mref != mend) {
+        const uint32_t m = __ldg(&sc.top_refs[mref++]);
+        const DMesh me = sc.meshes[m];
+        bool skip = sc.materials[me.material].type == 3u;  // shadow rays ignore refractive meshes (AccelerationStructure.cpp:67-71)
+        if (sc.dedup_meshes) {
+          const unsigned long long bit = 1ull << (m & 63u);
+          skip = skip || (seen & bit) != 0ull;
+          seen |= bit;
+        }
+        if (!skip) occluded = long_walk_shadow<CULL>(sc, wl, ray, dist, t_limit, me.node_begin, me.node_end);
+        continue;
+      }
+      below = false;
+      if (top == sc.top_end) break;
+      const float4 lo = __ldg(&sc.nodes[2 * (size_t)top]), hi = __ldg(&sc.nodes[2 * (size_t)top + 1]);
+      const uint32_t a = __float_as_uint(lo.w);
+      const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
+      float t0, t1;
+      bool pass = slab_test(lo, hi, ray, t0, t1);
+      if (CULL) {
+        const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
+        const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
+        pass = pass && !behind && !beyond;
+      }
+      top = (pass || leaf) ? top + 1u : a;
+      if (pass && leaf) {
+        mref = __float_as_uint(hi.w);
+        mend = mref + (a & ~CRT_LEAF_FLAG);
+      }
+    }
+    (void)below;
+    if (lane == 0) lv.vis[slot] = occluded ? 0 : 1;
+  }
 }
 
 // K3b: the light loop of RayTracer::calculateDiffusion (RayTracer.cpp:308-330): per diffuse hit, walk the lights IN

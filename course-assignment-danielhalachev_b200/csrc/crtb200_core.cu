@@ -86,6 +86,7 @@ struct crtb200_ctx {
   int l2_persist = 0;  // CRT_L2_PERSIST: 0 off (default, measured best), 1 arena persisting / rest of it streaming, 2 arena persisting / normal, 3 nodes only
   size_t nodes_bytes = 0;
   DevBuf<float4> wnodes, vtx_normal;
+  uint32_t long_budget = 0;  // CRT_LONG_BUDGET=n: shadow walks longer than n node-phase iterations go to k_shadow_long (0 = off)
   bool nested_ok = false;    // every child box of the uploaded mesh trees lies inside its parent's (crt_device.cuh "wide walk")
   bool use_steal = false;    // CRT_STEAL=1: range-stealing kernels k_*_s (exact, parity green, but measured slower: profiles/r1_tuning.md)
   bool wide_ok = false;      // the 4-wide layout is usable (trees nest and are shallow enough)
@@ -120,11 +121,13 @@ struct crtb200_ctx {
     DevBuf<float> hit_t;
     DevBuf<uint4> comb;
     DevBuf<uint8_t> vis;
+    DevBuf<uint4> ovf;          // suspended long shadow walks (k_shadow_long)
+    DevBuf<uint32_t> ovf_ctl;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     void release() {
       ray_o.release(); ray_d.release(); color.release(); dq.release(); hit_tri.release(); counts.release();
-      work.release(); hit_t.release(); comb.release(); vis.release();
+      work.release(); hit_t.release(); comb.release(); vis.release(); ovf.release(); ovf_ctl.release();
     }
   };
   std::vector<QueueSet> sets;
@@ -197,6 +200,7 @@ int crtb200_create(int device, crtb200_ctx **out) {
   if (const char *env = getenv("CRT_LAYOUT")) c->use_wide = std::string(env) == "wide";
   if (const char *env = getenv("CRT_L2_PERSIST")) c->l2_persist = atoi(env);
   if (const char *env = getenv("CRT_STEAL")) c->use_steal = atoi(env) != 0;
+  if (const char *env = getenv("CRT_LONG_BUDGET")) c->long_budget = (uint32_t)std::max(0, atoi(env));
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
   c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
   if (c->l2_persist && c->l2_persist_max)
@@ -694,6 +698,13 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     CUDA_TRY(q.comb.ensure(total));
     CUDA_TRY(q.dq.ensure(3 * total));
     CUDA_TRY(q.vis.ensure(std::max<uint64_t>(1, total * std::max<uint32_t>(1, c->sc.n_lights))));
+    const uint64_t ovf_cap = std::min<uint64_t>(8ull << 20, std::max<uint64_t>(1024, total * std::max<uint32_t>(1, c->sc.n_lights) / 4));
+    CUDA_TRY(q.ovf.ensure(2 * ovf_cap));
+    CUDA_TRY(q.ovf_ctl.ensure(2));
+    q.lv.ovf = q.ovf.p;
+    q.lv.ovf_ctl = q.ovf_ctl.p;
+    q.lv.ovf_cap = (uint32_t)ovf_cap;
+    q.lv.long_budget = 0;
     CUDA_TRY(q.counts.ensure(CRT_MAX_LEVELS + 1));
     CUDA_TRY(q.work.ensure(CRT_MAX_LEVELS + 2));
     q.lv.ray_o = q.ray_o.p;
@@ -881,6 +892,10 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       c->kev_kind.push_back(1);
     }
     uint32_t *swork = q.work.p + CRT_MAX_LEVELS;
+    // long shadow walks: suspended by k_shadow, finished one warp per ray by k_shadow_long (needs the nesting property)
+    const bool use_long = c->long_budget > 0 && c->nested_ok && o->count_work == 0 && !wide && !steal;
+    q.lv.long_budget = use_long ? c->long_budget : 0u;
+    if (use_long) CUDA_TRY(cudaMemsetAsync(q.ovf_ctl.p, 0, 2 * sizeof(uint32_t), qs));
     if (steal && cull)
       k_shadow_s<CRT_REFILL, true><<<c->blocks_shadow_s, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else if (steal)
@@ -899,6 +914,13 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else
       k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+    if (use_long) {
+      if (cull)
+        k_shadow_long<true><<<c->sm_count * 6, 32 * CRT_LONG_WARPS, 0, qs>>>(c->sc, fr, q.lv);
+      else
+        k_shadow_long<false><<<c->sm_count * 6, 32 * CRT_LONG_WARPS, 0, qs>>>(c->sc, fr, q.lv);
+      launches++;
+    }
     if (per_kernel) cudaEventRecord(next_event(c), qs);
     k_accumulate<<<grid_simple, 256, 0, qs>>>(c->sc, fr, q.lv);
     launches += 2;
