@@ -1325,8 +1325,8 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_
 // of the ray's itinerary (the remaining meshes of the top-level leaf, the rest of the top-level tree) follows, every
 // mesh tree walked the same way.  The first occluder ends the record.
 // ------------------------------------------------------------------------------------------------------------
-#define CRT_LONG_CAP 2048   // LIFO entries per warp
-#define CRT_LONG_WARPS 2    // warps per CTA (16 KB of LIFO each)
+#define CRT_LONG_CAP 512    // LIFO entries per warp (4 KB)
+#define CRT_LONG_WARPS 4    // warps per CTA
 struct __align__(16) WarpLong {
   uint2 stack[CRT_LONG_CAP];
   uint32_t refbase[32], owner[32];
@@ -1339,8 +1339,22 @@ CRT_DI bool long_walk_shadow(const DScene &sc, WarpLong &wl, const Ray &ray, con
   const uint32_t lane = lane_id();
   uint32_t sp = 0;
   if (begin < end) {
-    if (lane == 0) wl.stack[0] = make_uint2(begin, end);
-    sp = 1;
+    // Any node index is a valid start (nesting property), so a long range is cut into 32 index sub-ranges up front:
+    // the 32 lanes unfold 32 sibling chains at once instead of one.  Limits are clamped below, so every node belongs
+    // to exactly one sub-range.
+    const uint32_t len = end - begin;
+    if (len >= 2048u) {
+      const uint32_t step = (len + 31u) / 32u;
+      const uint32_t nsub = (len + step - 1u) / step;  // <= 32
+      if (lane < nsub) {
+        const uint32_t b = begin + lane * step;
+        wl.stack[nsub - 1u - lane] = make_uint2(b, (b + step < end) ? b + step : end);
+      }
+      sp = nsub;
+    } else {
+      if (lane == 0) wl.stack[0] = make_uint2(begin, end);
+      sp = 1;
+    }
   }
   __syncwarp();
   while (sp) {
@@ -1381,7 +1395,7 @@ CRT_DI bool long_walk_shadow(const DScene &sc, WarpLong &wl, const Ray &ray, con
     const uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
     uint32_t at = sp + incl - cnt;
     if (push_sib) wl.stack[at++] = make_uint2(endj, e.y);
-    if (push_child) wl.stack[at] = make_uint2(e.x + 1u, endj);
+    if (push_child) wl.stack[at] = make_uint2(e.x + 1u, endj < e.y ? endj : e.y);
     sp += total;
     __syncwarp();
     // triangles of the leaves that passed in this iteration, packed across the warp (cf. tri_phase)

@@ -916,9 +916,9 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     if (use_long) {
       if (cull)
-        k_shadow_long<true><<<c->sm_count * 6, 32 * CRT_LONG_WARPS, 0, qs>>>(c->sc, fr, q.lv);
+        k_shadow_long<true><<<c->sm_count * 12, 32 * CRT_LONG_WARPS, 0, qs>>>(c->sc, fr, q.lv);
       else
-        k_shadow_long<false><<<c->sm_count * 6, 32 * CRT_LONG_WARPS, 0, qs>>>(c->sc, fr, q.lv);
+        k_shadow_long<false><<<c->sm_count * 12, 32 * CRT_LONG_WARPS, 0, qs>>>(c->sc, fr, q.lv);
       launches++;
     }
     if (per_kernel) cudaEventRecord(next_event(c), qs);
