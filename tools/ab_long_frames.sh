@@ -1,3 +1,5 @@
-cd $GRAFT_REPO_ROOT
+#!/usr/bin/env bash
+# second pass for long shadow walks (CRT_LONG_BUDGET) on whole frames of several scenes -- tools only
+cd "$(dirname "$0")/.."
 t() { python tools/profile_frame.py --workload "$1" --frames 5 --concurrency 1 --shards "$2" 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('%-20s shards %s  %8.3f %8.3f %8.3f' % ('$1', '$2', d['device_ms'], d['closest_ms'], d['shadow_ms']))"; }
 for b in 0 64 128 256; do echo "== CRT_LONG_BUDGET=$b"; for w in synthetic_10M hw11_room_128 hw12_textures; do CRT_LONG_BUDGET=$b t $w 1; done; done
