@@ -26,17 +26,19 @@ namespace crtd {
 //  tri_geom  3 x float4 per triangle: {v0, n.x} {v1, n.y} {v2, n.z}  (48 B: everything Ray::intersectWithTriangle reads)
 //  tri_shade uint4 per triangle: {i0, i1, i2, mesh}  -- only touched once per ray, at shading time
 // ------------------------------------------------------------------------------------------------------------
-//  wnodes    the same mesh trees collapsed two levels at a time into 4-wide nodes of 128 B = one L2 line (8 x float4):
-//            entry k = {min.x, min.y, min.z, max.x} {max.y, max.z, a, b}; the entries are reference nodes (their exact
-//            boxes), in visiting order: for each child (child[1] first) the child itself when it is a leaf, else the
-//            child's children.  leaf entry: a = 0x80000000 | count, b = first reference; inner entry: a = index of the
-//            wide node of that reference node; absent entry: a = 0xFFFFFFFF.  Every mesh starts with a one-entry wide
-//            node holding its root.  See "wide walk" below for why walking this is exact.
+//
+// Conservative culling (traversal mode 0, the default).  DMesh::cull_margin (mu) is computed at upload so that every
+// leaf L listing a triangle T satisfies bbox(T) c inflate(L, mu) and every point the reference's triangle test can
+// accept for T lies within mu of bbox(T) (DESIGN.md section 3.6 has the derivation and the proof of exactness).
+// Consequence: a leaf (or subtree, by box nesting) whose box inflated by mu lies wholly behind the ray origin, or wholly
+// beyond a distance limit, contributes no finite candidate with t >= 0 (resp. t <= limit) -- skipping it removes no
+// candidate that can change the result.  mu = +inf switches culling off for a mesh (trees that do not nest, triangles
+// whose uploaded normal is not their geometric normal).
 struct DMesh {
   uint32_t node_begin, node_end;  // [begin, end) in `nodes`
   uint32_t material;
   uint32_t first_triangle;
-  uint32_t wroot;                 // index of the mesh's one-entry root wide node in `wnodes`, CRT_INVALID for an empty tree
+  float cull_margin;              // mu of this mesh's tree (see above); +inf = never cull
 };
 struct DMaterial {
   uint32_t type, smooth, texture;
@@ -59,7 +61,6 @@ struct DLight {
 
 struct DScene {
   const float4 *nodes;
-  const float4 *wnodes;
   const uint32_t *leaf_refs;
   const uint32_t *top_refs;
   const float4 *tri_geom;
@@ -71,7 +72,7 @@ struct DScene {
   const DTexture *textures;
   const float *texels;
   const DLight *lights;
-  uint32_t n_lights;
+  uint32_t n_lights, n_meshes;
   uint32_t top_begin, top_end;
   uint32_t width, height;
   float bg[3];
@@ -278,8 +279,10 @@ struct Trav {
   uint32_t tref, tend;    // cursor in the current mesh leaf's triangle list
   uint32_t below;         // 1 while working below a top-level leaf (mesh list / mesh trees)
   unsigned long long seen;  // meshes already traversed for this ray (scenes with <= 64 meshes)
-  uint32_t leaf;          // node index of the pending leaf (trav_fast2): encounter-order key for split walks
+  uint32_t leaf;          // node index of the pending leaf (trav_fast2): encounter-order key for the long-walk pass
+  float mu;               // culling margin of the tree being walked, in space units (+inf: top-level tree / culling off)
 };
+#define CRT_INF __int_as_float(0x7f800000)
 CRT_DI void trav_begin(Trav &s, const DScene &sc) {
   s.cur = sc.top_begin;
   s.cend = sc.top_end;
@@ -289,6 +292,45 @@ CRT_DI void trav_begin(Trav &s, const DScene &sc) {
   s.below = 0;
   s.seen = 0ull;
   s.leaf = 0;
+  s.mu = CRT_INF;
+}
+
+// Culling margin for ray r inside a mesh whose upload-time margin is `mesh_mu`: the rounding of the hit point and of
+// the slab parameters is bounded by a few ulp of (|o| + mesh extent); mesh_mu already carries the extent part, the
+// origin part is added here (64 ulp: an order of magnitude above the bound in DESIGN.md section 3.6).  Rays that take
+// the select-exact slab path (axis-parallel / non-finite components) are never culled.
+CRT_DI float cull_margin_for(const Ray &r, const float mesh_mu) {
+  if (r.flags & CRT_RAY_SLOW_MASK) return CRT_INF;
+  return mesh_mu + (64.0f * CRT_FLT_EPSILON) * (fabsf(r.o.x) + fabsf(r.o.y) + fabsf(r.o.z));
+}
+
+// The reference's slab test (pass / fail exactly as BoundingBox::hasIntersection) plus, for CULL, the two conservative
+// skips.  With tn_i / tf_i the near / far slab parameters of axis i and m_i = mu * |1 / d_i| (mu in t units along that axis):
+//   behind : some far plane lies more than mu behind the origin        tf_i < -m_i         (only when `allow_behind`)
+//   beyond : some near plane lies more than mu beyond the limit        tn_i - m_i > limit
+// Both are "box inflated by mu misses the ray segment [0, limit]" written per axis; NaN / +inf operands never cull.
+template <bool CULL>
+CRT_DI bool node_test(const float4 lo, const float4 hi, const Ray &r, const float mu, const float limit, const bool allow_behind) {
+  if (r.flags & CRT_RAY_SLOW_MASK) {
+    float t0, t1;
+    return slab_test_exact(lo, hi, r, t0, t1);
+  }
+  const float ax = fmul(fsub(lo.x, r.o.x), r.inv.x), bx = fmul(fsub(hi.x, r.o.x), r.inv.x);
+  const float ay = fmul(fsub(lo.y, r.o.y), r.inv.y), by = fmul(fsub(hi.y, r.o.y), r.inv.y);
+  const float az = fmul(fsub(lo.z, r.o.z), r.inv.z), bz = fmul(fsub(hi.z, r.o.z), r.inv.z);
+  const float nx = fminf(ax, bx), fx = fmaxf(ax, bx);
+  const float ny = fminf(ay, by), fy = fmaxf(ay, by);
+  const float nz = fminf(az, bz), fz = fmaxf(az, bz);
+  const float t0 = fmaxf(fmaxf(fmaxf(-CRT_FLT_MAX, nx), ny), nz);
+  const float t1 = fminf(fminf(fminf(CRT_FLT_MAX, fx), fy), fz);
+  bool pass = !(t0 > t1);
+  if (CULL) {
+    const float mx = mu * fabsf(r.inv.x), my = mu * fabsf(r.inv.y), mz = mu * fabsf(r.inv.z);
+    const bool behind = allow_behind && ((fx < -mx) || (fy < -my) || (fz < -mz));
+    const bool beyond = (nx - mx > limit) || (ny - my > limit) || (nz - mz > limit);
+    pass = pass && !behind && !beyond;
+  }
+  return pass;
 }
 
 // One traversal micro-step.  Returns 0 = keep stepping, 1 = a triangle list is pending (tref..tend), 2 = traversal
@@ -298,12 +340,14 @@ CRT_DI void trav_begin(Trav &s, const DScene &sc) {
 //                    Exact: a repeated traversal (KDTree.cpp:131-155 does repeat it) yields the same candidates again,
 //                    which can neither replace the kept one (strict <) nor be the first candidate.  Off when counting
 //                    the reference's visit-all work.
-//   CULL             traversal mode 1: additionally skip subtrees whose box lies wholly behind the ray origin (t1 < 0)
-//                    or wholly beyond t_limit (the best hit so far / the light).  NOT the reference's candidate set:
-//                    see DESIGN.md section 3.6 for what can differ and the measured mismatch counts.
+//   CULL             conservative culling inside mesh trees (node_test): `limit` = the best finite hit so far / the
+//                    light distance, `allow_behind` = a finite candidate exists (closest hit) / always (shadow).
 enum { TRAV_STEP = 0, TRAV_LEAF = 1, TRAV_DONE = 2 };
+template <bool SKIP_REFRACTIVE, bool DEDUP, bool CULL>
+CRT_DI int trav_slow(Trav &s, const DScene &sc, const Ray &r);
+
 template <bool SKIP_REFRACTIVE, bool COUNT, bool DEDUP, bool CULL>
-CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float t_limit) {
+CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float limit, const bool allow_behind) {
   if (s.cur != s.cend) {
     const uint32_t idx = s.cur;
     const float4 lo = __ldg(&sc.nodes[2 * (size_t)idx]);
@@ -311,15 +355,7 @@ CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tes
     const uint32_t a = __float_as_uint(lo.w);
     const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
     if (COUNT) node_tests++;
-    float t0, t1;
-    bool pass = slab_test(lo, hi, r, t0, t1);
-    if (CULL) {
-      // safety margins (1e-5 relative, ~170 ulp): a leaf that holds the hit point can only be culled by a rounding
-      // coincidence that is orders of magnitude larger than the slab arithmetic's error
-      const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
-      const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
-      pass = pass && !behind && !beyond;
-    }
+    const bool pass = node_test<CULL>(lo, hi, r, s.mu, limit, allow_behind);
     s.cur = (pass || leaf) ? idx + 1 : a;
     if (pass && leaf) {
       const uint32_t first = __float_as_uint(hi.w), last = first + (a & ~CRT_LEAF_FLAG);
@@ -336,28 +372,7 @@ CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tes
     }
     return TRAV_STEP;
   }
-  if (s.mref != s.mend) {
-    const uint32_t m = __ldg(&sc.top_refs[s.mref++]);
-    const DMesh me = sc.meshes[m];
-    bool skip = SKIP_REFRACTIVE && sc.materials[me.material].type == 3u;
-    if (DEDUP && sc.dedup_meshes) {
-      const unsigned long long bit = 1ull << (m & 63u);
-      skip = skip || (s.seen & bit) != 0ull;
-      s.seen |= bit;
-    }
-    if (!skip) {
-      s.cur = me.node_begin;
-      s.cend = me.node_end;
-    }
-    return TRAV_STEP;
-  }
-  if (s.below) {  // meshes of this top-level leaf are done: back to the top-level tree
-    s.below = 0u;
-    s.cur = s.resume;
-    s.cend = sc.top_end;
-    return TRAV_STEP;
-  }
-  return TRAV_DONE;
+  return trav_slow<SKIP_REFRACTIVE, DEDUP, CULL>(s, sc, r);
 }
 
 // trav_step split in two for the MODE 2 kernels (crt_kernels.cuh), whose tight node loop only wants the AABB step:
@@ -367,7 +382,7 @@ CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tes
 //               current top-level leaf, or back to the top-level tree, or TRAV_DONE.
 // Together they perform exactly the state transitions of trav_step.
 template <bool COUNT, bool CULL>
-CRT_DI bool trav_fast(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float t_limit) {
+CRT_DI bool trav_fast(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float limit, const bool allow_behind) {
   const uint32_t idx = s.cur;
   const float4 lo = __ldg(&sc.nodes[2 * (size_t)idx]);
   const float4 hi = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
@@ -378,13 +393,7 @@ CRT_DI bool trav_fast(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_te
   if (!leaf) asm volatile("prefetch.global.L1 [%0];" ::"l"(&sc.nodes[2 * (size_t)a]));
 #endif
   if (COUNT) node_tests++;
-  float t0, t1;
-  bool pass = slab_test(lo, hi, r, t0, t1);
-  if (CULL) {
-    const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
-    const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
-    pass = pass && !behind && !beyond;
-  }
+  const bool pass = node_test<CULL>(lo, hi, r, s.mu, limit, allow_behind);
   s.cur = (pass || leaf) ? idx + 1 : a;
   if (pass && leaf) {
     const uint32_t first = __float_as_uint(hi.w), last = first + (a & ~CRT_LEAF_FLAG);
@@ -398,9 +407,10 @@ CRT_DI bool trav_fast(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_te
       s.cur = s.cend;
       s.below = 1u;
     }
+    s.leaf = idx;
     return false;
   }
-  return s.cur < s.cend;  // '<': a skip link may jump past the end of a range that was split off (k_*_s kernels)
+  return s.cur < s.cend;
 }
 // trav_fast for two consecutive nodes at once (CRT_NODE_PAIR).  Node idx + 1 is the next node of the walk whenever
 // node idx passes or is a leaf -- about 56 % of the steps on the 1 M-triangle scene -- so its box is loaded and tested
@@ -408,24 +418,15 @@ CRT_DI bool trav_fast(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_te
 // of a loop whose iteration time is the latency of the slowest lane's load.  When node idx fails (an inner node) the
 // second test is simply discarded; testing a node the reference would not have reached cannot change the walk,
 // because only the pass / fail of nodes that ARE reached is acted on.
-// HINT (k_*_s kernels): when node idx passes and has two children, the subtree of the child visited second,
-// [sibling, a0), is work this walk will come back to.  `hint` remembers the outermost such sibling still ahead of the
-// cursor: the place where the walk can be cut with real work on both sides (steal_step).
-template <bool COUNT, bool CULL, bool HINT = false>
-CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float t_limit, uint32_t *hint = nullptr) {
+template <bool COUNT, bool CULL>
+CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float limit, const bool allow_behind) {
   const uint32_t idx = s.cur;
   const bool has2 = idx + 1u < s.cend;
   const uint32_t jdx = has2 ? idx + 1u : idx;
   const float4 lo0 = __ldg(&sc.nodes[2 * (size_t)idx]), hi0 = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
   const float4 lo1 = __ldg(&sc.nodes[2 * (size_t)jdx]), hi1 = __ldg(&sc.nodes[2 * (size_t)jdx + 1]);
-  float t00, t01, t10, t11;
-  bool pass0 = slab_test(lo0, hi0, r, t00, t01);
-  bool pass1 = slab_test(lo1, hi1, r, t10, t11);
-  if (CULL) {
-    const float lim = fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
-    pass0 = pass0 && !(t01 < -(1e-5f * (fabsf(t00) + fabsf(t01)))) && !(t00 > lim);
-    pass1 = pass1 && !(t11 < -(1e-5f * (fabsf(t10) + fabsf(t11)))) && !(t10 > lim);
-  }
+  const bool pass0 = node_test<CULL>(lo0, hi0, r, s.mu, limit, allow_behind);
+  const bool pass1 = node_test<CULL>(lo1, hi1, r, s.mu, limit, allow_behind);
   const uint32_t a0 = __float_as_uint(lo0.w), a1 = __float_as_uint(lo1.w);
   const bool leaf0 = (a0 & CRT_LEAF_FLAG) != 0u, leaf1 = (a1 & CRT_LEAF_FLAG) != 0u;
   if (COUNT) node_tests++;
@@ -433,10 +434,6 @@ CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_t
   // failing leaf) and a second one exists
   const bool second = has2 && (pass0 != leaf0);
   if (COUNT && second) node_tests++;
-  if (HINT) {
-    const uint32_t sib = leaf1 ? idx + 2u : a1;  // first node after the subtree of idx + 1
-    if (has2 && pass0 && !leaf0 && *hint <= idx && sib < a0 && a0 - sib >= 16u && a0 <= s.cend) *hint = sib;
-  }
   const uint32_t a = second ? a1 : a0, b = __float_as_uint(second ? hi1.w : hi0.w), at = second ? idx + 1u : idx;
   const bool pass = second ? pass1 : pass0, leaf = second ? leaf1 : leaf0;
   s.cur = (pass || leaf) ? at + 1u : a;
@@ -458,8 +455,8 @@ CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_t
   return s.cur < s.cend;
 }
 
-template <bool SKIP_REFRACTIVE, bool DEDUP>
-CRT_DI int trav_slow(Trav &s, const DScene &sc) {
+template <bool SKIP_REFRACTIVE, bool DEDUP, bool CULL>
+CRT_DI int trav_slow(Trav &s, const DScene &sc, const Ray &r) {
   if (s.mref != s.mend) {
     const uint32_t m = __ldg(&sc.top_refs[s.mref++]);
     const DMesh me = sc.meshes[m];
@@ -472,6 +469,7 @@ CRT_DI int trav_slow(Trav &s, const DScene &sc) {
     if (!skip) {
       s.cur = me.node_begin;
       s.cend = me.node_end;
+      if (CULL) s.mu = cull_margin_for(r, me.cull_margin);
     }
     return TRAV_STEP;
   }
@@ -479,177 +477,7 @@ CRT_DI int trav_slow(Trav &s, const DScene &sc) {
     s.below = 0u;
     s.cur = s.resume;
     s.cend = sc.top_end;
-    return TRAV_STEP;
-  }
-  return TRAV_DONE;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Wide walk (MODE 3).  The reference visits a leaf iff the slab test passes for the leaf AND all its ancestors
-// (KDTree.cpp:53-72).  Its child boxes are the exact halves of the parent box (BoundingBox.h:60-69: one plane replaced by
-// min + (max - min) / 2, which lies in [min, max] in binary32), and BoundingBox::hasIntersection is monotone in every
-// plane under round-to-nearest: moving min down or max up can only lower t0 / raise t1 (or widen the containment test
-// of a parallel axis), and a NaN never rejects.  So "leaf passes" implies "every ancestor passes": the visited leaves
-// are exactly the leaves whose OWN box passes, in tree order.  Any hierarchy over the same leaves in the same order
-// whose inner tests never reject a passing leaf enumerates the same candidates in the same order; the 4-wide nodes use
-// reference boxes for every entry, so an inner entry rejects only what the reference rejects at that node.
-// crtb200_upload_scene verifies the nesting for the uploaded trees and falls back to the binary walk otherwise.
-// The walk needs a stack of (wide node, remaining entries): one 32-bit word per level in shared memory.
-// ------------------------------------------------------------------------------------------------------------
-#define CRT_WIDE_STACK 16  // levels; upload checks the collapsed depth of every tree against it
-
-struct TravW {
-  uint32_t top;           // cursor in the top-level (binary, skip-linked) tree
-  uint32_t resume;        // top-level cursor to continue from once the current leaf's meshes are done
-  uint32_t mref, mend;    // cursor in the current top-level leaf's mesh list
-  uint32_t below;         // 1 while working below a top-level leaf
-  unsigned long long seen;
-  uint32_t wcur;          // current wide node, CRT_INVALID when not inside a mesh tree
-  uint32_t mask;          // entries of wcur that passed and are still to be taken (bits 0..3)
-  uint32_t sp;            // stack depth
-  uint32_t tref, tend;    // pending triangle range
-};
-CRT_DI void travw_begin(TravW &s, const DScene &sc) {
-  s.top = sc.top_begin;
-  s.resume = sc.top_end;
-  s.mref = s.mend = 0;
-  s.below = 0;
-  s.seen = 0ull;
-  s.wcur = CRT_INVALID;
-  s.mask = 0;
-  s.sp = 0;
-  s.tref = s.tend = 0;
-}
-
-// slab tests of the (up to) four entries of wide node w -> pass mask.  The common ray (finite, no axis-parallel
-// component: slab_test's fast path) gets straight-line code: all eight 16-byte loads of the 128-byte node are issued
-// before the first use and the four tests are independent instruction streams for the scheduler.
-template <bool CULL>
-CRT_DI uint32_t wide_test(const DScene &sc, const uint32_t w, const Ray &r, const float t_limit) {
-  const float4 *p = sc.wnodes + 8 * (size_t)w;
-  uint32_t m = 0;
-  if (r.flags & CRT_RAY_SLOW_MASK) {
-#pragma unroll 1
-    for (int k = 0; k < 4; k++) {
-      const float4 q0 = __ldg(p + 2 * k), q1 = __ldg(p + 2 * k + 1);
-      float t0, t1;
-      bool pass = slab_test_exact(make_float4(q0.x, q0.y, q0.z, 0.f), make_float4(q0.w, q1.x, q1.y, 0.f), r, t0, t1);
-      if (CULL) {
-        const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
-        const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
-        pass = pass && !behind && !beyond;
-      }
-      pass = pass && __float_as_uint(q1.z) != CRT_INVALID;
-      m |= pass ? (1u << k) : 0u;
-    }
-    return m;
-  }
-  float4 q[8];
-#pragma unroll
-  for (int k = 0; k < 8; k++) q[k] = __ldg(p + k);
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const float4 q0 = q[2 * k], q1 = q[2 * k + 1];
-    const float ax = fmul(fsub(q0.x, r.o.x), r.inv.x), bx = fmul(fsub(q0.w, r.o.x), r.inv.x);
-    const float ay = fmul(fsub(q0.y, r.o.y), r.inv.y), by = fmul(fsub(q1.x, r.o.y), r.inv.y);
-    const float az = fmul(fsub(q0.z, r.o.z), r.inv.z), bz = fmul(fsub(q1.y, r.o.z), r.inv.z);
-    const float t0 = fmaxf(fmaxf(fmaxf(-CRT_FLT_MAX, fminf(ax, bx)), fminf(ay, by)), fminf(az, bz));
-    const float t1 = fminf(fminf(fminf(CRT_FLT_MAX, fmaxf(ax, bx)), fmaxf(ay, by)), fmaxf(az, bz));
-    bool pass = !(t0 > t1);
-    if (CULL) {
-      const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
-      const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
-      pass = pass && !behind && !beyond;
-    }
-    pass = pass && __float_as_uint(q1.z) != CRT_INVALID;
-    m |= pass ? (1u << k) : 0u;
-  }
-  return m;
-}
-
-// One step inside a mesh tree for a lane with wcur valid and no pending triangles: take the next passing entry of the
-// current wide node (popping the stack when the node is used up); a leaf entry parks the lane with its triangle range,
-// an inner entry is descended into and its four entries are tested.  Returns true while the lane can take another step.
-template <bool CULL>
-CRT_DI bool travw_fast(TravW &s, const DScene &sc, const Ray &r, uint32_t *stack, const float t_limit) {
-  if (s.mask == 0u) {
-    if (s.sp == 0u) {  // mesh tree finished
-      s.wcur = CRT_INVALID;
-      return false;
-    }
-    const uint32_t e = stack[(--s.sp) * CRT_TRAV_BLOCK];
-    s.wcur = e >> 4;
-    s.mask = e & 15u;  // never 0: only nodes with entries left are pushed
-  }
-  const uint32_t k = (uint32_t)__ffs((int)s.mask) - 1u;
-  s.mask &= s.mask - 1u;
-  const float4 q1 = __ldg(sc.wnodes + 8 * (size_t)s.wcur + 2 * k + 1);
-  const uint32_t a = __float_as_uint(q1.z), b = __float_as_uint(q1.w);
-  if (a & CRT_LEAF_FLAG) {
-    s.tref = b;
-    s.tend = b + (a & ~CRT_LEAF_FLAG);
-    return false;
-  }
-  if (s.mask) stack[(s.sp++) * CRT_TRAV_BLOCK] = (s.wcur << 4) | s.mask;
-  s.wcur = a;
-  s.mask = wide_test<CULL>(sc, a, r, t_limit);
-  return true;
-}
-
-// Everything outside the mesh trees for a lane with wcur invalid and no pending triangles: top-level tree steps, the
-// mesh list of a top-level leaf, the root test of the next mesh.  Same order of events as trav_step.
-template <bool SKIP_REFRACTIVE, bool CULL>
-CRT_DI int travw_slow(TravW &s, const DScene &sc, const Ray &r, const float t_limit) {
-  if (!s.below && s.top != sc.top_end) {
-    const uint32_t idx = s.top;
-    const float4 lo = __ldg(&sc.nodes[2 * (size_t)idx]);
-    const float4 hi = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
-    const uint32_t a = __float_as_uint(lo.w);
-    const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
-    float t0, t1;
-    bool pass = slab_test(lo, hi, r, t0, t1);
-    if (CULL) {
-      const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
-      const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
-      pass = pass && !behind && !beyond;
-    }
-    s.top = (pass || leaf) ? idx + 1 : a;
-    if (pass && leaf) {
-      s.mref = __float_as_uint(hi.w);
-      s.mend = s.mref + (a & ~CRT_LEAF_FLAG);
-      s.resume = s.top;
-      s.below = 1u;
-    }
-    return TRAV_STEP;
-  }
-  if (s.mref != s.mend) {
-    const uint32_t m = __ldg(&sc.top_refs[s.mref++]);
-    const DMesh me = sc.meshes[m];
-    bool skip = (SKIP_REFRACTIVE && sc.materials[me.material].type == 3u) || me.wroot == CRT_INVALID;
-    if (sc.dedup_meshes) {
-      const unsigned long long bit = 1ull << (m & 63u);
-      skip = skip || (s.seen & bit) != 0ull;
-      s.seen |= bit;
-    }
-    if (!skip) {
-      // the root's own box (KDTree.cpp:53-57) = entry 0 of the mesh's root wide node
-      const float4 q0 = __ldg(sc.wnodes + 8 * (size_t)me.wroot), q1 = __ldg(sc.wnodes + 8 * (size_t)me.wroot + 1);
-      float t0, t1;
-      bool pass = slab_test(make_float4(q0.x, q0.y, q0.z, 0.f), make_float4(q0.w, q1.x, q1.y, 0.f), r, t0, t1);
-      if (CULL) {
-        const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
-        const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
-        pass = pass && !behind && !beyond;
-      }
-      s.sp = 0u;
-      s.mask = pass ? 1u : 0u;
-      if (pass) s.wcur = me.wroot;
-    }
-    return TRAV_STEP;
-  }
-  if (s.below) {
-    s.below = 0u;
-    s.top = s.resume;
+    s.mu = CRT_INF;  // the top-level tree is never culled (its leaves list whole meshes)
     return TRAV_STEP;
   }
   return TRAV_DONE;

@@ -5,8 +5,6 @@
 //   K4/K5 k_shade                   per-hit: barycentrics, smooth normal, texture sample, material switch,
 //                                   reflect / refract + Fresnel, compaction of children into the next level's queue
 //   K3  k_shadow                    persistent any-hit traversal, one (diffuse hit, light) pair per lane -> visibility
-//       k_closest_w / k_shadow_w    opt-in (CRT_LAYOUT=wide): the same walks over the 4-wide collapse of the trees
-//       k_closest_s / k_shadow_s    opt-in (CRT_STEAL=1): long walks hand pending sibling subtrees to idle lanes
 //   K3b k_accumulate                in-order light sum per diffuse hit
 //   K6  k_resolve                   bottom-up combine of the ray tree in the reference's expression order
 //   K7  k_store                     level-0 colours -> framebuffer (f32 + PPMColor u8)
@@ -50,11 +48,13 @@ struct Levels {
   uint32_t *counts;   // [CRT_MAX_LEVELS] rays per level; [CRT_MAX_LEVELS] = diffuse queue length
   unsigned long long *stats;  // [0..3] rays by type, [4],[5] closest node / triangle tests, [6],[7] shadow
   uint32_t offset[CRT_MAX_LEVELS + 1];
-  // long shadow walks (k_shadow_long): a walk that has taken more than long_budget node-phase iterations is suspended
-  // into ovf[] (2 x uint4 per record) and finished by a whole warp; long_budget = 0 switches this off
+  // tail hand-off (k_coop): once the work queue of a traversal kernel is dry, the walks still running are written to
+  // ovf[] (3 x uint4 per record) and finished one WARP per ray; tail_grace = 0 switches this off
   uint4 *ovf;
-  uint32_t *ovf_ctl;  // [0] records written, [1] records taken
-  uint32_t ovf_cap, long_budget;
+  uint32_t *ovf_ctl;  // per traversal launch L (level, or CRT_MAX_LEVELS for the shadow pass): [2L] written, [2L+1] taken
+  uint32_t ovf_cap;
+  uint32_t tail_lanes;  // hand off as soon as this few lanes of the warp are still walking ...
+  uint32_t tail_grace;  // ... or after this many rounds past the end of the queue, whichever comes first
 };
 
 enum { COMB_FINAL = 0, COMB_REFLECT = 1, COMB_FRESNEL = 2, COMB_COPY = 3 };
@@ -146,9 +146,6 @@ __device__ unsigned long long g_iter_hist[2][32];  // debug: rays by floor(log2(
 #define CRT_PC_FLUSH(base)
 #endif
 
-#ifndef CRT_TRI_CARRY
-#define CRT_TRI_CARRY 0  // tuning: deal out full 32-slot windows only, the remainder waits for the next triangle phase
-#endif
 #ifndef CRT_NODE_MIN
 #define CRT_NODE_MIN 16  // leave the node phase when fewer lanes than this still need an AABB step (and leaves wait)
 #endif
@@ -185,10 +182,6 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, const
   uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
   const uint32_t start = incl - cnt;
   if (cnt) ws.refbase[lane] = tref - start;
-#if CRT_TRI_CARRY
-  // full windows only (unless `flush`): the tail of the concatenation stays parked and rides with the next phase
-  if (!flush && total >= 32u) total &= ~31u;
-#endif
   for (uint32_t base = 0; base < total; base += 32u) {
     // segment heads of this window: an owner whose range intersects [base, base + 32) marks its first slot in the window
     const bool in_win = cnt && start < base + 32u && start + cnt > base;
@@ -238,6 +231,33 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, const
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Tail hand-off.  A ray is walked by one lane, and 2-3 % of the rays of a large-mesh frame need hundreds of node-phase
+// iterations: once the queue is dry a traversal kernel used to wait 0.3-0.8 ms for its last few lanes.
+// Now a warp whose queue is dry hands the walks it still holds to k_coop: each lane's state goes into one 48-byte record
+//   r0 = {ray id (queue node / visibility slot), cur, cend, resume}     r1 = {mref, mend, seen lo, seen hi}
+//   r2 = {below, bits(mu), bits(best_t), best_tri}
+// written at the top of a round, where no lane has a pending triangle range.  min_t is implied: best_t when that is
+// below +inf, else +inf (closest_offer keeps it so).
+// ------------------------------------------------------------------------------------------------------------
+CRT_DI bool tail_handoff(const Levels &lv, const uint32_t launch, const bool active, uint32_t &grace, const uint32_t id, const Trav &tv,
+                         const float best_t, const uint32_t best_tri) {
+  const uint32_t am = __ballot_sync(CRT_FULL_MASK, active);
+  if (!am) return false;
+  if ((uint32_t)__popc(am) > lv.tail_lanes && ++grace <= lv.tail_grace) return false;
+  uint32_t base = 0;
+  if (lane_id() == 0) base = atomicAdd(&lv.ovf_ctl[2u * launch], (uint32_t)__popc(am));
+  base = __shfl_sync(CRT_FULL_MASK, base, 0);
+  const uint32_t r = base + __popc(am & lanemask_lt());
+  if (!active || r >= lv.ovf_cap) return false;  // a full buffer (never, by its sizing) just leaves the lane walking
+  uint4 *rec = lv.ovf + 3 * (size_t)r;
+  rec[0] = make_uint4(id, tv.cur, tv.cend, tv.resume);
+  rec[1] = make_uint4(tv.mref, tv.mend, (uint32_t)tv.seen, (uint32_t)(tv.seen >> 32));
+  rec[2] = make_uint4(tv.below, __float_as_uint(tv.mu), __float_as_uint(best_t), best_tri);
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K2: closest hit.  Replaces RayTracer::trace -> KDTree<ObjectKDTreeSubTree>::intersect -> KDTree<Triangle>::intersect
 // (RayTracer.cpp:453-458, KDTree.cpp:127-166, 48-87).
@@ -263,7 +283,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
   const uint32_t node_base = lv.offset[level];
   const uint32_t lane = lane_id();
   bool active = false, exhausted = false;
-  uint32_t node = 0, n_nodes = 0, n_tris = 0;
+  uint32_t node = 0, n_nodes = 0, n_tris = 0, grace = 0;
 #if CRT_PHASE_CLOCKS
   uint32_t ray_iters = 0;
 #endif
@@ -315,6 +335,9 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
         }
       }
     }
+    if (!COUNT && exhausted && lv.tail_grace) {
+      if (tail_handoff(lv, level, active, grace, node, tv, cl.best_t, cl.best_tri)) active = false;
+    }
     if (!__any_sync(CRT_FULL_MASK, active)) {
       if (exhausted) break;
       continue;
@@ -326,7 +349,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
       for (;;) {
         const bool slow = active && tv.tref == tv.tend && tv.cur == tv.cend;
         if (!__any_sync(CRT_FULL_MASK, slow)) break;
-        if (slow && trav_slow<false, !COUNT>(tv, sc) == TRAV_DONE) {
+        if (slow && trav_slow<false, !COUNT, CULL>(tv, sc, ray) == TRAV_DONE) {
           lv.hit_tri[node] = cl.best_tri;
           lv.hit_t[node] = cl.best_t;
           active = false;
@@ -342,7 +365,11 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
 #if CRT_PHASE_CLOCKS
         if (need) ray_iters++;
 #endif
-        if (need) need = CRT_NODE_PAIR ? trav_fast2<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t) : trav_fast<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t);
+        if (need) {
+          // conservative culling: beyond the best finite hit; behind the origin once a finite hit exists (crt_device.cuh)
+          const bool fin = cl.min_t < CRT_INF;
+          need = CRT_NODE_PAIR ? trav_fast2<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t, fin) : trav_fast<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t, fin);
+        }
       }
       CRT_PC_MARK(2)
       // ---- triangle phase: all pending leaves, packed across the warp ----
@@ -592,6 +619,12 @@ CRT_DI void shadow_ray_setup(const DScene &sc, const Frame &fr, const V3 P, cons
   ray.d = ld;
 }
 
+// CULL only: no candidate beyond this parameter can satisfy |P - o| <= dist (|d| = 1 within 2 ulp; the slack covers the
+// rounding of P and of the length)
+CRT_DI float shadow_limit(const Ray &ray, const float dist) {
+  return dist * 1.0001f + 1e-4f + 1e-6f * (fabsf(ray.o.x) + fabsf(ray.o.y) + fabsf(ray.o.z));
+}
+
 template <int COUNT, int REFILL, int MODE, bool CULL>
 __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(const DScene sc, const Frame fr, const Levels lv,
                                                                              uint32_t *__restrict__ work_counter) {
@@ -602,7 +635,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
   const uint32_t total = n_hits * sc.n_lights;
   const uint32_t lane = lane_id();
   bool active = false, exhausted = false, occluded = false;
-  uint32_t slot = 0, n_nodes = 0, n_tris = 0, walk_iters = 0;
+  uint32_t slot = 0, n_nodes = 0, n_tris = 0, grace = 0;
 #if CRT_PHASE_CLOCKS
   uint32_t ray_iters = 0;
 #endif
@@ -631,11 +664,10 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
         shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
         ray_prepare(ray, false);
         trav_begin(tv, sc);
-        t_limit = fadd(fmul(dist, 1.0001f), 1e-4f);  // CULL only: nothing beyond the light can satisfy |P - o| <= dist
+        t_limit = shadow_limit(ray, dist);
         occluded = false;
         slot = hit * sc.n_lights + light;
         active = true;
-        walk_iters = 0;
 #if CRT_PHASE_CLOCKS
         ray_iters = 0;
 #endif
@@ -644,6 +676,9 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
           ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
         }
       }
+    }
+    if (COUNT == 0 && exhausted && lv.tail_grace) {
+      if (tail_handoff(lv, CRT_MAX_LEVELS, active, grace, slot, tv, 0.0f, CRT_INVALID)) active = false;
     }
     if (!__any_sync(CRT_FULL_MASK, active)) {
       if (exhausted) break;
@@ -655,7 +690,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
       for (;;) {
         const bool slow = active && tv.tref == tv.tend && tv.cur == tv.cend;
         if (!__any_sync(CRT_FULL_MASK, slow)) break;
-        if (slow && trav_slow<true, (COUNT != 1)>(tv, sc) == TRAV_DONE) {
+        if (slow && trav_slow<true, (COUNT != 1), CULL>(tv, sc, ray) == TRAV_DONE) {
           lv.vis[slot] = occluded ? 0 : 1;
           active = false;
           CRT_PC_RAY_DONE(1, ray_iters)
@@ -669,19 +704,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
 #if CRT_PHASE_CLOCKS
         if (need) ray_iters++;
 #endif
-        if (need) need = CRT_NODE_PAIR ? trav_fast2<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit) : trav_fast<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit);
-        if (COUNT == 0 && lv.long_budget) {
-          // a walk past its iteration budget, still inside a mesh tree: hand the rest to k_shadow_long (one warp per ray)
-          if (need && ++walk_iters > lv.long_budget && tv.below) {
-            const uint32_t r = atomicAdd(&lv.ovf_ctl[0], 1u);
-            if (r < lv.ovf_cap) {
-              lv.ovf[2 * (size_t)r] = make_uint4(slot, tv.cur, tv.cend, tv.resume);
-              lv.ovf[2 * (size_t)r + 1] = make_uint4(tv.mref, tv.mend, (uint32_t)tv.seen, (uint32_t)(tv.seen >> 32));
-              active = false;
-              need = false;
-            }
-          }
-        }
+        if (need) need = CRT_NODE_PAIR ? trav_fast2<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit, true) : trav_fast<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit, true);
       }
       CRT_PC_MARK(2)
       const bool parked = active && tv.tref != tv.tend;
@@ -715,677 +738,78 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K2 / K3 on the 4-wide layout (MODE 3, the default when the uploaded trees nest; crt_device.cuh "wide walk").  Same
-// round structure as MODE 2 -- refill, between-trees bookkeeping, thresholded node phase, warp-cooperative triangle
-// phase -- but a node-phase step descends one wide node (four reference boxes from one 128-byte line), which cuts the
-// chain of dependent loads per ray ~3.5x and gives the four slab tests of a step to the scheduler as independent work.
-// No counters here: the counting modes measure the reference's binary visit-all walk and run the MODE 2 kernels.
-// ------------------------------------------------------------------------------------------------------------
-template <bool PRIMARY, int REFILL, bool CULL>
-__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest_w(const DScene sc, const Frame fr, const Levels lv,
-                                                                                const uint32_t level,
-                                                                                uint32_t *__restrict__ work_counter) {
-  __shared__ WarpShare s_ws[CRT_TRAV_BLOCK / 32];
-  __shared__ uint32_t s_stack[CRT_WIDE_STACK * CRT_TRAV_BLOCK];
-  WarpShare *ws = &s_ws[threadIdx.x >> 5];
-  uint32_t *stack = s_stack + threadIdx.x;
-  const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
-  const uint32_t node_base = lv.offset[level];
-  const uint32_t lane = lane_id();
-  bool active = false, exhausted = false;
-  uint32_t node = 0, n_tris = 0;
-  Ray ray;
-  TravW tv;
-  Closest cl;
-  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
-  ray.flags = 0;
-  travw_begin(tv, sc);
-  closest_begin(cl);
-  for (;;) {
-    const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !active);
-    if (!exhausted && __popc(idle) >= REFILL) {
-      const uint32_t want = __popc(idle);
-      uint32_t start = 0;
-      if (lane == 0) start = atomicAdd(work_counter, want);
-      start = __shfl_sync(CRT_FULL_MASK, start, 0);
-      if (start + want >= total) exhausted = true;
-      const uint32_t i = start + __popc(idle & lanemask_lt());
-      if (!active && i < total) {
-        bool valid = true;
-        if (PRIMARY) {
-          uint32_t row, col;
-          valid = item_pixel(fr, sc, fr.item_begin + i, row, col);
-          if (valid) primary_ray(fr.cam, sc.width, sc.height, row, col, ray.o, ray.d);
-        } else {
-          const float4 o = lv.ray_o[node_base - lv.offset[1] + i];
-          const float4 d = lv.ray_d[node_base - lv.offset[1] + i];
-          ray.o = mk(o.x, o.y, o.z);
-          ray.d = mk(d.x, d.y, d.z);
-        }
-        if (valid) {
-          ray_prepare(ray, PRIMARY);
-          travw_begin(tv, sc);
-          closest_begin(cl);
-          node = node_base + i;
-          active = true;
-          ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.f);
-          ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
-        }
-      }
-    }
-    if (!__any_sync(CRT_FULL_MASK, active)) {
-      if (exhausted) break;
-      continue;
-    }
-    for (;;) {  // between-trees bookkeeping
-      const bool slow = active && tv.tref == tv.tend && tv.wcur == CRT_INVALID;
-      if (!__any_sync(CRT_FULL_MASK, slow)) break;
-      if (slow && travw_slow<false, CULL>(tv, sc, ray, cl.min_t) == TRAV_DONE) {
-        lv.hit_tri[node] = cl.best_tri;
-        lv.hit_t[node] = cl.best_t;
-        active = false;
-      }
-    }
-    bool need = active && tv.tref == tv.tend;
-    const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
-    while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
-      if (need) need = travw_fast<CULL>(tv, sc, ray, stack, cl.min_t);
-    }
-    const bool parked = active && tv.tref != tv.tend;
-    if (__any_sync(CRT_FULL_MASK, parked)) {
-      bool dummy = false;
-      tri_phase<false, PRIMARY, false>(sc, *ws, parked, !__any_sync(CRT_FULL_MASK, need), tv.tref, tv.tend, cl, dummy, n_tris);
-    }
-  }
-}
-
-template <int REFILL, bool CULL>
-__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_w(const DScene sc, const Frame fr, const Levels lv,
-                                                                               uint32_t *__restrict__ work_counter) {
-  __shared__ WarpShare s_ws[CRT_TRAV_BLOCK / 32];
-  __shared__ uint32_t s_stack[CRT_WIDE_STACK * CRT_TRAV_BLOCK];
-  WarpShare *ws = &s_ws[threadIdx.x >> 5];
-  uint32_t *stack = s_stack + threadIdx.x;
-  const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];
-  const uint32_t total = n_hits * sc.n_lights;
-  const uint32_t lane = lane_id();
-  bool active = false, exhausted = false, occluded = false;
-  uint32_t slot = 0, n_tris = 0;
-  float dist = 0.0f, t_limit = 0.0f;
-  Ray ray;
-  TravW tv;
-  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
-  ray.flags = 0;
-  travw_begin(tv, sc);
-  for (;;) {
-    const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !active);
-    if (!exhausted && __popc(idle) >= REFILL) {
-      const uint32_t want = __popc(idle);
-      uint32_t start = 0;
-      if (lane == 0) start = atomicAdd(work_counter, want);
-      start = __shfl_sync(CRT_FULL_MASK, start, 0);
-      if (start + want >= total) exhausted = true;
-      const uint32_t i = start + __popc(idle & lanemask_lt());
-      if (!active && i < total) {
-        const uint32_t light = i / n_hits, hit = i - light * n_hits;
-        const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
-        float contrib;
-        shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
-        ray_prepare(ray, false);
-        travw_begin(tv, sc);
-        t_limit = fadd(fmul(dist, 1.0001f), 1e-4f);  // CULL only
-        occluded = false;
-        slot = hit * sc.n_lights + light;
-        active = true;
-        ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, dist);
-        ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
-      }
-    }
-    if (!__any_sync(CRT_FULL_MASK, active)) {
-      if (exhausted) break;
-      continue;
-    }
-    for (;;) {
-      const bool slow = active && tv.tref == tv.tend && tv.wcur == CRT_INVALID;
-      if (!__any_sync(CRT_FULL_MASK, slow)) break;
-      if (slow && travw_slow<true, CULL>(tv, sc, ray, t_limit) == TRAV_DONE) {
-        lv.vis[slot] = 1;  // an occluded ray never gets here: it retires in the triangle phase
-        active = false;
-      }
-    }
-    bool need = active && tv.tref == tv.tend;
-    const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, active)));
-    while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
-      if (need) need = travw_fast<CULL>(tv, sc, ray, stack, t_limit);
-    }
-    const bool parked = active && tv.tref != tv.tend;
-    if (__any_sync(CRT_FULL_MASK, parked)) {
-      Closest unused;
-      tri_phase<true, false, false>(sc, *ws, parked, !__any_sync(CRT_FULL_MASK, need), tv.tref, tv.tend, unused, occluded, n_tris);
-      if (active && occluded) {  // any-hit: the rest of the walk cannot change the answer
-        tv.tref = tv.tend = 0;
-        lv.vis[slot] = 0;
-        active = false;
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// K2 / K3 with range stealing (the default for the timed path when the uploaded trees nest).
+// K2b / K3b: k_coop -- one WARP per handed-off walk (records written by tail_handoff).
 //
-// Problem (profiles/r1_tuning.md, "tails"): a ray is walked by one lane, and 2-3 % of the rays need 256-1000 node-phase
-// iterations of ~1 us each.  Once the work queue is dry a warp is down to ~11 busy lanes and the kernel ends when the
-// last such ray does: 20-27 % of the kernel span at 4K on one GPU, and almost all of it when a frame is sharded 8 ways.
+// Why any order is allowed.  The reference's child boxes are the exact halves of the parent box (BoundingBox.h:60-69: one
+// plane replaced by min + (max - min) / 2, which lies in [min, max] in binary32) and BoundingBox::hasIntersection is
+// monotone in every plane under round-to-nearest (moving min down or max up can only lower t0 / raise t1 or widen the
+// containment test of a parallel axis; a NaN never rejects).  So "leaf passes" implies "every ancestor passes": the
+// leaves the reference visits (KDTree.cpp:53-72) are exactly the leaves whose OWN box passes, in tree order.
+// crtb200_upload_scene verifies the nesting for the uploaded trees; without it nothing is handed off.  The set of
+// tested triangles therefore does not depend on the order in which a subtree is explored, only the ORDER of the
+// candidates does, and that order is restored from a key:
+//   shadow rays   the answer is an OR over candidates: no order needed
+//   closest hit   KDTree.cpp:75-86 keeps the first candidate unless a later one has strictly smaller t.  Every candidate
+//                 carries key = (leaf node index, leaf reference index) = its position in the reference's encounter
+//                 order; a mesh walk reduces its candidates to (a) the minimum of (t, key) over candidates with
+//                 t < +inf and (b) the candidate with the smallest key, and folds them into the ray's running Closest
+//                 exactly as the in-order sequence of closest_offer calls would have.
 //
-// Cure: the nesting property (crt_device.cuh "wide walk") makes ANY node index a valid place to start a sub-walk -- a
-// walk over nodes [m, e) finds exactly the passing leaves in [m, e), in order, whatever happened before m.  So, after
-// the queue has run dry, a lane whose cursor still has a long way to go hands the upper half [mid, cend) of its range
-// to an idle lane of its warp ("helper"), repeatedly, until everybody is busy.  Exactness of the result:
-//   shadow   the answer is an OR over candidates: helpers raise ws.occ[ray]; order is irrelevant.
-//   closest  the reference keeps "the first candidate unless a later one has strictly smaller t".  Every helper range
-//            lies after its donor's own remaining range in encounter order and inside the same mesh tree, so the owner
-//            (i) finishes its own part sequentially, (ii) waits at the end of that mesh tree until its helpers are done,
-//            (iii) folds their candidates in as if they had come next: helper candidates are reduced order-independently
-//            with the key (leaf node index, position in leaf) = encounter order: first candidate = minimal key,
-//            best = minimal (t, key) over candidates with t < inf.  Only then does the owner go on to the next mesh.
+// The walk.  The warp keeps a LIFO of node indices in shared memory.  One iteration pops up to 32 nodes, one per lane;
+// a lane loads its node, drops it when its whole subtree lies before the hand-off cursor (already walked), tests the
+// box (node_test: the reference's slab test + the conservative culling of crt_device.cuh), and pushes both children of
+// a passing inner node (first child = index + 1, second child = the node's `b` word).  The passing leaves of an
+// iteration are tested together, their triangle lists packed 32 slots at a time like tri_phase.  After a 5-iteration
+// ramp a ray's walk advances 32 boxes per iteration instead of one.
 // ------------------------------------------------------------------------------------------------------------
-#ifndef CRT_MIN_SPLIT
-#define CRT_MIN_SPLIT 16  // nodes: a donated range is at least this long
-#endif
-
-struct __align__(16) WarpShareS {
-  float4 ro[32], rd[32];   // ray table (origin + w = light distance for shadow rays, direction), indexed by ray = owner lane
-  uint32_t refbase[32], owner[32];
-  uint32_t rayof[32];      // lane -> ray it is walking (itself, or the owner it helps)
-  uint32_t pend[32];       // ray -> helper ranges still being walked
-  uint32_t occ[32];        // shadow: ray is occluded
-  float best_t[32];        // closest: candidates found by the helpers of a ray since its last fold
-  uint32_t best_tri[32], first_tri[32];
-  float first_t[32];
-  unsigned long long best_key[32], first_key[32];
+#define CRT_COOP_CAP 512    // LIFO entries per warp (2 KB)
+#define CRT_COOP_WARPS 4    // warps per CTA
+struct __align__(16) WarpCoop {
+  uint32_t stack[CRT_COOP_CAP];
+  uint32_t refbase[32], owner[32], leafidx[32];
 };
 
-CRT_DI void acc_reset(WarpShareS &ws, uint32_t ray) {
-  ws.best_t[ray] = __int_as_float(0x7f800000);
-  ws.best_tri[ray] = CRT_INVALID;
-  ws.best_key[ray] = ~0ull;
-  ws.first_tri[ray] = CRT_INVALID;
-  ws.first_key[ray] = ~0ull;
-  ws.first_t[ray] = 0.0f;
-}
-// one candidate of a helper range (executed by one lane at a time)
-CRT_DI void acc_offer(WarpShareS &ws, uint32_t ray, uint32_t tri, float t, unsigned long long key) {
-  if (key < ws.first_key[ray]) {
-    ws.first_key[ray] = key;
-    ws.first_tri[ray] = tri;
-    ws.first_t[ray] = t;
-  }
-  const float bt = ws.best_t[ray];
-  if (t < __int_as_float(0x7f800000) && (t < bt || (!(bt < t) && key < ws.best_key[ray]))) {
-    ws.best_t[ray] = t;
-    ws.best_tri[ray] = tri;
-    ws.best_key[ray] = key;
-  }
-}
-// the owner folds its helpers' candidates in as the continuation of its own sequence (KDTree.cpp:75-86 semantics)
-CRT_DI void acc_fold(WarpShareS &ws, uint32_t ray, Closest &cl) {
-  const uint32_t ft = ws.first_tri[ray];
-  if (ft == CRT_INVALID) return;
-  if (cl.best_tri == CRT_INVALID) {
-    cl.best_tri = ft;
-    cl.best_t = ws.first_t[ray];
-  }
-  const float bt = ws.best_t[ray];
-  if (ws.best_tri[ray] != CRT_INVALID && bt < cl.min_t) {
-    cl.min_t = bt;
-    cl.best_t = bt;
-    cl.best_tri = ws.best_tri[ray];
-  }
-  acc_reset(ws, ray);
-}
-
-// tri_phase for the stealing kernels: the ray of a parked lane is ws.rayof[lane]; candidates of a helper go to the
-// owner's accumulator (closest) / occlusion flag (shadow) instead of the parking lane's registers.
-template <bool SHADOW, bool PRIMARY>
-CRT_DI void tri_phase_s(const DScene &sc, WarpShareS &ws, const bool pending, uint32_t &tref, const uint32_t tend, const bool helper,
-                        const uint32_t jown, const uint32_t leafnode, Closest &cl, bool &occluded) {
-  const uint32_t lane = lane_id();
-  const uint32_t cnt = pending ? tend - tref : 0u;
-  uint32_t incl = cnt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t v = __shfl_up_sync(CRT_FULL_MASK, incl, d);
-    if (lane >= (uint32_t)d) incl += v;
-  }
-  const uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
-  const uint32_t start = incl - cnt;
-  if (cnt) ws.refbase[lane] = tref - start;
-  for (uint32_t base = 0; base < total; base += 32u) {
-    const bool in_win = cnt && start < base + 32u && start + cnt > base;
-    const uint32_t hp = (in_win && start > base) ? start - base : 0u;
-    const uint32_t heads = __reduce_or_sync(CRT_FULL_MASK, in_win ? (1u << hp) : 0u);
-    if (in_win) ws.owner[hp] = lane;
-    __syncwarp();
-    const uint32_t g = base + lane;
-    bool hit = false;
-    float t = 0.0f;
-    uint32_t tri = 0, own = 0;
-    if (g < total) {
-      own = ws.owner[31 - __clz(heads & (CRT_FULL_MASK >> (31u - lane)))];
-      tri = __ldg(&sc.leaf_refs[ws.refbase[own] + g]);
-      const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
-      const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
-      const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
-      const uint32_t ri = ws.rayof[own];
-      const float4 o4 = ws.ro[ri], d4 = ws.rd[ri];
-      Ray r;
-      r.o = mk(o4.x, o4.y, o4.z);
-      r.d = mk(d4.x, d4.y, d4.z);
-      r.flags = PRIMARY ? 8u : 0u;
-      V3 p;
-      hit = triangle_test(g0, g1, g2, r, t, p);
-      if (SHADOW) hit = hit && vlen(vsub(p, r.o)) <= o4.w;
-    }
-    uint32_t hm = __ballot_sync(CRT_FULL_MASK, hit);
-    while (hm) {
-      const int l = __ffs(hm) - 1;
-      hm &= hm - 1u;
-      const uint32_t o_l = __shfl_sync(CRT_FULL_MASK, own, l);
-      if (SHADOW) {
-        if (lane == o_l) {
-          ws.occ[jown] = 1u;
-          occluded = true;
-        }
-      } else {
-        const uint32_t tri_l = __shfl_sync(CRT_FULL_MASK, tri, l);
-        const float t_l = __shfl_sync(CRT_FULL_MASK, t, l);
-        if (lane == o_l) {
-          if (helper)
-            acc_offer(ws, jown, tri_l, t_l, ((unsigned long long)leafnode << 32) | (unsigned long long)(base + (uint32_t)l - start));
-          else
-            closest_offer(cl, tri_l, t_l);
-        }
-      }
-    }
-    __syncwarp();
-  }
-  if (cnt) tref = tend;
-}
-
-// Donation step (warp-uniform, every round).  job: 0 = nothing to walk, 1 = own ray, 2 = helper range.  A walk with a
-// pending sibling subtree ahead of its cursor (`hint`, trav_fast2) can be cut there: it keeps [cur, hint) and the i-th
-// lane without a job takes [hint, cend) of the i-th such walk.
-CRT_DI void steal_step(WarpShareS &ws, Trav &tv, uint32_t &job, uint32_t &jown, uint32_t &hint, bool &took) {
-  const uint32_t lane = lane_id();
-  const bool avail = job == 0u;
-  const bool donor = job != 0u && tv.tref == tv.tend && tv.below != 0u && hint > tv.cur && hint < tv.cend &&
-                     (tv.cend - hint) >= (uint32_t)CRT_MIN_SPLIT;
-  const uint32_t am = __ballot_sync(CRT_FULL_MASK, avail), dm = __ballot_sync(CRT_FULL_MASK, donor);
-  const int n = min(__popc(am), __popc(dm));
-  took = false;
-  if (n == 0) return;
-  const int ra = __popc(am & lanemask_lt()), rd = __popc(dm & lanemask_lt());
-  const bool give = donor && rd < n, take = avail && ra < n;
-  const int partner = take ? (int)__fns(dm, 0, ra + 1) : (int)lane;
-  const uint32_t p_mid = __shfl_sync(CRT_FULL_MASK, hint, partner);
-  const uint32_t p_end = __shfl_sync(CRT_FULL_MASK, tv.cend, partner);
-  const uint32_t p_own = __shfl_sync(CRT_FULL_MASK, jown, partner);
-  if (give) {
-    tv.cend = hint;
-    hint = 0u;
-    atomicAdd(&ws.pend[jown], 1u);
-  }
-  if (take) {
-    job = 2u;
-    jown = p_own;
-    tv.cur = p_mid;
-    tv.cend = p_end;
-    tv.below = 1u;
-    tv.tref = tv.tend = 0u;
-    ws.rayof[lane] = p_own;
-    hint = 0u;
-    took = true;
-  }
-}
-
-template <bool PRIMARY, int REFILL, bool CULL>
-__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest_s(const DScene sc, const Frame fr, const Levels lv,
-                                                                                const uint32_t level,
-                                                                                uint32_t *__restrict__ work_counter) {
-  __shared__ WarpShareS s_ws[CRT_TRAV_BLOCK / 32];
-  WarpShareS *ws = &s_ws[threadIdx.x >> 5];
-  const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
-  const uint32_t node_base = lv.offset[level];
-  const uint32_t lane = lane_id();
-  bool has_ray = false, exhausted = false, dirty = false;  // dirty: `ray` / tv.below hold a helped ray's state, not the own ray's
-  uint32_t job = 0, jown = lane, node = 0, own_below = 0, hint = 0;
-  Ray ray;
-  Trav tv;
-  Closest cl;
-  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
-  ray.flags = 0;
-  trav_begin(tv, sc);
-  tv.tref = tv.tend = 0;
-  closest_begin(cl);
-  ws->pend[lane] = 0u;
-  ws->rayof[lane] = lane;
-  acc_reset(*ws, lane);
-  __syncwarp();
-  CRT_PC_DECL
-  for (;;) {
-    CRT_PC_MARK(4)
-    CRT_PC_COUNT(7, 1)
-    CRT_PC_TAIL(exhausted, job != 0u)
-    __syncwarp();  // pend / occ / accumulators written by other lanes last round
-    const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !has_ray && job == 0u);
-    if (!exhausted && __popc(idle) >= REFILL) {
-      const uint32_t want = __popc(idle);
-      uint32_t start = 0;
-      if (lane == 0) start = atomicAdd(work_counter, want);
-      start = __shfl_sync(CRT_FULL_MASK, start, 0);
-      if (start + want >= total) exhausted = true;
-      const uint32_t i = start + __popc(idle & lanemask_lt());
-      if (!has_ray && job == 0u && i < total) {
-        bool valid = true;
-        if (PRIMARY) {
-          uint32_t row, col;
-          valid = item_pixel(fr, sc, fr.item_begin + i, row, col);
-          if (valid) primary_ray(fr.cam, sc.width, sc.height, row, col, ray.o, ray.d);
-        } else {
-          const float4 o = lv.ray_o[node_base - lv.offset[1] + i];
-          const float4 d = lv.ray_d[node_base - lv.offset[1] + i];
-          ray.o = mk(o.x, o.y, o.z);
-          ray.d = mk(d.x, d.y, d.z);
-        }
-        if (valid) {
-          ray_prepare(ray, PRIMARY);
-          trav_begin(tv, sc);
-          closest_begin(cl);
-          node = node_base + i;
-          has_ray = true;
-          job = 1u;
-          jown = lane;
-          hint = 0u;
-          dirty = false;
-          ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.f);
-          ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
-          ws->rayof[lane] = lane;
-        }
-      }
-    }
-    if (!__any_sync(CRT_FULL_MASK, has_ray || job != 0u)) {
-      if (exhausted) break;
-      continue;
-    }
-    // Donations only start once the work queue is dry (before that an idle lane is better used on a fresh ray), so
-    // helpers, paused owners and pending counters only exist in the tail: the bulk of the kernel skips their checks.
-    const bool tail = exhausted;
-    // an owner that paused at the end of a mesh tree resumes once its helpers are done
-    if (tail && has_ray && job == 0u && ws->pend[lane] == 0u) {
-      job = 1u;
-      jown = lane;
-      ws->rayof[lane] = lane;
-      if (dirty) {
-        const float4 o = ws->ro[lane], d = ws->rd[lane];
-        ray.o = mk(o.x, o.y, o.z);
-        ray.d = mk(d.x, d.y, d.z);
-        ray_prepare(ray, PRIMARY);
-        tv.below = own_below;
-        dirty = false;
-      }
-      tv.cur = tv.cend = 0u;
-      tv.tref = tv.tend = 0u;
-    }
-    // ---- ranges that ran out: helpers retire, owners fold their helpers' candidates and do the between-trees step ----
-    for (;;) {
-      const bool fin = job != 0u && tv.tref == tv.tend && tv.cur >= tv.cend;
-      if (!__any_sync(CRT_FULL_MASK, fin)) break;
-      if (fin) {
-        if (job == 2u) {
-          atomicSub(&ws->pend[jown], 1u);
-          job = 0u;
-        } else if (tail && ws->pend[lane] != 0u) {
-          job = 0u;  // pause: helpers of this ray are still walking the rest of this mesh tree
-          own_below = tv.below;
-        } else {
-          if (tail) acc_fold(*ws, lane, cl);
-          hint = 0u;  // node indices of the next tree are unrelated
-          if (trav_slow<false, true>(tv, sc) == TRAV_DONE) {
-            lv.hit_tri[node] = cl.best_tri;
-            lv.hit_t[node] = cl.best_t;
-            has_ray = false;
-            job = 0u;
-          }
-        }
-      }
-    }
-    if (tail) {
-      bool took;
-      steal_step(*ws, tv, job, jown, hint, took);
-      CRT_PC_COUNT(6, __popc(__ballot_sync(CRT_FULL_MASK, took)))
-      if (took) {
-        const float4 o = ws->ro[jown], d = ws->rd[jown];
-        ray.o = mk(o.x, o.y, o.z);
-        ray.d = mk(d.x, d.y, d.z);
-        ray_prepare(ray, PRIMARY);
-        dirty = true;
-      }
-    }
-    CRT_PC_MARK(1)
-    // ---- node phase ----
-    bool need = job != 0u && tv.tref == tv.tend && tv.cur < tv.cend;
-    const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, job != 0u)));
-    uint32_t dummy_count = 0;
-    while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
-      CRT_PC_COUNT(5, 1)
-      if (need) need = trav_fast2<false, CULL, true>(tv, sc, ray, dummy_count, job == 1u ? cl.min_t : __int_as_float(0x7f800000), &hint);
-    }
-    CRT_PC_MARK(2)
-    // ---- triangle phase ----
-    const bool parked = job != 0u && tv.tref != tv.tend;
-    bool unused_occ = false;
-    if (__any_sync(CRT_FULL_MASK, parked)) tri_phase_s<false, PRIMARY>(sc, *ws, parked, tv.tref, tv.tend, job == 2u, jown, tv.leaf, cl, unused_occ);
-    CRT_PC_MARK(3)
-  }
-  CRT_PC_FLUSH(8)
-}
-
-template <int REFILL, bool CULL>
-__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow_s(const DScene sc, const Frame fr, const Levels lv,
-                                                                               uint32_t *__restrict__ work_counter) {
-  __shared__ WarpShareS s_ws[CRT_TRAV_BLOCK / 32];
-  WarpShareS *ws = &s_ws[threadIdx.x >> 5];
-  const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];
-  const uint32_t total = n_hits * sc.n_lights;
-  const uint32_t lane = lane_id();
-  bool has_ray = false, exhausted = false, dirty = false, own_done = false, occluded = false;
-  uint32_t job = 0, jown = lane, slot = 0, own_below = 0, hint = 0;
-  float t_limit = 0.0f, own_limit = 0.0f;
-  Ray ray;
-  Trav tv;
-  Closest unused;
-  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
-  ray.flags = 0;
-  trav_begin(tv, sc);
-  tv.tref = tv.tend = 0;
-  ws->pend[lane] = 0u;
-  ws->occ[lane] = 0u;
-  ws->rayof[lane] = lane;
-  __syncwarp();
-  CRT_PC_DECL
-  for (;;) {
-    CRT_PC_MARK(4)
-    CRT_PC_COUNT(7, 1)
-    CRT_PC_TAIL(exhausted, job != 0u)
-    __syncwarp();  // pend / occ / accumulators written by other lanes last round
-    const uint32_t idle = __ballot_sync(CRT_FULL_MASK, !has_ray && job == 0u);
-    if (!exhausted && __popc(idle) >= REFILL) {
-      const uint32_t want = __popc(idle);
-      uint32_t start = 0;
-      if (lane == 0) start = atomicAdd(work_counter, want);
-      start = __shfl_sync(CRT_FULL_MASK, start, 0);
-      if (start + want >= total) exhausted = true;
-      const uint32_t i = start + __popc(idle & lanemask_lt());
-      if (!has_ray && job == 0u && i < total) {
-        const uint32_t light = i / n_hits, hit = i - light * n_hits;
-        const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
-        float contrib, dist;
-        shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
-        ray_prepare(ray, false);
-        trav_begin(tv, sc);
-        t_limit = own_limit = fadd(fmul(dist, 1.0001f), 1e-4f);  // CULL only
-        slot = hit * sc.n_lights + light;
-        has_ray = true;
-        own_done = false;
-        job = 1u;
-        jown = lane;
-        hint = 0u;
-        dirty = false;
-        ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, dist);
-        ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
-        ws->rayof[lane] = lane;
-        ws->occ[lane] = 0u;
-      }
-    }
-    if (!__any_sync(CRT_FULL_MASK, has_ray || job != 0u)) {
-      if (exhausted) break;
-      continue;
-    }
-    const bool tail = exhausted;  // see k_closest_s
-    // any-hit: a ray somebody found occluded needs no more walking, by its owner or by its helpers.
-    // Before the tail the only finder is the owner itself (register flag `occluded`).
-    if (job != 0u && (occluded || (tail && ws->occ[jown] != 0u))) {
-      if (job == 2u) atomicSub(&ws->pend[jown], 1u);
-      else own_done = true;
-      job = 0u;
-      occluded = false;
-      tv.tref = tv.tend = 0u;
-    }
-    // an owner whose own walk is over retires once its helpers are done
-    if (has_ray && job == 0u && own_done && (!tail || ws->pend[lane] == 0u)) {
-      lv.vis[slot] = ws->occ[lane] ? 0 : 1;
-      has_ray = false;
-    }
-    for (;;) {
-      const bool fin = job != 0u && tv.tref == tv.tend && tv.cur >= tv.cend;
-      if (!__any_sync(CRT_FULL_MASK, fin)) break;
-      if (fin) {
-        if (job == 2u) {
-          atomicSub(&ws->pend[jown], 1u);
-          job = 0u;
-        } else {
-          hint = 0u;  // node indices of the next tree are unrelated
-          if (trav_slow<true, true>(tv, sc) == TRAV_DONE) {
-            own_done = true;  // retires above, next round, when no helper of this ray is left
-            job = 0u;
-          }
-        }
-      }
-    }
-    if (tail) {
-      bool took;
-      steal_step(*ws, tv, job, jown, hint, took);
-      CRT_PC_COUNT(6, __popc(__ballot_sync(CRT_FULL_MASK, took)))
-      if (took) {
-        const float4 o = ws->ro[jown], d = ws->rd[jown];
-        ray.o = mk(o.x, o.y, o.z);
-        ray.d = mk(d.x, d.y, d.z);
-        ray_prepare(ray, false);
-        t_limit = fadd(fmul(o.w, 1.0001f), 1e-4f);
-        dirty = true;
-      }
-    }
-    CRT_PC_MARK(1)
-    bool need = job != 0u && tv.tref == tv.tend && tv.cur < tv.cend;
-    const uint32_t thr = node_threshold(__popc(__ballot_sync(CRT_FULL_MASK, job != 0u)));
-    uint32_t dummy_count = 0;
-    while ((uint32_t)__popc(__ballot_sync(CRT_FULL_MASK, need)) >= thr) {
-      CRT_PC_COUNT(5, 1)
-      if (need) need = trav_fast2<false, CULL, true>(tv, sc, ray, dummy_count, t_limit, &hint);
-    }
-    CRT_PC_MARK(2)
-    const bool parked = job != 0u && tv.tref != tv.tend;
-    if (__any_sync(CRT_FULL_MASK, parked)) tri_phase_s<true, false>(sc, *ws, parked, tv.tref, tv.tend, job == 2u, jown, tv.leaf, unused, occluded);
-    CRT_PC_MARK(3)
-  }
-  CRT_PC_FLUSH(16)
-  (void)dirty; (void)own_below; (void)own_limit;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// K3 second pass: one WARP per long shadow walk (records written by k_shadow when a walk exceeds lv.long_budget).
-//
-// By the nesting property (crt_device.cuh "wide walk") only a leaf's own box decides whether its triangles are tested,
-// and a shadow ray's answer is an OR over candidates, so the remaining node range [cur, cend) of the suspended walk can
-// be covered in any order.  The warp keeps a LIFO of (node, end of the enclosing range) entries in shared memory:
-// popping (j, limit) loads node j, pushes its next sibling (the first node after j's subtree, if that is still below
-// limit) and, when j's box passes, its first child (j + 1, end of j's subtree).  After a short ramp 32 boxes are tested
-// per iteration instead of one; passing leaves of an iteration are tested together, 32 triangles at a time.  The rest
-// of the ray's itinerary (the remaining meshes of the top-level leaf, the rest of the top-level tree) follows, every
-// mesh tree walked the same way.  The first occluder ends the record.
-// ------------------------------------------------------------------------------------------------------------
-#define CRT_LONG_CAP 512    // LIFO entries per warp (4 KB)
-#define CRT_LONG_WARPS 4    // warps per CTA
-struct __align__(16) WarpLong {
-  uint2 stack[CRT_LONG_CAP];
-  uint32_t refbase[32], owner[32];
+struct CoopBest {            // per-lane partial result of one mesh walk (closest hit)
+  float t;                   // (a) smallest t < +inf seen by this lane, ties by key
+  unsigned long long key;
+  uint32_t tri;
+  unsigned long long fkey;   // (b) smallest key seen by this lane, whatever its t
+  float ft;
+  uint32_t ftri;
 };
+#define CRT_KEY_NONE 0xFFFFFFFFFFFFFFFFull
 
-// walks nodes [begin, end) for one ray with the whole warp; true = an occluder within `dist` was found
-template <bool CULL>
-CRT_DI bool long_walk_shadow(const DScene &sc, WarpLong &wl, const Ray &ray, const float dist, const float t_limit, const uint32_t begin,
-                             const uint32_t end) {
+// Walks the nodes of mesh tree [root, end) that lie at or after `from` (visiting order) with the whole warp.
+// SHADOW: returns true as soon as a candidate within `dist` is found.  CLOSEST: candidates go to cb; `lim` (warp-uniform)
+// is the best finite t known so far and tightens as the walk finds closer candidates.
+template <bool SHADOW, bool CULL>
+CRT_DI bool coop_walk(const DScene &sc, WarpCoop &wc, const Ray &ray, const float dist, const uint32_t root, const uint32_t from,
+                      const float mu, float &lim, CoopBest &cb) {
   const uint32_t lane = lane_id();
-  uint32_t sp = 0;
-  if (begin < end) {
-    // Any node index is a valid start (nesting property), so a long range is cut into 32 index sub-ranges up front:
-    // the 32 lanes unfold 32 sibling chains at once instead of one.  Limits are clamped below, so every node belongs
-    // to exactly one sub-range.
-    const uint32_t len = end - begin;
-    if (len >= 2048u) {
-      const uint32_t step = (len + 31u) / 32u;
-      const uint32_t nsub = (len + step - 1u) / step;  // <= 32
-      if (lane < nsub) {
-        const uint32_t b = begin + lane * step;
-        wl.stack[nsub - 1u - lane] = make_uint2(b, (b + step < end) ? b + step : end);
-      }
-      sp = nsub;
-    } else {
-      if (lane == 0) wl.stack[0] = make_uint2(begin, end);
-      sp = 1;
-    }
-  }
+  uint32_t sp = 1;
+  if (lane == 0) wc.stack[0] = root;
   __syncwarp();
   while (sp) {
-    // pop up to 32 entries; close to capacity fall back to one at a time (a depth-first walk grows by at most one entry per step)
-    const uint32_t n = (CRT_LONG_CAP - sp < 128u) ? 1u : (sp < 32u ? sp : 32u);
+    // pop up to 32 entries; close to capacity fall back to one at a time (then the LIFO grows by at most one entry per step)
+    const uint32_t n = (CRT_COOP_CAP - sp < 72u) ? 1u : (sp < 32u ? sp : 32u);
     const bool have = lane < n;
-    uint2 e = make_uint2(0u, 0u);
-    if (have) e = wl.stack[sp - 1u - lane];
+    uint32_t j = 0;
+    if (have) j = wc.stack[sp - 1u - lane];
     sp -= n;
     __syncwarp();
-    bool push_sib = false, push_child = false, leaf_hit = false;
-    uint32_t endj = 0, a = 0, first = 0;
+    bool leaf_hit = false;
+    uint32_t a = 0, b = CRT_INVALID, cnt = 0;
     if (have) {
-      const float4 lo = __ldg(&sc.nodes[2 * (size_t)e.x]), hi = __ldg(&sc.nodes[2 * (size_t)e.x + 1]);
+      const float4 lo = __ldg(&sc.nodes[2 * (size_t)j]), hi = __ldg(&sc.nodes[2 * (size_t)j + 1]);
       a = __float_as_uint(lo.w);
+      b = __float_as_uint(hi.w);
       const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
-      endj = leaf ? e.x + 1u : a;
-      push_sib = endj < e.y;
-      float t0, t1;
-      bool pass = slab_test(lo, hi, ray, t0, t1);
-      if (CULL) {
-        const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
-        const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
-        pass = pass && !behind && !beyond;
+      const uint32_t endj = leaf ? j + 1u : a;
+      if (endj > from && node_test<CULL>(lo, hi, ray, mu, lim, SHADOW || lim < CRT_INF)) {
+        leaf_hit = leaf;
+        if (!leaf) cnt = (b != CRT_INVALID) ? 2u : 1u;
       }
-      push_child = pass && !leaf && e.x + 1u < endj;
-      leaf_hit = pass && leaf;
-      first = __float_as_uint(hi.w);
     }
-    // pushes: sibling below child, so the child's subtree is taken first (depth-first keeps the LIFO short)
-    const uint32_t cnt = (push_sib ? 1u : 0u) + (push_child ? 1u : 0u);
     uint32_t incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1394,8 +818,8 @@ CRT_DI bool long_walk_shadow(const DScene &sc, WarpLong &wl, const Ray &ray, con
     }
     const uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
     uint32_t at = sp + incl - cnt;
-    if (push_sib) wl.stack[at++] = make_uint2(endj, e.y);
-    if (push_child) wl.stack[at] = make_uint2(e.x + 1u, endj < e.y ? endj : e.y);
+    if (cnt == 2u) wc.stack[at++] = b;   // second child below the first: the first child's subtree is taken first
+    if (cnt) wc.stack[at] = j + 1u;
     sp += total;
     __syncwarp();
     // triangles of the leaves that passed in this iteration, packed across the warp (cf. tri_phase)
@@ -1409,26 +833,53 @@ CRT_DI bool long_walk_shadow(const DScene &sc, WarpLong &wl, const Ray &ray, con
       }
       const uint32_t ttotal = __shfl_sync(CRT_FULL_MASK, tincl, 31);
       const uint32_t tstart = tincl - tcnt;
-      if (tcnt) wl.refbase[lane] = first - tstart;
+      if (tcnt) {
+        wc.refbase[lane] = b - tstart;
+        wc.leafidx[lane] = j;
+      }
       for (uint32_t base = 0; base < ttotal; base += 32u) {
         const bool in_win = tcnt && tstart < base + 32u && tstart + tcnt > base;
         const uint32_t hp = (in_win && tstart > base) ? tstart - base : 0u;
         const uint32_t heads = __reduce_or_sync(CRT_FULL_MASK, in_win ? (1u << hp) : 0u);
-        if (in_win) wl.owner[hp] = lane;
+        if (in_win) wc.owner[hp] = lane;
         __syncwarp();
         const uint32_t g = base + lane;
         bool hit = false;
+        float t = 0.0f;
         if (g < ttotal) {
-          const uint32_t own = wl.owner[31 - __clz(heads & (CRT_FULL_MASK >> (31u - lane)))];
-          const uint32_t tri = __ldg(&sc.leaf_refs[wl.refbase[own] + g]);
+          const uint32_t own = wc.owner[31 - __clz(heads & (CRT_FULL_MASK >> (31u - lane)))];
+          const uint32_t ref = wc.refbase[own] + g;
+          const uint32_t tri = __ldg(&sc.leaf_refs[ref]);
           const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
           const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
           const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
-          float t;
           V3 p;
-          hit = triangle_test(g0, g1, g2, ray, t, p) && vlen(vsub(p, ray.o)) <= dist;
+          hit = triangle_test(g0, g1, g2, ray, t, p);
+          if (SHADOW) {
+            hit = hit && vlen(vsub(p, ray.o)) <= dist;
+          } else if (hit) {
+            const unsigned long long key = ((unsigned long long)wc.leafidx[own] << 32) | ref;
+            if (key < cb.fkey) {
+              cb.fkey = key;
+              cb.ft = t;
+              cb.ftri = tri;
+            }
+            if (t < CRT_INF && (t < cb.t || (t == cb.t && key < cb.key))) {
+              cb.t = t;
+              cb.key = key;
+              cb.tri = tri;
+            }
+          }
         }
-        if (__any_sync(CRT_FULL_MASK, hit)) return true;
+        if (SHADOW) {
+          if (__any_sync(CRT_FULL_MASK, hit)) return true;
+        } else if (CULL) {
+          // tighten the culling limit: smallest finite t of this window (t >= 0, so the int order is the float order; -0.0
+          // sorts first, which is still a correct bound)
+          const int m = __reduce_min_sync(CRT_FULL_MASK, (hit && t < CRT_INF) ? __float_as_int(t) : 0x7f800000);
+          const float tm = __int_as_float(m);
+          if (tm < lim) lim = tm;
+        }
         __syncwarp();
       }
     }
@@ -1436,64 +887,157 @@ CRT_DI bool long_walk_shadow(const DScene &sc, WarpLong &wl, const Ray &ray, con
   return false;
 }
 
-template <bool CULL>
-__global__ void __launch_bounds__(32 * CRT_LONG_WARPS) k_shadow_long(const DScene sc, const Frame fr, const Levels lv) {
-  __shared__ WarpLong s_wl[CRT_LONG_WARPS];
-  WarpLong &wl = s_wl[threadIdx.x >> 5];
+// fold the lanes' partial results of one mesh walk into the ray's running Closest (all lanes end with the same cl)
+CRT_DI void coop_fold(CoopBest &cb, Closest &cl) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const float t = __shfl_xor_sync(CRT_FULL_MASK, cb.t, d);
+    const unsigned long long key = __shfl_xor_sync(CRT_FULL_MASK, cb.key, d);
+    const uint32_t tri = __shfl_xor_sync(CRT_FULL_MASK, cb.tri, d);
+    if (t < cb.t || (t == cb.t && key < cb.key)) {
+      cb.t = t;
+      cb.key = key;
+      cb.tri = tri;
+    }
+    const unsigned long long fkey = __shfl_xor_sync(CRT_FULL_MASK, cb.fkey, d);
+    const float ft = __shfl_xor_sync(CRT_FULL_MASK, cb.ft, d);
+    const uint32_t ftri = __shfl_xor_sync(CRT_FULL_MASK, cb.ftri, d);
+    if (fkey < cb.fkey) {
+      cb.fkey = fkey;
+      cb.ft = ft;
+      cb.ftri = ftri;
+    }
+  }
+  // = closest_offer over the mesh's candidates in key order: the first one is kept if nothing was kept before, and the
+  // first one achieving the smallest t < +inf replaces it iff that t is strictly below the running minimum
+  if (cb.fkey != CRT_KEY_NONE && cl.best_tri == CRT_INVALID) {
+    cl.best_tri = cb.ftri;
+    cl.best_t = cb.ft;
+  }
+  if (cb.key != CRT_KEY_NONE && cb.t < cl.min_t) {
+    cl.min_t = cb.t;
+    cl.best_t = cb.t;
+    cl.best_tri = cb.tri;
+  }
+}
+
+template <bool SHADOW, bool PRIMARY, bool CULL>
+__global__ void __launch_bounds__(32 * CRT_COOP_WARPS) k_coop(const DScene sc, const Frame fr, const Levels lv, const uint32_t level) {
+  __shared__ WarpCoop s_wc[CRT_COOP_WARPS];
+  WarpCoop &wc = s_wc[threadIdx.x >> 5];
   const uint32_t lane = lane_id();
-  const uint32_t n_rec = min(lv.ovf_ctl[0], lv.ovf_cap);
+  const uint32_t launch = SHADOW ? (uint32_t)CRT_MAX_LEVELS : level;
+  const uint32_t n_rec = min(lv.ovf_ctl[2u * launch], lv.ovf_cap);
   for (;;) {
     uint32_t r = 0;
-    if (lane == 0) r = atomicAdd(&lv.ovf_ctl[1], 1u);
+    if (lane == 0) r = atomicAdd(&lv.ovf_ctl[2u * launch + 1u], 1u);
     r = __shfl_sync(CRT_FULL_MASK, r, 0);
     if (r >= n_rec) break;
-    const uint4 r0 = lv.ovf[2 * (size_t)r], r1 = lv.ovf[2 * (size_t)r + 1];
-    const uint32_t slot = r0.x;
-    const uint32_t hit = slot / sc.n_lights, light = slot - hit * sc.n_lights;
-    const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
+    const uint4 r0 = lv.ovf[3 * (size_t)r], r1 = lv.ovf[3 * (size_t)r + 1], r2 = lv.ovf[3 * (size_t)r + 2];
+    const uint32_t id = r0.x;
     Ray ray;
-    float dist, contrib;
-    shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
-    ray_prepare(ray, false);
-    const float t_limit = fadd(fmul(dist, 1.0001f), 1e-4f);
-    // the rest of the suspended mesh tree, then the rest of the itinerary (trav_step's order of events, warp-uniform)
-    bool occluded = long_walk_shadow<CULL>(sc, wl, ray, dist, t_limit, r0.y, r0.z);
-    uint32_t top = r0.w, mref = r1.x, mend = r1.y;
+    float dist = 0.0f;
+    if (SHADOW) {
+      const uint32_t hit = id / sc.n_lights, light = id - hit * sc.n_lights;
+      const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
+      float contrib;
+      shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
+    } else if (PRIMARY) {
+      uint32_t row, col;
+      item_pixel(fr, sc, fr.item_begin + (id - lv.offset[0]), row, col);  // valid: the main kernel started this ray
+      primary_ray(fr.cam, sc.width, sc.height, row, col, ray.o, ray.d);
+    } else {
+      const float4 o = lv.ray_o[id - lv.offset[1]], d = lv.ray_d[id - lv.offset[1]];
+      ray.o = mk(o.x, o.y, o.z);
+      ray.d = mk(d.x, d.y, d.z);
+    }
+    ray_prepare(ray, PRIMARY);
+    // the walk's state where the main kernel left it (all warp-uniform from here on)
+    uint32_t cur = r0.y, cend = r0.z, resume = r0.w, mref = r1.x, mend = r1.y, below = r2.x;
     unsigned long long seen = (unsigned long long)r1.z | ((unsigned long long)r1.w << 32);
-    bool below = true;
-    while (!occluded) {
+    float mu = __uint_as_float(r2.y);
+    Closest cl;
+    cl.best_t = __uint_as_float(r2.z);
+    cl.best_tri = r2.w;
+    cl.min_t = (cl.best_tri != CRT_INVALID && cl.best_t < CRT_INF) ? cl.best_t : CRT_INF;
+    float lim = SHADOW ? shadow_limit(ray, dist) : cl.min_t;
+    bool occluded = false;
+    for (;;) {
+      if (cur < cend) {
+        if (below) {
+          // the rest of a mesh tree: [cur, cend) of the tree whose range contains cur
+          uint32_t root = CRT_INVALID;
+          for (uint32_t m0 = 0; root == CRT_INVALID; m0 += 32u) {  // cur lies in exactly one mesh's node range
+            const uint32_t m = m0 + lane;
+            uint32_t nb = CRT_INVALID;
+            if (m < sc.n_meshes) {
+              const DMesh me = sc.meshes[m];
+              if (cur >= me.node_begin && cur < me.node_end) nb = me.node_begin;
+            }
+            root = __reduce_min_sync(CRT_FULL_MASK, nb);
+            if (m0 + 32u >= sc.n_meshes) break;
+          }
+          if (root != CRT_INVALID) {
+            CoopBest cb;
+            cb.t = CRT_INF;
+            cb.key = cb.fkey = CRT_KEY_NONE;
+            cb.tri = cb.ftri = CRT_INVALID;
+            cb.ft = 0.0f;
+            occluded = coop_walk<SHADOW, CULL>(sc, wc, ray, dist, root, cur, mu, lim, cb);
+            if (SHADOW) {
+              if (occluded) break;
+            } else {
+              coop_fold(cb, cl);
+              lim = cl.min_t;
+            }
+          }
+          cur = cend;
+        } else {
+          // one step in the top-level tree (a handful of nodes: every lane does the same step; never culled)
+          const float4 lo = __ldg(&sc.nodes[2 * (size_t)cur]), hi = __ldg(&sc.nodes[2 * (size_t)cur + 1]);
+          const uint32_t a = __float_as_uint(lo.w);
+          const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
+          const bool pass = node_test<false>(lo, hi, ray, CRT_INF, CRT_INF, false);
+          cur = (pass || leaf) ? cur + 1u : a;
+          if (pass && leaf) {
+            mref = __float_as_uint(hi.w);
+            mend = mref + (a & ~CRT_LEAF_FLAG);
+            resume = cur;
+            cur = cend;
+            below = 1u;
+          }
+        }
+        continue;
+      }
       if (mref != mend) {
         const uint32_t m = __ldg(&sc.top_refs[mref++]);
         const DMesh me = sc.meshes[m];
-        bool skip = sc.materials[me.material].type == 3u;  // shadow rays ignore refractive meshes (AccelerationStructure.cpp:67-71)
+        bool skip = SHADOW && sc.materials[me.material].type == 3u;  // shadow rays ignore refractive meshes (AccelerationStructure.cpp:67-71)
         if (sc.dedup_meshes) {
           const unsigned long long bit = 1ull << (m & 63u);
           skip = skip || (seen & bit) != 0ull;
           seen |= bit;
         }
-        if (!skip) occluded = long_walk_shadow<CULL>(sc, wl, ray, dist, t_limit, me.node_begin, me.node_end);
+        if (!skip) {
+          cur = me.node_begin;
+          cend = me.node_end;
+          mu = CULL ? cull_margin_for(ray, me.cull_margin) : CRT_INF;
+        }
         continue;
       }
-      below = false;
-      if (top == sc.top_end) break;
-      const float4 lo = __ldg(&sc.nodes[2 * (size_t)top]), hi = __ldg(&sc.nodes[2 * (size_t)top + 1]);
-      const uint32_t a = __float_as_uint(lo.w);
-      const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
-      float t0, t1;
-      bool pass = slab_test(lo, hi, ray, t0, t1);
-      if (CULL) {
-        const bool behind = t1 < -(1e-5f * (fabsf(t0) + fabsf(t1)));
-        const bool beyond = t0 > fadd(t_limit, fmul(1e-5f, fabsf(t_limit)));
-        pass = pass && !behind && !beyond;
-      }
-      top = (pass || leaf) ? top + 1u : a;
-      if (pass && leaf) {
-        mref = __float_as_uint(hi.w);
-        mend = mref + (a & ~CRT_LEAF_FLAG);
+      if (!below) break;
+      below = 0u;
+      cur = resume;
+      cend = sc.top_end;
+    }
+    if (lane == 0) {
+      if (SHADOW) {
+        lv.vis[id] = occluded ? 0 : 1;
+      } else {
+        lv.hit_tri[id] = cl.best_tri;
+        lv.hit_t[id] = cl.best_t;
       }
     }
-    (void)below;
-    if (lane == 0) lv.vis[slot] = occluded ? 0 : 1;
   }
 }
 
@@ -1675,7 +1219,7 @@ __global__ void __launch_bounds__(256) k_query(const DScene sc, const float *__r
       bool occ = false;
       for (;;) {
         int st = TRAV_STEP;
-        while (st == TRAV_STEP) st = trav_step<true, false, true, false>(tv, sc, ray, dummy, 0.0f);
+        while (st == TRAV_STEP) st = trav_step<true, false, true, false>(tv, sc, ray, dummy, 0.0f, false);
         if (st == TRAV_DONE || occ) break;
         while (tv.tref != tv.tend) {
           const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
@@ -1693,7 +1237,7 @@ __global__ void __launch_bounds__(256) k_query(const DScene sc, const float *__r
       closest_begin(cl);
       for (;;) {
         int st = TRAV_STEP;
-        while (st == TRAV_STEP) st = trav_step<false, false, true, false>(tv, sc, ray, dummy, 0.0f);
+        while (st == TRAV_STEP) st = trav_step<false, false, true, false>(tv, sc, ray, dummy, 0.0f, false);
         if (st == TRAV_DONE) break;
         while (tv.tref != tv.tend) {
           const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);

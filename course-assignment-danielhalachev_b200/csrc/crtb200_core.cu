@@ -7,7 +7,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -85,13 +87,12 @@ struct crtb200_ctx {
   size_t l2_persist_max = 0, l2_window_max = 0;
   int l2_persist = 0;  // CRT_L2_PERSIST: 0 off (default, measured best), 1 arena persisting / rest of it streaming, 2 arena persisting / normal, 3 nodes only
   size_t nodes_bytes = 0;
-  DevBuf<float4> wnodes, vtx_normal;
-  uint32_t long_budget = 0;  // CRT_LONG_BUDGET=n: shadow walks longer than n node-phase iterations go to k_shadow_long (0 = off)
-  bool nested_ok = false;    // every child box of the uploaded mesh trees lies inside its parent's (crt_device.cuh "wide walk")
-  bool use_steal = false;    // CRT_STEAL=1: range-stealing kernels k_*_s (exact, parity green, but measured slower: profiles/r1_tuning.md)
-  bool wide_ok = false;      // the 4-wide layout is usable (trees nest and are shallow enough)
-  bool use_wide = false;     // CRT_LAYOUT=wide: walk the 4-wide layout (MODE 3 kernels).  Measured equal to slightly slower
-                             // than the binary walk on every workload (profiles/r1_tuning.md), so it is opt-in
+  DevBuf<float4> vtx_normal;
+  bool nested_ok = false;    // every child box of the uploaded mesh trees lies inside its parent's and no tree is deeper
+                             // than the k_coop LIFO allows: the order-free walk of k_coop and the subtree culling are exact
+  uint32_t tail_lanes = 16;  // tail hand-off (crt_kernels.cuh): hand a warp's walks to k_coop once the queue is dry and at
+  uint32_t tail_grace = 4;   //   most tail_lanes lanes are still walking, or after tail_grace more rounds.  CRT_TAIL_LANES /
+                             //   CRT_TAIL_GRACE override (tools); CRT_TAIL_GRACE=0 switches the hand-off off
   DevBuf<uint32_t> top_refs;
   DevBuf<uint4> tri_shade;
   DevBuf<float2> vtx_uv;
@@ -117,17 +118,17 @@ struct crtb200_ctx {
   struct QueueSet {
     Levels lv{};
     DevBuf<float4> ray_o, ray_d, color, dq;
-    DevBuf<uint32_t> hit_tri, counts, work;
+    DevBuf<uint32_t> hit_tri, ctl;  // ctl = counts | work cursors | hand-off counters, zeroed by one memset per chunk
     DevBuf<float> hit_t;
     DevBuf<uint4> comb;
     DevBuf<uint8_t> vis;
-    DevBuf<uint4> ovf;          // suspended long shadow walks (k_shadow_long)
-    DevBuf<uint32_t> ovf_ctl;
+    DevBuf<uint4> ovf;          // walks handed off to k_coop (3 x uint4 per record)
+    uint32_t *work = nullptr;   // into ctl
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     void release() {
-      ray_o.release(); ray_d.release(); color.release(); dq.release(); hit_tri.release(); counts.release();
-      work.release(); hit_t.release(); comb.release(); vis.release(); ovf.release(); ovf_ctl.release();
+      ray_o.release(); ray_d.release(); color.release(); dq.release(); hit_tri.release(); ctl.release();
+      hit_t.release(); comb.release(); vis.release(); ovf.release();
     }
   };
   std::vector<QueueSet> sets;
@@ -138,7 +139,7 @@ struct crtb200_ctx {
   uint32_t cap_depth = 0xFFFFFFFFu;
   uint32_t cap_sets = 0;
 
-  int blocks_closest = 0, blocks_shadow = 0, blocks_closest_w = 0, blocks_shadow_w = 0, blocks_closest_s = 0, blocks_shadow_s = 0;
+  int blocks_closest = 0, blocks_shadow = 0, blocks_coop = 0;
   crtb200_stats last{};
   bool last_pending = false;
 };
@@ -184,23 +185,15 @@ int crtb200_create(int device, crtb200_ctx **out) {
   c->blocks_closest = std::max(1, occ) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest_w<true, CRT_REFILL, false>, CRT_TRAV_BLOCK, 0);
-  c->blocks_closest_w = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_w<CRT_REFILL, false>, CRT_TRAV_BLOCK, 0);
-  c->blocks_shadow_w = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest_s<true, CRT_REFILL, false>, CRT_TRAV_BLOCK, 0);
-  c->blocks_closest_s = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_s<CRT_REFILL, false>, CRT_TRAV_BLOCK, 0);
-  c->blocks_shadow_s = std::max(1, occ) * c->sm_count;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_coop<true, false, true>, 32 * CRT_COOP_WARPS, 0);
+  c->blocks_coop = std::max(1, occ) * c->sm_count;
   if (const char *env = getenv("CRT_BLOCKS_PER_SM")) {  // tuning only (tools/): resident persistent CTAs per SM
     const int b = atoi(env);
-    if (b > 0)
-      c->blocks_closest = c->blocks_shadow = c->blocks_closest_w = c->blocks_shadow_w = c->blocks_closest_s = c->blocks_shadow_s = b * c->sm_count;
+    if (b > 0) c->blocks_closest = c->blocks_shadow = b * c->sm_count;
   }
-  if (const char *env = getenv("CRT_LAYOUT")) c->use_wide = std::string(env) == "wide";
   if (const char *env = getenv("CRT_L2_PERSIST")) c->l2_persist = atoi(env);
-  if (const char *env = getenv("CRT_STEAL")) c->use_steal = atoi(env) != 0;
-  if (const char *env = getenv("CRT_LONG_BUDGET")) c->long_budget = (uint32_t)std::max(0, atoi(env));
+  if (const char *env = getenv("CRT_TAIL_LANES")) c->tail_lanes = (uint32_t)std::max(0, std::min(32, atoi(env)));
+  if (const char *env = getenv("CRT_TAIL_GRACE")) c->tail_grace = (uint32_t)std::max(0, atoi(env));
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
   c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
   if (c->l2_persist && c->l2_persist_max)
@@ -216,7 +209,7 @@ int crtb200_destroy(crtb200_ctx *c) {
   if (!c) return CRTB200_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->arena.release(); c->wnodes.release(); c->vtx_normal.release(); c->top_refs.release();
+  c->arena.release(); c->vtx_normal.release(); c->top_refs.release();
   c->tri_shade.release(); c->vtx_uv.release(); c->meshes.release(); c->materials.release(); c->textures.release();
   c->texels.release(); c->lights.release(); c->frame.release(); c->frame8.release(); c->hits.release();
   c->mask.release();
@@ -256,7 +249,8 @@ int crtb200_set_queue_budget(crtb200_ctx *c, uint64_t bytes) {
 // node whose box passes, and never reorders.  So the visiting order is a fixed total order of the nodes and a failed
 // slab test simply jumps over the node's subtree.
 static bool relayout_tree(const crtb200_kdnode *nodes, uint32_t n, uint32_t out_base, uint32_t ref_base,
-                          uint32_t ref_count, std::vector<float4> &out, std::string &err) {
+                          uint32_t ref_count, std::vector<float4> &out, std::string &err, uint32_t *max_depth = nullptr) {
+  if (max_depth) *max_depth = 0;
   if (n == 0) return true;
   std::vector<uint32_t> order;
   order.reserve(n);
@@ -286,6 +280,16 @@ static bool relayout_tree(const crtb200_kdnode *nodes, uint32_t n, uint32_t out_
     }
   }
   const uint32_t m = (uint32_t)order.size();
+  if (max_depth) {  // order is a pre-order: a parent precedes its children
+    std::vector<uint32_t> depth(n, 1);
+    for (uint32_t k = 0; k < m; k++) {
+      const crtb200_kdnode &nd = nodes[order[k]];
+      *max_depth = std::max(*max_depth, depth[order[k]]);
+      if (nd.leaf_count == 0)
+        for (int side = 0; side < 2; side++)
+          if (nd.child[side] != CRTB200_INVALID) depth[nd.child[side]] = depth[order[k]] + 1;
+    }
+  }
   std::vector<uint32_t> newidx(n, 0), size(n, 1);
   for (uint32_t k = 0; k < m; k++) newidx[order[k]] = k;
   for (uint32_t k = m; k-- > 0;) {
@@ -306,7 +310,8 @@ static bool relayout_tree(const crtb200_kdnode *nodes, uint32_t n, uint32_t out_
       b = ref_base + nd.leaf_start;
     } else {
       a = out_base + k + size[order[k]];
-      b = CRT_INVALID;
+      // b = the child visited second (child[0] when both exist): k_coop pushes both children of a passing node at once
+      b = (nd.child[0] != CRTB200_INVALID && nd.child[1] != CRTB200_INVALID) ? out_base + newidx[nd.child[0]] : CRT_INVALID;
     }
     float4 lo = make_float4(nd.box_min[0], nd.box_min[1], nd.box_min[2], 0.f);
     float4 hi = make_float4(nd.box_max[0], nd.box_max[1], nd.box_max[2], 0.f);
@@ -318,95 +323,73 @@ static bool relayout_tree(const crtb200_kdnode *nodes, uint32_t n, uint32_t out_
   return true;
 }
 
-// ---- host flattener H1b: reference tree -> 4-wide nodes (crt_device.cuh "wide walk") ---------------------------
-// Entry order inside a wide node = the reference's visiting order: child[1] (or its children) before child[0] (or its
-// children).  `ok` goes false when a child box is not contained plane-by-plane in its parent's (then the walk would
-// not be equivalent to the reference's) or when the collapsed tree is deeper than the device stack.
-struct WideBuild {
-  const crtb200_kdnode *nodes;
-  uint32_t ref_base;
-  std::vector<float4> *out;
-  bool ok;
-};
-static void wide_put(std::vector<float4> &out, uint32_t w, int k, const crtb200_kdnode &nd, uint32_t a, uint32_t b) {
-  float fa, fb;
-  std::memcpy(&fa, &a, 4);
-  std::memcpy(&fb, &b, 4);
-  out[8 * (size_t)w + 2 * k] = make_float4(nd.box_min[0], nd.box_min[1], nd.box_min[2], nd.box_max[0]);
-  out[8 * (size_t)w + 2 * k + 1] = make_float4(nd.box_max[1], nd.box_max[2], fa, fb);
-}
 static bool box_nested(const crtb200_kdnode &parent, const crtb200_kdnode &child) {
   for (int k = 0; k < 3; k++)
     if (!(child.box_min[k] >= parent.box_min[k]) || !(child.box_max[k] <= parent.box_max[k]) || !(child.box_min[k] <= child.box_max[k]))
       return false;
   return true;
 }
-static uint32_t wide_new(std::vector<float4> &out) {
-  const uint32_t w = (uint32_t)(out.size() / 8);
-  float inv;
-  const uint32_t bits = CRT_INVALID;
-  std::memcpy(&inv, &bits, 4);
-  out.resize(out.size() + 8, make_float4(0.f, 0.f, 0.f, 0.f));
-  for (int k = 0; k < 4; k++) out[8 * (size_t)w + 2 * k + 1].z = inv;  // absent
-  return w;
-}
-// wide node for the children of reference inner node i
-static uint32_t wide_build(WideBuild &wb, uint32_t i, uint32_t level) {
-  std::vector<float4> &out = *wb.out;
-  const uint32_t w = wide_new(out);
-  if (level >= CRT_WIDE_STACK) {
-    wb.ok = false;
-    return w;
-  }
-  uint32_t e[4];
-  int n = 0;
-  const crtb200_kdnode &p = wb.nodes[i];
-  for (int side = 1; side >= 0; side--) {
-    const uint32_t ch = p.child[side];
-    if (ch == CRTB200_INVALID) continue;
-    const crtb200_kdnode &cn = wb.nodes[ch];
-    if (!box_nested(p, cn)) wb.ok = false;
-    if (cn.leaf_count) {
-      e[n++] = ch;
-    } else {
-      for (int s2 = 1; s2 >= 0; s2--) {
-        const uint32_t g = cn.child[s2];
-        if (g == CRTB200_INVALID) continue;
-        if (!box_nested(cn, wb.nodes[g])) wb.ok = false;
-        e[n++] = g;
+
+// ---- culling margin of one mesh (crt_device.cuh "Conservative culling") -----------------------
+// mu = overhang + 4 * slop + 64 ulp * |coordinates|, in double:
+//   overhang  how far the bounding box of a triangle sticks out of a leaf that lists it (max over all leaf references):
+//             then bbox(T) lies inside L inflated by overhang for EVERY leaf L through which the reference can meet T
+//   slop      how far outside T a point can lie and still pass Triangle::pointIsInTriangle's -FLT_EPSILON tests
+//             (Triangle.cpp:37-57): eps * (1 + 8 e^2) * perimeter / (2 * area), e = longest edge (rounding of the edge
+//             functions included); x4 for safety
+//   the ulp term covers the rounding of the hit point and of the slab parameters for this mesh's extent (the ray
+//   origin's share is added per ray, cull_margin_for)
+// +inf (never cull) when the tree does not nest or a triangle's uploaded normal is not its geometric unit normal (then
+// the slop bound does not describe what the triangle test accepts).  Zero-area triangles with a zero / non-finite
+// normal are harmless: they never yield a finite t (Ray.cpp:11-18).
+static float mesh_cull_margin(const crtb200_scene *s, const crtb200_mesh &me, bool nested) {
+  const float inf = std::numeric_limits<float>::infinity();
+  if (!nested) return inf;
+  double overhang = 0.0, slop = 0.0, absmax = 0.0;
+  const crtb200_kdnode *nodes = s->mesh_nodes + me.first_node;
+  for (uint32_t k = 0; k < me.n_nodes; k++) {
+    const crtb200_kdnode &nd = nodes[k];
+    for (int i = 0; i < 3; i++) absmax = std::max(absmax, std::max(std::fabs((double)nd.box_min[i]), std::fabs((double)nd.box_max[i])));
+    for (uint32_t q = 0; q < nd.leaf_count; q++) {
+      const uint32_t *iv = s->triangle_vertex + 3 * (size_t)(me.first_triangle + s->mesh_leaf_refs[me.first_leaf_ref + nd.leaf_start + q]);
+      for (int i = 0; i < 3; i++) {
+        const double x0 = s->vertex_position[3 * (size_t)iv[0] + i], x1 = s->vertex_position[3 * (size_t)iv[1] + i],
+                     x2 = s->vertex_position[3 * (size_t)iv[2] + i];
+        const double lo = std::min(x0, std::min(x1, x2)), hi = std::max(x0, std::max(x1, x2));
+        overhang = std::max(overhang, std::max((double)nd.box_min[i] - lo, hi - (double)nd.box_max[i]));
       }
     }
   }
-  for (int k = 0; k < n && wb.ok; k++) {
-    const crtb200_kdnode &nd = wb.nodes[e[k]];
-    uint32_t a, b = 0;
-    if (nd.leaf_count) {
-      a = CRT_LEAF_FLAG | nd.leaf_count;
-      b = wb.ref_base + nd.leaf_start;
-    } else {
-      a = wide_build(wb, e[k], level + 1);
+  for (uint32_t t = 0; t < me.n_triangles; t++) {
+    const uint32_t *iv = s->triangle_vertex + 3 * (size_t)(me.first_triangle + t);
+    double p[3][3];
+    for (int v = 0; v < 3; v++)
+      for (int i = 0; i < 3; i++) {
+        p[v][i] = s->vertex_position[3 * (size_t)iv[v] + i];
+        absmax = std::max(absmax, std::fabs(p[v][i]));
+      }
+    double len[3];
+    for (int k = 0; k < 3; k++) {
+      const double *a = p[k], *b = p[(k + 1) % 3];
+      len[k] = std::sqrt((b[0] - a[0]) * (b[0] - a[0]) + (b[1] - a[1]) * (b[1] - a[1]) + (b[2] - a[2]) * (b[2] - a[2]));
     }
-    wide_put(out, w, k, nd, a, b);  // `out` may have grown: index, not reference
+    const double u[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]};
+    const double w[3] = {p[2][0] - p[0][0], p[2][1] - p[0][1], p[2][2] - p[0][2]};
+    const double cr[3] = {u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0]};
+    const double a2 = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+    const float *nn = s->triangle_normal + 3 * (size_t)(me.first_triangle + t);
+    if (!(a2 > 0.0) || !std::isfinite(a2)) {
+      for (int i = 0; i < 3; i++)
+        if (std::isfinite(nn[i]) && nn[i] != 0.0f) return inf;
+      continue;
+    }
+    for (int i = 0; i < 3; i++)
+      if (!(std::fabs((double)nn[i] - cr[i] / a2) <= 1e-3)) return inf;
+    const double emax = std::max(len[0], std::max(len[1], len[2]));
+    slop = std::max(slop, (double)CRT_FLT_EPSILON * (1.0 + 8.0 * emax * emax) * (len[0] + len[1] + len[2]) / a2);
   }
-  return w;
-}
-// returns the mesh's root wide node (one entry: the reference root), CRT_INVALID for an empty tree
-static uint32_t wide_build_mesh(WideBuild &wb, uint32_t n_nodes) {
-  if (n_nodes == 0) return CRT_INVALID;
-  std::vector<float4> &out = *wb.out;
-  const uint32_t w = wide_new(out);
-  const crtb200_kdnode &root = wb.nodes[0];
-  for (int k = 0; k < 3; k++)
-    if (!(root.box_min[k] <= root.box_max[k])) wb.ok = false;
-  uint32_t a, b = 0;
-  if (root.leaf_count) {
-    a = CRT_LEAF_FLAG | root.leaf_count;
-    b = wb.ref_base + root.leaf_start;
-  } else {
-    a = wide_build(wb, 0, 1);
-  }
-  wide_put(out, w, 0, wb.nodes[0], a, b);
-  return w;
+  const double mu = overhang + 4.0 * slop + 64.0 * (double)CRT_FLT_EPSILON * absmax;
+  return (std::isfinite(mu) && mu < 1e30) ? (float)(mu * (1.0 + 1e-6)) : inf;
 }
 
 int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
@@ -447,9 +430,8 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
     shade[t] = make_uint4(iv[0], iv[1], iv[2], tri_mesh[t]);
   }
   // trees: mesh trees first, top-level tree last, one node array
-  std::vector<float4> nodes, wnodes;
+  std::vector<float4> nodes;
   bool nested_ok = true;
-  bool wide_ok = c->use_wide;  // the 4-wide copy of the trees is only built when it will be walked
   std::vector<uint32_t> refs(s->n_mesh_leaf_refs);
   std::vector<DMesh> meshes(s->n_meshes);
   uint32_t node_cursor = 0;
@@ -462,14 +444,16 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
       refs[me.first_leaf_ref + k] = me.first_triangle + local;
     }
     const size_t before = nodes.size() / 2;
-    if (!relayout_tree(s->mesh_nodes + me.first_node, me.n_nodes, node_cursor, me.first_leaf_ref, me.n_leaf_refs, nodes, err))
+    uint32_t depth = 0;
+    if (!relayout_tree(s->mesh_nodes + me.first_node, me.n_nodes, node_cursor, me.first_leaf_ref, me.n_leaf_refs, nodes, err, &depth))
       return fail(CRTB200_ERR_SCENE, err);
+    if (depth > 64) nested_ok = false;  // k_coop's LIFO is sized for trees up to this deep (the reference's limit is far below)
     const uint32_t placed = (uint32_t)(nodes.size() / 2 - before);
     meshes[m].node_begin = node_cursor;
     meshes[m].node_end = node_cursor + placed;
     meshes[m].material = me.material;
     meshes[m].first_triangle = me.first_triangle;
-    meshes[m].wroot = CRT_INVALID;
+    meshes[m].cull_margin = std::numeric_limits<float>::infinity();
     node_cursor += placed;
     for (uint32_t k = 0; k < me.n_nodes && nested_ok; k++) {  // relayout_tree has validated the child indices
       const crtb200_kdnode &p = s->mesh_nodes[me.first_node + k];
@@ -478,11 +462,6 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
       if (p.leaf_count) continue;
       for (int side = 0; side < 2; side++)
         if (p.child[side] != CRTB200_INVALID && !box_nested(p, s->mesh_nodes[me.first_node + p.child[side]])) nested_ok = false;
-    }
-    if (wide_ok) {  // relayout_tree has validated the tree's shape
-      WideBuild wb{s->mesh_nodes + me.first_node, me.first_leaf_ref, &wnodes, true};
-      meshes[m].wroot = wide_build_mesh(wb, me.n_nodes);
-      wide_ok = wb.ok && wnodes.size() / 8 < (1u << 28);
     }
   }
   for (uint32_t k = 0; k < s->n_top_leaf_refs; k++)
@@ -494,6 +473,9 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
     node_cursor += (uint32_t)(nodes.size() / 2 - before);
   }
   const uint32_t top_end = node_cursor;
+  // culling margins (one pass over the leaf references and the triangles of each mesh; meshes in parallel would be easy,
+  // but this is 0.1 s per million triangles)
+  for (uint32_t m = 0; m < s->n_meshes; m++) meshes[m].cull_margin = mesh_cull_margin(s, s->meshes[m], nested_ok);
 
   std::vector<float4> vn(s->n_vertices);
   for (uint32_t v = 0; v < s->n_vertices; v++)
@@ -559,9 +541,6 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
     if (!refs.empty()) CUDA_TRY(cudaMemcpy(c->leaf_refs_p, refs.data(), refs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (!geom.empty()) CUDA_TRY(cudaMemcpy(c->tri_geom_p, geom.data(), geom.size() * sizeof(float4), cudaMemcpyHostToDevice));
   }
-  if (!wide_ok) wnodes.clear();
-  CUDA_TRY(c->wnodes.upload(wnodes));
-  c->wide_ok = wide_ok;
   c->nested_ok = nested_ok;
   CUDA_TRY(c->top_refs.upload(top_refs));
   CUDA_TRY(c->tri_shade.upload(shade));
@@ -572,11 +551,10 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   CUDA_TRY(c->textures.upload(texs));
   CUDA_TRY(c->texels.upload(texels));
   CUDA_TRY(c->lights.upload(lights));
-  c->scene_bytes = nodes.size() * 16 + wnodes.size() * 16 + refs.size() * 4 + geom.size() * 16 + shade.size() * 16 + vn.size() * 16;
+  c->scene_bytes = nodes.size() * 16 + refs.size() * 4 + geom.size() * 16 + shade.size() * 16 + vn.size() * 16;
 
   DScene &d = c->sc;
   d.nodes = c->nodes_p;
-  d.wnodes = c->wnodes.p;
   d.leaf_refs = c->leaf_refs_p;
   d.top_refs = c->top_refs.p;
   d.tri_geom = c->tri_geom_p;
@@ -589,6 +567,7 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   d.texels = c->texels.p;
   d.lights = c->lights.p;
   d.n_lights = s->n_lights;
+  d.n_meshes = s->n_meshes;
   d.top_begin = top_begin;
   d.top_end = top_end;
   d.width = s->width;
@@ -650,7 +629,8 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
   branching_sum(c, max_depth, per_level);
   uint64_t sum = 0;
   for (uint32_t l = 0; l <= max_depth; l++) sum += per_level[l];
-  const uint64_t bytes_per_node = 32 + 8 + 16 + 16 + 48;  // ray + hit + colour + comb + diffuse item
+  const uint32_t n_lights = std::max<uint32_t>(1, c->sc.n_lights);
+  const uint64_t bytes_per_node = 32 + 8 + 16 + 16 + 48 + n_lights;  // ray + hit + colour + comb + diffuse item + visibility bytes
   // sets used: up to `concurrency`, but never chunks smaller than 64 Ki items (launch overhead would dominate)
   uint32_t n_sets = std::max<uint32_t>(1, std::min<uint32_t>(c->concurrency, (shard_items + 65535u) / 65536u));
   // host-bound frames: two chunks per set of at least ~256 Ki items each (tools/e2e_time.py: the 4K frame is best with 6
@@ -673,7 +653,9 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
   uint64_t even = ((uint64_t)shard_items + parts - 1) / parts;
   even = ((even + row_items - 1) / row_items) * row_items;
   items = std::min<uint64_t>(items, even);
-  if (items * sum >= 0x7FFFFFFFull) items = ((0x7FFFFFFFull / sum) - 32) & ~31ull;
+  // node ids and (diffuse item, light) slots are 32-bit on the device
+  if (items * sum * n_lights >= 0x7FFFFFFFull) items = ((0x7FFFFFFFull / (sum * n_lights)) - 32) & ~31ull;
+  if (items < 32) return fail(CRTB200_ERR_MEMORY, "too many lights x ray-tree nodes for 32-bit queue slots");
   if (items >= row_items) items = (items / row_items) * row_items;  // whole tile rows (band copies need it)
   if (c->cap_items == items && c->cap_depth == max_depth && c->cap_sets == n_sets) return CRTB200_OK;
   if (c->sets.size() < n_sets) c->sets.resize(n_sets);
@@ -698,15 +680,17 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     CUDA_TRY(q.comb.ensure(total));
     CUDA_TRY(q.dq.ensure(3 * total));
     CUDA_TRY(q.vis.ensure(std::max<uint64_t>(1, total * std::max<uint32_t>(1, c->sc.n_lights))));
-    const uint64_t ovf_cap = std::min<uint64_t>(8ull << 20, std::max<uint64_t>(1024, total * std::max<uint32_t>(1, c->sc.n_lights) / 4));
-    CUDA_TRY(q.ovf.ensure(2 * ovf_cap));
-    CUDA_TRY(q.ovf_ctl.ensure(2));
+    // hand-off records: every lane of a traversal grid hands off at most once per launch
+    const uint64_t ovf_cap = (uint64_t)std::max(c->blocks_closest, c->blocks_shadow) * CRT_TRAV_BLOCK;
+    CUDA_TRY(q.ovf.ensure(3 * ovf_cap));
+    const size_t n_counts = CRT_MAX_LEVELS + 1, n_work = CRT_MAX_LEVELS + 2, n_ovf = 2 * (CRT_MAX_LEVELS + 1);
+    CUDA_TRY(q.ctl.ensure(n_counts + n_work + n_ovf));
+    q.work = q.ctl.p + n_counts;
     q.lv.ovf = q.ovf.p;
-    q.lv.ovf_ctl = q.ovf_ctl.p;
+    q.lv.ovf_ctl = q.ctl.p + n_counts + n_work;
     q.lv.ovf_cap = (uint32_t)ovf_cap;
-    q.lv.long_budget = 0;
-    CUDA_TRY(q.counts.ensure(CRT_MAX_LEVELS + 1));
-    CUDA_TRY(q.work.ensure(CRT_MAX_LEVELS + 2));
+    q.lv.tail_lanes = 0;
+    q.lv.tail_grace = 0;
     q.lv.ray_o = q.ray_o.p;
     q.lv.ray_d = q.ray_d.p;
     q.lv.hit_tri = q.hit_tri.p;
@@ -715,7 +699,7 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     q.lv.comb = q.comb.p;
     q.lv.dq = q.dq.p;
     q.lv.vis = q.vis.p;
-    q.lv.counts = q.counts.p;
+    q.lv.counts = q.ctl.p;
     q.lv.stats = c->stats_dev.p;
   }
   c->cap_items = (uint32_t)items;
@@ -771,21 +755,11 @@ static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const 
 }
 
 template <bool CULL>
-static void launch_closest_s(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, uint32_t *work,
-                             cudaStream_t st) {
+static void launch_coop_closest(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, cudaStream_t st) {
   if (primary)
-    k_closest_s<true, CRT_REFILL, CULL><<<c->blocks_closest_s, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
+    k_coop<false, true, CULL><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
   else
-    k_closest_s<false, CRT_REFILL, CULL><<<c->blocks_closest_s, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
-}
-
-template <bool CULL>
-static void launch_closest_w(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, uint32_t *work,
-                             cudaStream_t st) {
-  if (primary)
-    k_closest_w<true, CRT_REFILL, CULL><<<c->blocks_closest_w, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
-  else
-    k_closest_w<false, CRT_REFILL, CULL><<<c->blocks_closest_w, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
+    k_coop<false, false, CULL><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
 }
 
 // Host destinations of crtb200_render: each chunk's band of rows is copied back on the chunk's own stream right after
@@ -799,19 +773,16 @@ struct HostOut {
 // Enqueue one frame on `st`.  d_rgb / d_rgb8 / d_hits / d_slab are device pointers (any may be null).
 static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_options *o, float *d_rgb,
                          uint8_t *d_rgb8, HitRec *d_hits, float *d_slab, cudaStream_t st, bool timed,
-                         const HostOut *host = nullptr) {
+                         const HostOut *host = nullptr, bool *host_done = nullptr) {
   if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
   if (o->max_depth > 31) return fail(CRTB200_ERR_ARG, "max_depth > 31 is not supported");
   if (o->n_rects && !o->rects) return fail(CRTB200_ERR_ARG, "n_rects > 0 but rects is null");
   if (o->traversal > 1) return fail(CRTB200_ERR_ARG, "unknown traversal mode");
   if (o->count_work > 2) return fail(CRTB200_ERR_ARG, "unknown count_work mode");
-  if (o->traversal == 1 && o->count_work == 1)
-    return fail(CRTB200_ERR_ARG, "count_work = 1 counts the reference's visit-all work and needs traversal = 0");
-  const bool cull = o->traversal == 1;
-  // opt-in 4-wide walk (CRT_LAYOUT=wide); the counting modes always measure the reference's binary visit-all walk
-  const bool wide = c->use_wide && c->wide_ok && o->count_work == 0;
-  // range stealing needs the nesting property too; the counting modes keep the plain kernels (they count the reference's walk)
-  const bool steal = !wide && c->use_steal && c->nested_ok && o->count_work == 0;
+  // traversal 0 (default): conservative culling + tail hand-off, both exact and both resting on the nesting property of
+  // the uploaded trees; traversal 1 and the visit-all counting mode walk the reference's literal itinerary
+  const bool cull = o->traversal == 0 && o->count_work != 1 && c->nested_ok;
+  const bool handoff = o->traversal == 0 && o->count_work == 0 && c->nested_ok && c->tail_grace > 0;
   const uint32_t shard_count = o->shard_count ? o->shard_count : 1;
   if (o->shard_index >= shard_count) return fail(CRTB200_ERR_ARG, "shard_index >= shard_count");
   int rc = plan_mask(c, o);
@@ -838,6 +809,11 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   if (rc) return rc;
   const bool secondary = c->has_reflective || c->has_refractive;
   const uint32_t levels = secondary ? o->max_depth + 1 : 1;
+  // Band copies need chunks that own whole rows of tiles: with a small queue budget or a deep refractive scene a chunk
+  // is smaller than a tile row, two chunks on different streams would then share a 4-row band and a band copy could
+  // pick up the other chunk's stale pixels.  Then the caller copies the whole frame after the join instead.
+  const bool band_copies = host && shard_count == 1 && c->cap_items % row_items == 0;
+  if (host_done) *host_done = band_copies;
   const int grid_simple = c->sm_count * 8;
 
   CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 32 * sizeof(unsigned long long), st));
@@ -860,29 +836,29 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     cudaStream_t qs = q.stream;
     fr.item_begin = begin;
     fr.n_items0 = std::min(c->cap_items, shard_items - begin);
-    CUDA_TRY(cudaMemsetAsync(q.counts.p, 0, (CRT_MAX_LEVELS + 1) * sizeof(uint32_t), qs));
-    CUDA_TRY(cudaMemsetAsync(q.work.p, 0, (CRT_MAX_LEVELS + 2) * sizeof(uint32_t), qs));
+    CUDA_TRY(cudaMemsetAsync(q.ctl.p, 0, q.ctl.n * sizeof(uint32_t), qs));
+    q.lv.tail_lanes = handoff ? c->tail_lanes : 0u;
+    q.lv.tail_grace = handoff ? c->tail_grace : 0u;
     for (uint32_t l = 0; l < levels; l++) {
       if (per_kernel) {
         cudaEventRecord(next_event(c), qs);
         c->kev_kind.push_back(0);
       }
-      if (steal && cull)
-        launch_closest_s<true>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
-      else if (steal)
-        launch_closest_s<false>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
-      else if (wide && cull)
-        launch_closest_w<true>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
-      else if (wide)
-        launch_closest_w<false>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
-      else if (o->count_work && cull)
-        launch_closest<true, true>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
+      if (o->count_work && cull)
+        launch_closest<true, true>(c, l == 0, fr, q.lv, l, q.work + l, qs);
       else if (o->count_work)
-        launch_closest<true, false>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
+        launch_closest<true, false>(c, l == 0, fr, q.lv, l, q.work + l, qs);
       else if (cull)
-        launch_closest<false, true>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
+        launch_closest<false, true>(c, l == 0, fr, q.lv, l, q.work + l, qs);
       else
-        launch_closest<false, false>(c, l == 0, fr, q.lv, l, q.work.p + l, qs);
+        launch_closest<false, false>(c, l == 0, fr, q.lv, l, q.work + l, qs);
+      if (handoff) {
+        if (cull)
+          launch_coop_closest<true>(c, l == 0, fr, q.lv, l, qs);
+        else
+          launch_coop_closest<false>(c, l == 0, fr, q.lv, l, qs);
+        launches++;
+      }
       if (per_kernel) cudaEventRecord(next_event(c), qs);
       k_shade<<<grid_simple, 256, 0, qs>>>(c->sc, fr, q.lv, l);
       launches += 2;
@@ -891,20 +867,8 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       cudaEventRecord(next_event(c), qs);
       c->kev_kind.push_back(1);
     }
-    uint32_t *swork = q.work.p + CRT_MAX_LEVELS;
-    // long shadow walks: suspended by k_shadow, finished one warp per ray by k_shadow_long (needs the nesting property)
-    const bool use_long = c->long_budget > 0 && c->nested_ok && o->count_work == 0 && !wide && !steal;
-    q.lv.long_budget = use_long ? c->long_budget : 0u;
-    if (use_long) CUDA_TRY(cudaMemsetAsync(q.ovf_ctl.p, 0, 2 * sizeof(uint32_t), qs));
-    if (steal && cull)
-      k_shadow_s<CRT_REFILL, true><<<c->blocks_shadow_s, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
-    else if (steal)
-      k_shadow_s<CRT_REFILL, false><<<c->blocks_shadow_s, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
-    else if (wide && cull)
-      k_shadow_w<CRT_REFILL, true><<<c->blocks_shadow_w, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
-    else if (wide)
-      k_shadow_w<CRT_REFILL, false><<<c->blocks_shadow_w, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
-    else if (o->count_work == 1)
+    uint32_t *swork = q.work + CRT_MAX_LEVELS;
+    if (o->count_work == 1)
       k_shadow<1, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else if (o->count_work == 2 && cull)
       k_shadow<2, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
@@ -914,11 +878,11 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     else
       k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
-    if (use_long) {
+    if (handoff) {
       if (cull)
-        k_shadow_long<true><<<c->sm_count * 12, 32 * CRT_LONG_WARPS, 0, qs>>>(c->sc, fr, q.lv);
+        k_coop<true, false, true><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, qs>>>(c->sc, fr, q.lv, 0);
       else
-        k_shadow_long<false><<<c->sm_count * 12, 32 * CRT_LONG_WARPS, 0, qs>>>(c->sc, fr, q.lv);
+        k_coop<true, false, false><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, qs>>>(c->sc, fr, q.lv, 0);
       launches++;
     }
     if (per_kernel) cudaEventRecord(next_event(c), qs);
@@ -930,7 +894,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     }
     k_store<<<grid_simple, 256, 0, qs>>>(c->sc, fr, q.lv, d_rgb, d_rgb8, d_hits, d_slab);
     launches++;
-    if (host && shard_count == 1) {
+    if (band_copies) {
       const uint32_t row0 = (begin / row_items) * 4u;
       const uint32_t row1 = std::min<uint32_t>(H, ((begin + fr.n_items0 + row_items - 1) / row_items) * 4u);
       const size_t off = (size_t)row0 * W, cnt = (size_t)(row1 - row0) * W;
@@ -1040,9 +1004,10 @@ int crtb200_render(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_opti
   host.hits = hits_out;
   int rc = plan_mask(c, o);
   if (rc) return rc;
-  const bool banded = !shard && !c->mask_needed && (rgb_out || rgb8_out || hits_out);
+  const bool want_bands = !shard && !c->mask_needed && (rgb_out || rgb8_out || hits_out);
+  bool banded = false;
   rc = enqueue_frame(c, cam, o, c->frame.p, rgb8_out ? c->frame8.p : nullptr, hits_out ? c->hits.p : nullptr, nullptr,
-                     c->stream, true, banded ? &host : nullptr);
+                     c->stream, true, want_bands ? &host : nullptr, &banded);
   if (rc) return rc;
   if (!banded) {
     if (rgb_out) CUDA_TRY(cudaMemcpyAsync(rgb_out, c->frame.p, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1183,7 +1148,7 @@ int crtb200_trace_rays(crtb200_ctx *c, const float *rays, uint32_t n, uint32_t r
   if (!c || !rays) return fail(CRTB200_ERR_ARG, "null argument");
   if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
   if (ray_type > 3) return fail(CRTB200_ERR_ARG, "bad ray type");
-  if (traversal != 0) return fail(CRTB200_ERR_ARG, "traversal mode 1 (ordered + culled) is not available in this build");
+  if (traversal > 1) return fail(CRTB200_ERR_ARG, "unknown traversal mode");  // caller-supplied rays always take the literal walk
   if (ray_type == CRTB200_RAY_SHADOW ? (!max_distance || !occluded_out) : !hits_out) return fail(CRTB200_ERR_ARG, "missing output / distance array");
   if (n == 0) return CRTB200_OK;
   CUDA_TRY(cudaSetDevice(c->device));

@@ -51,6 +51,9 @@ def lib() -> C.CDLL:
         l.crt_oracle_quantize.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         l.crt_oracle_generate_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         l.crt_oracle_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.crt_oracle_skip_margins.argtypes = [C.c_void_p, C.c_void_p]
+        l.crt_oracle_render_skip_model.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.POINTER(OracleStats), C.c_int]
         _lib = l
     return _lib
 
@@ -69,6 +72,31 @@ def render(scene_ptr, camera, options, threads: int = 0, want_hits: bool = True,
                                  hits.ctypes.data if hits is not None else None, C.byref(st), threads)
     if rc != 0:
         raise RuntimeError("crt_oracle_render failed")
+    return rgb, hits, st.as_dict()
+
+
+def skip_margins(scene_ptr) -> np.ndarray:
+    """Per-mesh margins of the skip-rule model (crt_oracle_skip_margins); +inf = the mesh is never culled."""
+    mu = np.zeros(max(1, scene_ptr.contents.n_meshes), np.float32)
+    if lib().crt_oracle_skip_margins(C.cast(scene_ptr, C.c_void_p), mu.ctypes.data) != 0:
+        raise RuntimeError("crt_oracle_skip_margins failed")
+    return mu[:scene_ptr.contents.n_meshes]
+
+
+def render_skip_model(scene_ptr, camera, options, mu: np.ndarray, threads: int = 0, want_hits: bool = True):
+    """The restated reference walk with the product's conservative culling applied (CPU model, see crt_oracle.c)."""
+    s = scene_ptr.contents
+    h, w = s.height, s.width
+    rgb = np.zeros((h, w, 3), np.float32)
+    hits = np.zeros((h, w), HIT_DTYPE) if want_hits else None
+    st = OracleStats()
+    mu = np.ascontiguousarray(mu, dtype=np.float32)
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    rc = lib().crt_oracle_render_skip_model(C.cast(scene_ptr, C.c_void_p), C.byref(camera), C.byref(options), mu.ctypes.data,
+                                            rgb.ctypes.data, hits.ctypes.data if hits is not None else None, C.byref(st), threads)
+    if rc != 0:
+        raise RuntimeError("crt_oracle_render_skip_model failed")
     return rgb, hits, st.as_dict()
 
 

@@ -59,7 +59,12 @@ typedef struct {
   uint64_t node_tests[2], tri_tests[2]; /* [0] closest-hit queries, [1] shadow queries */
   int shadow_query;
   uint64_t max_query_tests; /* most AABB + triangle tests spent on a single query (latency tail) */
+  /* skip-rule model (crt_oracle_render_skip_model, see the end of this file); all zero for the reference walk */
+  const float *skip_mu;   /* per-mesh margin, NULL = the reference's visit-all walk */
+  float shadow_limit;     /* distance limit of the current shadow query */
 } octx;
+
+static int skip_node(const octx *c, const crtb200_kdnode *n, const ray_t *r, float mu, float limit, int allow_behind);
 
 /* ---- BoundingBox::hasIntersection  include/tracer/BoundingBox.h:85-108 ---- */
 static int box_hit(const crtb200_kdnode *n, const ray_t *r) {
@@ -122,7 +127,7 @@ typedef struct {
 #define STACK_MAX 4096
 
 /* ---- KDTree<Triangle>::intersect  src/KDTree.cpp:48-87 ---- */
-static hitinfo mesh_intersect(octx *c, uint32_t mesh_index, const ray_t *r) {
+static hitinfo mesh_intersect(octx *c, uint32_t mesh_index, const ray_t *r, float outer_min_t) {
   const crtb200_scene *s = c->s;
   const crtb200_mesh *m = &s->meshes[mesh_index];
   const crtb200_kdnode *nodes = s->mesh_nodes + m->first_node;
@@ -138,6 +143,10 @@ static hitinfo mesh_intersect(octx *c, uint32_t mesh_index, const ray_t *r) {
     const crtb200_kdnode *n = &nodes[stack[--sp]];
     c->node_tests[c->shadow_query]++;
     if (!box_hit(n, r)) continue;
+    if (c->skip_mu) { /* model of the product's conservative skip; never taken by the reference walk */
+      const float lim = c->shadow_query ? c->shadow_limit : (min_t < outer_min_t ? min_t : outer_min_t);
+      if (skip_node(c, n, r, c->skip_mu[mesh_index], lim, c->shadow_query || lim < INFINITY)) continue;
+    }
     if (n->leaf_count) {
       for (uint32_t k = 0; k < n->leaf_count; k++) {
         uint32_t tri = m->first_triangle + refs[n->leaf_start + k];
@@ -195,7 +204,7 @@ static hitinfo scene_intersect(octx *c, const ray_t *r) {
     if (n->leaf_count) {
       for (uint32_t k = 0; k < n->leaf_count; k++) {
         uint32_t mi = s->top_leaf_refs[n->leaf_start + k];
-        hitinfo h = mesh_intersect(c, mi, r);
+        hitinfo h = mesh_intersect(c, mi, r, min_t);
         if (h.has) {
           if (!best.has) best = h;
           if (h.t < min_t) { min_t = h.t; best = h; }
@@ -238,6 +247,7 @@ static int scene_occluded(octx *c, const ray_t *r, float distance_to_light) {
   int sp = 0;
   c->rays[CRTB200_RAY_SHADOW]++;
   c->shadow_query = 1;
+  c->shadow_limit = distance_to_light * 1.0001f + 1e-4f + 1e-6f * (fabsf(r->o.x) + fabsf(r->o.y) + fabsf(r->o.z));
   if (s->n_top_nodes == 0) return 0;
   stack[sp++] = 0;
   while (sp > 0) {
@@ -249,7 +259,7 @@ static int scene_occluded(octx *c, const ray_t *r, float distance_to_light) {
         uint32_t mi = s->top_leaf_refs[n->leaf_start + k];
         if (r->type == CRTB200_RAY_SHADOW && s->materials[s->meshes[mi].material].type == CRTB200_MAT_REFRACTIVE)
           continue;
-        hitinfo h = mesh_intersect(c, mi, r);
+        hitinfo h = mesh_intersect(c, mi, r, INFINITY);
         if (h.has && vlen(vsub(h.p, r->o)) <= distance_to_light) found = 1; /* no early out in the reference */
       }
     } else {
@@ -400,8 +410,8 @@ static ray_t get_ray(const crtb200_scene *s, const crtb200_camera *cam, unsigned
   return r;
 }
 
-int crt_oracle_render(const crtb200_scene *s, const crtb200_camera *cam, const crtb200_options *opt, float *rgb,
-                      crtb200_hit *hits, crt_oracle_stats *stats, int threads) {
+static int render_impl(const crtb200_scene *s, const crtb200_camera *cam, const crtb200_options *opt, float *rgb,
+                       crtb200_hit *hits, crt_oracle_stats *stats, int threads, const float *skip_mu) {
   if (!s || !cam || !opt || !rgb) return -1;
   crtb200_rect full = {0, 0, s->width, s->height};
   const crtb200_rect *rects = opt->n_rects ? opt->rects : &full;
@@ -422,6 +432,7 @@ int crt_oracle_render(const crtb200_scene *s, const crtb200_camera *cam, const c
       c.shadow_bias = opt->shadow_bias;
       c.reflection_bias = opt->reflection_bias;
       c.refraction_bias = opt->refraction_bias;
+      c.skip_mu = skip_mu;
       for (uint32_t col = rc.col; col < col_limit; col++) {
         ray_t r = get_ray(s, cam, row, col);
         if (hits) {
@@ -462,6 +473,11 @@ int crt_oracle_render(const crtb200_scene *s, const crtb200_camera *cam, const c
     if (max_q > stats->max_query_tests) stats->max_query_tests = max_q;
   }
   return 0;
+}
+
+int crt_oracle_render(const crtb200_scene *s, const crtb200_camera *cam, const crtb200_options *opt, float *rgb,
+                      crtb200_hit *hits, crt_oracle_stats *stats, int threads) {
+  return render_impl(s, cam, opt, rgb, hits, stats, threads, NULL);
 }
 
 /* PPMColor  src/Color.cpp:12-16 */
@@ -514,4 +530,112 @@ int crt_oracle_trace_rays(const crtb200_scene *s, const float *rays, uint32_t n,
     }
   }
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Skip-rule model.  NOT part of the reference restatement: a CPU model of the conservative culling the product's
+ * traversal kernels apply by default (csrc/crt_device.cuh node_test), layered on the restated
+ * reference walk above so that tests can check on the CPU -- at any size, without GPU time -- that skipping the
+ * subtrees the product skips leaves every hit id, t and pixel of the reference walk unchanged.
+ *   mu[mesh]  margin in space units such that (i) every leaf L listing a triangle T has bbox(T) inside L inflated by
+ *             mu and (ii) every point the triangle test can accept for T is within mu of bbox(T); +inf = never skip.
+ *   skip      inside a mesh tree only, for rays with finite o, d, 1/d and no axis-parallel component:
+ *             behind: some far slab plane lies more than mu behind the origin        (shadow rays: always; closest
+ *                     hit: only once a finite candidate exists)
+ *             beyond: some near slab plane lies more than mu beyond the limit        (best finite t / the light)
+ * ------------------------------------------------------------------------------------------------------------------ */
+static int skip_node(const octx *c, const crtb200_kdnode *n, const ray_t *r, float mesh_mu, float limit, int allow_behind) {
+  (void)c;
+  const float o[3] = {r->o.x, r->o.y, r->o.z}, d[3] = {r->d.x, r->d.y, r->d.z};
+  float inv[3];
+  for (int i = 0; i < 3; i++) {
+    if (fabsf(d[i]) < FLT_EPSILON) return 0;
+    inv[i] = 1.0f / d[i];
+    if (!isfinite(o[i]) || !isfinite(d[i]) || !isfinite(inv[i])) return 0;
+  }
+  const float mu = mesh_mu + (64.0f * FLT_EPSILON) * (fabsf(o[0]) + fabsf(o[1]) + fabsf(o[2]));
+  for (int i = 0; i < 3; i++) {
+    const float a = (n->box_min[i] - o[i]) * inv[i], b = (n->box_max[i] - o[i]) * inv[i];
+    const float tn = fminf(a, b), tf = fmaxf(a, b);
+    const float m = mu * fabsf(inv[i]);
+    if (allow_behind && tf < -m) return 1;
+    if (tn - m > limit) return 1;
+  }
+  return 0;
+}
+
+int crt_oracle_skip_margins(const crtb200_scene *s, float *mu_out) {
+  if (!s || !mu_out) return -1;
+  for (uint32_t mi = 0; mi < s->n_meshes; mi++) {
+    const crtb200_mesh *m = &s->meshes[mi];
+    const crtb200_kdnode *nodes = s->mesh_nodes + m->first_node;
+    const uint32_t *refs = s->mesh_leaf_refs + m->first_leaf_ref;
+    double overhang = 0, slop = 0, absmax = 0;
+    int ok = 1;
+    for (uint32_t k = 0; k < m->n_nodes && ok; k++) {
+      const crtb200_kdnode *n = &nodes[k];
+      for (int i = 0; i < 3; i++) {
+        if (!(n->box_min[i] <= n->box_max[i])) ok = 0;
+        absmax = fmax(absmax, fmax(fabs(n->box_min[i]), fabs(n->box_max[i])));
+      }
+      if (n->leaf_count == 0) { /* children must lie inside the parent (the skip of a subtree relies on it) */
+        for (int side = 0; side < 2; side++) {
+          if (n->child[side] == CRTB200_INVALID) continue;
+          const crtb200_kdnode *ch = &nodes[n->child[side]];
+          for (int i = 0; i < 3; i++)
+            if (!(ch->box_min[i] >= n->box_min[i]) || !(ch->box_max[i] <= n->box_max[i])) ok = 0;
+        }
+        continue;
+      }
+      for (uint32_t q = 0; q < n->leaf_count; q++) {
+        const uint32_t *iv = s->triangle_vertex + 3 * (size_t)(m->first_triangle + refs[n->leaf_start + q]);
+        for (int i = 0; i < 3; i++) {
+          double lo = INFINITY, hi = -INFINITY;
+          for (int v = 0; v < 3; v++) {
+            const double x = s->vertex_position[3 * (size_t)iv[v] + i];
+            lo = fmin(lo, x);
+            hi = fmax(hi, x);
+          }
+          overhang = fmax(overhang, fmax(n->box_min[i] - lo, hi - n->box_max[i]));
+        }
+      }
+    }
+    for (uint32_t t = 0; t < m->n_triangles && ok; t++) {
+      const uint32_t *iv = s->triangle_vertex + 3 * (size_t)(m->first_triangle + t);
+      double p[3][3];
+      for (int v = 0; v < 3; v++)
+        for (int i = 0; i < 3; i++) {
+          p[v][i] = s->vertex_position[3 * (size_t)iv[v] + i];
+          absmax = fmax(absmax, fabs(p[v][i]));
+        }
+      double e[3][3], len[3];
+      for (int k = 0; k < 3; k++) {
+        for (int i = 0; i < 3; i++) e[k][i] = p[(k + 1) % 3][i] - p[k][i];
+        len[k] = sqrt(e[k][0] * e[k][0] + e[k][1] * e[k][1] + e[k][2] * e[k][2]);
+      }
+      const double u[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]};
+      const double w[3] = {p[2][0] - p[0][0], p[2][1] - p[0][1], p[2][2] - p[0][2]};
+      const double cr[3] = {u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0]};
+      const double a2 = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+      const float *nn = s->triangle_normal + 3 * (size_t)(m->first_triangle + t);
+      if (!(a2 > 0) || !isfinite(a2)) { /* no plane: only a zero / non-finite normal is harmless (t is never finite) */
+        for (int i = 0; i < 3; i++)
+          if (isfinite(nn[i]) && nn[i] != 0.0f) ok = 0;
+        continue;
+      }
+      for (int i = 0; i < 3; i++)
+        if (!(fabs(nn[i] - cr[i] / a2) <= 1e-3)) ok = 0;
+      const double emax = fmax(len[0], fmax(len[1], len[2]));
+      slop = fmax(slop, FLT_EPSILON * (1.0 + 8.0 * emax * emax) * (len[0] + len[1] + len[2]) / a2);
+    }
+    const double mu = overhang + 4.0 * slop + 64.0 * FLT_EPSILON * absmax;
+    mu_out[mi] = (ok && isfinite(mu) && mu < 1e30) ? (float)(mu * (1.0 + 1e-6)) : INFINITY;
+  }
+  return 0;
+}
+
+int crt_oracle_render_skip_model(const crtb200_scene *s, const crtb200_camera *cam, const crtb200_options *opt,
+                                 const float *mu, float *rgb, crtb200_hit *hits, crt_oracle_stats *stats, int threads) {
+  if (!mu) return -1;
+  return render_impl(s, cam, opt, rgb, hits, stats, threads, mu);
 }

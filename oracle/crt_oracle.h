@@ -26,6 +26,13 @@ int crt_oracle_generate_rays(const crtb200_scene *scene, const crtb200_camera *c
 int crt_oracle_trace_rays(const crtb200_scene *scene, const float *rays, uint32_t n, uint32_t ray_type,
                           const float *max_distance, crtb200_hit *hits_out, uint8_t *occluded_out);
 
+
+/* Skip-rule model (see the end of crt_oracle.c): the restated reference walk with the product's conservative culling
+ * applied, for checking on the CPU that the culling changes no result.  mu = per-mesh margins (crt_oracle_skip_margins). */
+int crt_oracle_skip_margins(const crtb200_scene *scene, float *mu_out);
+int crt_oracle_render_skip_model(const crtb200_scene *scene, const crtb200_camera *camera, const crtb200_options *options,
+                                 const float *mu, float *rgb, crtb200_hit *hits, crt_oracle_stats *stats, int threads);
+
 #ifdef __cplusplus
 }
 #endif

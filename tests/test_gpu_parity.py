@@ -154,20 +154,45 @@ def test_chunked_frame_identical(gpu, loaded, crt):
     assert sa["rays_total"] == sb["rays_total"]
 
 
-@pytest.mark.parametrize("name", [n for n in SMALL_SCENES if n != "degenerate_uv"])
-def test_culled_mode_matches_exact_on_test_scenes(name, gpu, loaded, crt):
-    """traversal = 1 (skip subtrees wholly behind the origin / beyond the best hit or the light) is NOT guaranteed to
-    see the reference's candidate set; on every clean test scene it must nevertheless reproduce the
-    exact mode bit for bit.  (The NaN-triangle scene is excluded: non-finite candidates are position-independent.)"""
+def test_small_chunks_with_moving_camera(gpu, loaded, crt, scenes_mod):
+    """Chunks smaller than a row of tiles (tiny queue budget on a refractive scene, several chunk streams): band copies
+    to the host would race between chunks sharing a 4-row band and leave stale rows of the PREVIOUS frame -- visible
+    only when the camera moves between renders."""
+    sf, flat, _, _ = loaded["hw11_room"]
+    gpu.upload(flat, keepalive=sf)
+    cams = [crt.Camera.make(p, r) for p, r in scenes_mod.orbit_cameras(12, radius=1.0, center_z=-2.0)[:4]]
+    gpu.set_queue_budget(16 << 30)
+    big = [gpu.render(cam, crt.make_options())[0].copy() for cam in cams]
+    gpu.set_queue_budget(64 << 20)
+    gpu.set_concurrency(6)
+    small = [gpu.render(cam, crt.make_options())[0].copy() for cam in cams]
+    gpu.set_queue_budget(16 << 30)
+    for a, b in zip(big, small):
+        assert same_f32(a, b).all()
+    assert not same_f32(big[0], big[1]).all()  # the camera did move
+
+
+@pytest.mark.parametrize("name", list(SMALL_SCENES))
+def test_default_traversal_equals_literal_walk(name, gpu, loaded, crt):
+    """traversal = 0 (default: conservative culling + tail hand-off) against traversal = 1 (the
+    reference's literal visit-all itinerary): hit ids, t, float RGB and ray counts must be bit-identical on every scene,
+    the NaN-triangle scene included (non-finite candidates only matter while no finite one exists, and nothing is
+    culled until then).  The culled walk must also do less work than the literal one where there is anything to cull."""
     sf, flat, rects, n = loaded[name]
     gpu.upload(flat, keepalive=sf)
-    a, _, ha, sa = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=0), want_hits=True)
-    b, _, hb, sb = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=1, count_work=2), want_hits=True)
+    a, _, ha, sa = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=1, count_work=2), want_hits=True)
+    b, _, hb, sb = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=0, count_work=2), want_hits=True)
     assert same_f32(a, b).all()
     assert np.array_equal(ha["mesh"], hb["mesh"]) and np.array_equal(ha["triangle"], hb["triangle"])
+    assert same_f32(ha["t"], hb["t"]).all()
     assert sa["rays_total"] == sb["rays_total"]
-    with pytest.raises(crt.CrtError):  # visit-all counting is only defined for the exact walk
-        gpu.render(sf.camera(), crt.make_options(traversal=1, count_work=1))
+    assert sb["node_tests"] <= sa["node_tests"] and sb["triangle_tests"] <= sa["triangle_tests"]
+    if name in ("hw14_small", "hw11_room", "hw07_scene0b"):
+        assert sb["node_tests"] < sa["node_tests"]
+    # count_work = 1 counts the reference's visit-all work whatever `traversal` says
+    _, _, _, sc1 = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=0, count_work=1))
+    _, _, _, sc2 = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=1, count_work=1))
+    assert sc1["node_tests"] == sc2["node_tests"] and sc1["triangle_tests"] == sc2["triangle_tests"]
 
 
 def test_dedup_does_less_work_than_visit_all_with_same_pixels(gpu, loaded, crt):
@@ -197,74 +222,55 @@ def test_production_path_matches_golden(name, gpu, loaded, crt):
     assert [st["rays_primary"], st["rays_shadow"], st["rays_reflection"], st["rays_refraction"]] == list(g["rays"])
 
 
-@pytest.fixture(scope="module")
-def gpu_wide(built):
-    """A context that walks the opt-in 4-wide layout (CRT_LAYOUT is read by crtb200_create)."""
-    os.environ["CRT_LAYOUT"] = "wide"
+def _ctx_with_env(built, **env):
+    """A context created under tuning environment variables (crtb200_create reads them once)."""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
     try:
-        ctx = built.Context(0)
+        return built.Context(0)
     finally:
-        del os.environ["CRT_LAYOUT"]
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.fixture(scope="module")
+def gpu_coop_all(built):
+    """Every walk is handed to k_coop before its first step (a small frame's queue is dry after the first refill, and
+    tail_lanes = 32 hands off at once): the warp-per-ray walk does ALL the traversal work of the frame."""
+    ctx = _ctx_with_env(built, CRT_TAIL_LANES=32, CRT_TAIL_GRACE=1)
     yield ctx
     ctx.close()
 
 
-@pytest.mark.parametrize("name", list(SMALL_SCENES))
-def test_wide_layout_matches_golden(name, gpu_wide, loaded, crt):
-    """The 4-wide collapse of the reference trees (crt_device.cuh "wide walk") enumerates the same candidates in the same
-    order: hit ids, t and float RGB bit-identical to the reference fixtures, NaN-ray scene included."""
-    sf, flat, rects, n = loaded[name]
-    gpu_wide.upload(flat, keepalive=sf)
-    for traversal in (0, 1):
-        if traversal == 1 and name == "degenerate_uv":
-            continue
-        rgb, rgb8, hits, st = gpu_wide.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=traversal),
-                                              want_rgb8=True, want_hits=True)
-        g = np.load(os.path.join(GOLDEN, name + ".npz"))
-        cov = _covered(sf, rects, n)
-        assert np.array_equal(hits["mesh"][cov], g["hits"]["mesh"][cov]) and np.array_equal(hits["triangle"][cov], g["hits"]["triangle"][cov])
-        _assert_pixels(name, rgb, g["rgb"], rgb8, g["ppm"])
-        assert [st["rays_primary"], st["rays_shadow"], st["rays_reflection"], st["rays_refraction"]] == list(g["rays"])
-
-
-def test_wide_layout_falls_back_when_boxes_do_not_nest(gpu_wide, built, scene_dir, ob, crt):
-    """The wide walk is only equivalent to the reference's when every child box lies inside its parent's.  A caller may
-    upload any tree through the C ABI: shrink one inner box so its children stick out -> the library must keep walking
-    the binary layout, i.e. still agree with the oracle run on the very same (odd) tree."""
-    sf = built.SceneFile("hw14_small.crtscene", scene_dir)
-    flat = sf.flatten()
-    s = flat.contents
-    big = max(range(s.n_meshes), key=lambda m: s.meshes[m].n_nodes)
-    root = s.mesh_nodes[s.meshes[big].first_node]
-    assert root.leaf_count == 0
-    root.box_min[0] += 0.25 * (root.box_max[0] - root.box_min[0])  # children keep the old min.x: no longer nested
-    gpu_wide.upload(flat, keepalive=sf)
-    rgb, _, hits, st = gpu_wide.render(sf.camera(), crt.make_options(), want_hits=True)
-    o_rgb, o_hits, o_st = ob.render(flat, sf.camera(), crt.make_options())
-    assert np.array_equal(hits["mesh"], o_hits["mesh"]) and np.array_equal(hits["triangle"], o_hits["triangle"])
-    assert same_f32(rgb, o_rgb).all()
-    assert st["rays_total"] == o_st["rays_total"]
-
-
 @pytest.fixture(scope="module")
-def gpu_steal(built):
-    """A context that runs the opt-in range-stealing kernels k_closest_s / k_shadow_s (CRT_STEAL is read by crtb200_create)."""
-    os.environ["CRT_STEAL"] = "1"
-    try:
-        ctx = built.Context(0)
-    finally:
-        del os.environ["CRT_STEAL"]
+def gpu_coop_mid(built):
+    """Walks are handed off in mid-flight: two rounds after the queue ran dry, whatever is still walking."""
+    ctx = _ctx_with_env(built, CRT_TAIL_LANES=0, CRT_TAIL_GRACE=2)
     yield ctx
     ctx.close()
 
 
+@pytest.fixture(scope="module")
+def gpu_no_handoff(built):
+    ctx = _ctx_with_env(built, CRT_TAIL_GRACE=0)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("which", ["all", "mid", "off"])
 @pytest.mark.parametrize("name", list(SMALL_SCENES))
-def test_range_stealing_matches_golden(name, gpu_steal, loaded, crt):
-    """Long walks hand the far part of their node range to idle lanes of the warp (crt_kernels.cuh, k_*_s): helper
-    candidates are folded back in encounter order, so hit ids, t and float RGB stay bit-identical to the reference."""
+def test_tail_handoff_matches_golden(name, which, gpu_coop_all, gpu_coop_mid, gpu_no_handoff, loaded, crt):
+    """k_coop explores a handed-off walk in a different order (a LIFO of subtrees, 32 boxes per iteration); by the nesting
+    property the set of tested leaves is the same, and closest-hit candidates are put back into the reference's
+    encounter order by their (leaf, reference) key -- so hit ids, t and every pixel stay bit-identical to the
+    reference fixtures, with culling (traversal 0) and without (traversal 1 has no hand-off: literal walk)."""
+    ctx = {"all": gpu_coop_all, "mid": gpu_coop_mid, "off": gpu_no_handoff}[which]
     sf, flat, rects, n = loaded[name]
-    gpu_steal.upload(flat, keepalive=sf)
-    rgb, rgb8, hits, st = gpu_steal.render(sf.camera(), crt.make_options(rects=rects, n_rects=n), want_rgb8=True, want_hits=True)
+    ctx.upload(flat, keepalive=sf)
+    rgb, rgb8, hits, st = ctx.render(sf.camera(), crt.make_options(rects=rects, n_rects=n), want_rgb8=True, want_hits=True)
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     cov = _covered(sf, rects, n)
     assert np.array_equal(hits["mesh"][cov], g["hits"]["mesh"][cov]) and np.array_equal(hits["triangle"][cov], g["hits"]["triangle"][cov])
@@ -274,49 +280,43 @@ def test_range_stealing_matches_golden(name, gpu_steal, loaded, crt):
     assert [st["rays_primary"], st["rays_shadow"], st["rays_reflection"], st["rays_refraction"]] == list(g["rays"])
 
 
-def test_range_stealing_full_size_equals_default(gpu, gpu_steal, built):
-    """1920x1080 room with 196 608-triangle mirror and glass spheres (thousands of long walks, depth 5): the stealing
-    kernels and the default kernels must agree bit for bit on hits and colours."""
+def test_tail_handoff_full_size_equals_literal_walk(gpu, gpu_coop_mid, built):
+    """1920x1080 room with 196 608-triangle mirror and glass spheres, depth 5 (thousands of long walks on every level):
+    default kernels, aggressive mid-flight hand-off and the literal walk must agree bit for bit."""
     import importlib
     bench_mod = importlib.import_module("bench")
     f, folder, kw, tex, depth = bench_mod.ensure_scene("hw11_room_128", {})
     sf = built.SceneFile(f, folder)
     flat = sf.flatten()
     outs = []
-    for ctx in (gpu, gpu_steal):
+    for ctx, trav in ((gpu, 1), (gpu, 0), (gpu_coop_mid, 0)):
         ctx.upload(flat, keepalive=sf)
-        rgb, _, hits, st = ctx.render(sf.camera(), built.make_options(max_depth=depth), want_hits=True)
+        rgb, _, hits, st = ctx.render(sf.camera(), built.make_options(max_depth=depth, traversal=trav), want_hits=True)
         outs.append((rgb, hits, st))
-    assert np.array_equal(outs[0][1]["triangle"], outs[1][1]["triangle"]) and np.array_equal(outs[0][1]["mesh"], outs[1][1]["mesh"])
-    assert same_f32(outs[0][1]["t"], outs[1][1]["t"]).all()
-    assert same_f32(outs[0][0], outs[1][0]).all()
-    assert outs[0][2]["rays_total"] == outs[1][2]["rays_total"]
+    for k in (1, 2):
+        assert np.array_equal(outs[0][1]["triangle"], outs[k][1]["triangle"]) and np.array_equal(outs[0][1]["mesh"], outs[k][1]["mesh"])
+        assert same_f32(outs[0][1]["t"], outs[k][1]["t"]).all()
+        assert same_f32(outs[0][0], outs[k][0]).all()
+        assert outs[0][2]["rays_total"] == outs[k][2]["rays_total"]
 
 
-@pytest.fixture(scope="module")
-def gpu_long(built):
-    """A context that suspends every shadow walk after 4 node-phase iterations and finishes it in k_shadow_long, one warp
-    per ray (CRT_LONG_BUDGET is read by crtb200_create; the default, 0, never suspends)."""
-    os.environ["CRT_LONG_BUDGET"] = "4"
-    try:
-        ctx = built.Context(0)
-    finally:
-        del os.environ["CRT_LONG_BUDGET"]
-    yield ctx
-    ctx.close()
-
-
-@pytest.mark.parametrize("name", list(SMALL_SCENES))
-def test_long_walk_second_pass_matches_golden(name, gpu_long, loaded, crt):
-    """The warp-per-ray walk covers the rest of a suspended shadow walk in a different order (LIFO of subtrees, 32 boxes
-    per iteration); by the nesting property the set of tested leaves is the same, so every pixel stays bit-identical."""
-    sf, flat, rects, n = loaded[name]
-    gpu_long.upload(flat, keepalive=sf)
-    for traversal in (0, 1):
-        if traversal == 1 and name == "degenerate_uv":
-            continue
-        rgb, rgb8, hits, st = gpu_long.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=traversal),
-                                              want_rgb8=True, want_hits=True)
-        g = np.load(os.path.join(GOLDEN, name + ".npz"))
-        _assert_pixels(name, rgb, g["rgb"], rgb8, g["ppm"])
-        assert [st["rays_primary"], st["rays_shadow"], st["rays_reflection"], st["rays_refraction"]] == list(g["rays"])
+def test_trees_that_do_not_nest_take_the_literal_walk(gpu, built, scene_dir, ob, crt):
+    """Culling and the order-free walk of k_coop are only equivalent to the reference's walk when every child box lies
+    inside its parent's.  A caller may upload any tree through the C ABI: shrink one inner box so its children stick out
+    -> the library must fall back to the literal walk, i.e. still agree with the oracle run on the very same (odd) tree."""
+    sf = built.SceneFile("hw14_small.crtscene", scene_dir)
+    flat = sf.flatten()
+    s = flat.contents
+    big = max(range(s.n_meshes), key=lambda m: s.meshes[m].n_nodes)
+    root = s.mesh_nodes[s.meshes[big].first_node]
+    assert root.leaf_count == 0
+    root.box_min[0] += 0.25 * (root.box_max[0] - root.box_min[0])  # children keep the old min.x: no longer nested
+    gpu.upload(flat, keepalive=sf)
+    rgb, _, hits, st = gpu.render(sf.camera(), crt.make_options(), want_hits=True)
+    o_rgb, o_hits, o_st = ob.render(flat, sf.camera(), crt.make_options())
+    assert np.array_equal(hits["mesh"], o_hits["mesh"]) and np.array_equal(hits["triangle"], o_hits["triangle"])
+    assert same_f32(rgb, o_rgb).all()
+    assert st["rays_total"] == o_st["rays_total"]
+    _, _, _, a = gpu.render(sf.camera(), crt.make_options(count_work=2, traversal=0))
+    _, _, _, b = gpu.render(sf.camera(), crt.make_options(count_work=2, traversal=1))
+    assert a["node_tests"] == b["node_tests"]  # nothing was culled

@@ -1,0 +1,91 @@
+#!/usr/bin/env python3
+"""Round-2 A/B matrix in one process (tools only): device ms per frame (median of N, concurrency 1, L2 flushed) for
+  traversal   0 = default (conservative culling + tail hand-off)   1 = literal visit-all walk
+  hand-off    CRT_TAIL_LANES / CRT_TAIL_GRACE settings (read by crtb200_create, so one context per setting)
+  shards      whole frame and shard 0 of 2 / 4 / 8 (the per-rank work of a tile-sharded N-GPU frame)
+
+  python tools/r2_measure.py --workloads hw14_dragon_class,synthetic_10M,hw11_room --tails 16:4,32:1,8:8,0:0
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def ctx_with_env(crt, env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return crt.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workloads", default="hw14_dragon_class")
+    ap.add_argument("--tails", default="16:4,0:0", help="lanes:grace pairs; grace 0 = hand-off off")
+    ap.add_argument("--shards", default="1,8")
+    ap.add_argument("--frames", type=int, default=7)
+    ap.add_argument("--json", default="")
+    args = ap.parse_args()
+    import torch
+    crt = importlib.import_module(bench.PKG)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    rows = []
+    for w in args.workloads.split(","):
+        f, folder, kw, tex, depth = bench.ensure_scene(w, {})
+        sf = crt.SceneFile(f, folder)
+        flat = sf.flatten()
+        configs = [("literal", 1, None)] + [(f"default tail {t}", 0, t) for t in args.tails.split(",")]
+        for label, trav, tail in configs:
+            env = {}
+            if tail is not None:
+                lanes, grace = tail.split(":")
+                env = {"CRT_TAIL_LANES": lanes, "CRT_TAIL_GRACE": grace}
+            ctx = ctx_with_env(crt, env)
+            ctx.upload(flat, keepalive=sf)
+            ctx.set_concurrency(1)
+            for shards in [int(x) for x in args.shards.split(",")]:
+                opt = crt.make_options(max_depth=depth, traversal=trav, shard_index=0, shard_count=shards)
+                if shards > 1:
+                    out = torch.zeros((ctx.shard_items(shards), 3), dtype=torch.float32, device="cuda")
+                else:
+                    out = torch.zeros((sf.info.height, sf.info.width, 3), dtype=torch.float32, device="cuda")
+                ms, cms, sms = [], [], []
+                for k in range(args.frames + 2):
+                    flush.fill_(k & 0xFF)
+                    torch.cuda.synchronize()
+                    ctx.render_device(sf.camera(), opt, d_rgb=out.data_ptr(), stream=stream)
+                    torch.cuda.synchronize()
+                    st = ctx.last_stats()
+                    if k >= 2:
+                        ms.append(st["device_ms"])
+                        cms.append(st["closest_ms"])
+                        sms.append(st["shadow_ms"])
+                row = {"workload": w, "config": label, "shards": shards, "device_ms": statistics.median(ms), "min_ms": min(ms),
+                       "closest_ms": statistics.median(cms), "shadow_ms": statistics.median(sms), "rays": st["rays_total"],
+                       "mrays_s": st["rays_total"] / statistics.median(ms) / 1e3}
+                rows.append(row)
+                print("%-20s %-22s shards %d  frame %7.3f ms (min %7.3f)  closest %7.3f  shadow %7.3f  %8.1f Mrays/s" %
+                      (w, label, shards, row["device_ms"], row["min_ms"], row["closest_ms"], row["shadow_ms"], row["mrays_s"]), flush=True)
+                del out
+            ctx.close()
+    if args.json:
+        with open(args.json, "w") as fh:
+            json.dump(rows, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()
