@@ -111,7 +111,9 @@ class Stats(C.Structure):
                 ("rays_refraction", C.c_uint64), ("node_tests_closest", C.c_uint64), ("triangle_tests_closest", C.c_uint64),
                 ("node_tests_shadow", C.c_uint64), ("triangle_tests_shadow", C.c_uint64),
                 ("device_ms", C.c_double), ("closest_ms", C.c_double), ("shadow_ms", C.c_double), ("total_ms", C.c_double),
-                ("kernel_launches", C.c_uint32), ("levels", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("levels", C.c_uint32),
+                ("handoff_closest", C.c_uint64), ("handoff_shadow", C.c_uint64),
+                ("coop_closest_ms", C.c_double), ("coop_shadow_ms", C.c_double)]
 
     def as_dict(self) -> dict:
         d = {n: getattr(self, n) for n, _ in self._fields_}
@@ -185,6 +187,8 @@ def front() -> C.CDLL:
         lib.crtfe_camera_roll.argtypes = [C.POINTER(Camera), C.c_float]
         lib.crtfe_camera_truck.argtypes = [C.POINTER(Camera), C.POINTER(C.c_float)]
         lib.crtfe_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        lib.crtfe_append_f32.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64]
+        lib.crtfe_append_u32.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64]
         lib.crtfe_tracer_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         lib.crtfe_tracer_free.argtypes = [C.c_void_p]
         lib.crtfe_tracer_set_camera.argtypes = [C.c_void_p, C.POINTER(Camera)]

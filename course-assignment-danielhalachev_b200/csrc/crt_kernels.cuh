@@ -46,15 +46,14 @@ struct Levels {
   float4 *dq;         // diffuse queue, 3 x float4 per item: {P, bits(node)} {N, base.r} {base.g, base.b, -, -}
   uint8_t *vis;       // per (diffuse item, light): 1 = the light is visible from the hit
   uint32_t *counts;   // [CRT_MAX_LEVELS] rays per level; [CRT_MAX_LEVELS] = diffuse queue length
-  unsigned long long *stats;  // [0..3] rays by type, [4],[5] closest node / triangle tests, [6],[7] shadow
+  unsigned long long *stats;  // [0..3] rays by type, [4],[5] closest node / triangle tests, [6],[7] shadow, [32],[33] walks handed to k_coop
   uint32_t offset[CRT_MAX_LEVELS + 1];
   // tail hand-off (k_coop): once the work queue of a traversal kernel is dry, the walks still running are written to
   // ovf[] (3 x uint4 per record) and finished one WARP per ray; tail_grace = 0 switches this off
   uint4 *ovf;
   uint32_t *ovf_ctl;  // per traversal launch L (level, or CRT_MAX_LEVELS for the shadow pass): [2L] written, [2L+1] taken
   uint32_t ovf_cap;
-  uint32_t tail_lanes;  // hand off as soon as this few lanes of the warp are still walking ...
-  uint32_t tail_grace;  // ... or after this many rounds past the end of the queue, whichever comes first
+  uint32_t tail_iters;  // 0 = off; else once the queue is dry a walk that has taken tail_iters - 1 node-phase iterations is handed off
 };
 
 enum { COMB_FINAL = 0, COMB_REFLECT = 1, COMB_FRESNEL = 2, COMB_COPY = 3 };
@@ -235,22 +234,30 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, const
 // ------------------------------------------------------------------------------------------------------------
 // Tail hand-off.  A ray is walked by one lane, and 2-3 % of the rays of a large-mesh frame need hundreds of node-phase
 // iterations: once the queue is dry a traversal kernel used to wait 0.3-0.8 ms for its last few lanes.
-// Now a warp whose queue is dry hands the walks it still holds to k_coop: each lane's state goes into one 48-byte record
+// Now, once the queue is dry (every warp polls the global cursor, so a warp full of long walks learns it too), a lane
+// whose walk has already taken lv.tail_iters node-phase iterations hands it to k_coop, where a whole warp finishes it;
+// young walks keep going here (most end within a few iterations; the rest reach the threshold and follow).  So a
+// traversal kernel ends at most ~tail_iters iterations after its queue ran dry, and k_coop only sees walks that are
+// long enough to amortise its ramp.  A walk's state goes into one 48-byte record
 //   r0 = {ray id (queue node / visibility slot), cur, cend, resume}     r1 = {mref, mend, seen lo, seen hi}
 //   r2 = {below, bits(mu), bits(best_t), best_tri}
 // written at the top of a round, where no lane has a pending triangle range.  min_t is implied: best_t when that is
 // below +inf, else +inf (closest_offer keeps it so).
 // ------------------------------------------------------------------------------------------------------------
-CRT_DI bool tail_handoff(const Levels &lv, const uint32_t launch, const bool active, uint32_t &grace, const uint32_t id, const Trav &tv,
+CRT_DI bool queue_dry(const uint32_t *work_counter, const uint32_t total) {
+  uint32_t v = 0;
+  if (lane_id() == 0) v = *reinterpret_cast<const volatile uint32_t *>(work_counter);
+  return __shfl_sync(CRT_FULL_MASK, v, 0) >= total;
+}
+CRT_DI bool tail_handoff(const Levels &lv, const uint32_t launch, const bool want, const uint32_t id, const Trav &tv,
                          const float best_t, const uint32_t best_tri) {
-  const uint32_t am = __ballot_sync(CRT_FULL_MASK, active);
-  if (!am) return false;
-  if ((uint32_t)__popc(am) > lv.tail_lanes && ++grace <= lv.tail_grace) return false;
+  const uint32_t wm = __ballot_sync(CRT_FULL_MASK, want);
+  if (!wm) return false;
   uint32_t base = 0;
-  if (lane_id() == 0) base = atomicAdd(&lv.ovf_ctl[2u * launch], (uint32_t)__popc(am));
+  if (lane_id() == 0) base = atomicAdd(&lv.ovf_ctl[2u * launch], (uint32_t)__popc(wm));
   base = __shfl_sync(CRT_FULL_MASK, base, 0);
-  const uint32_t r = base + __popc(am & lanemask_lt());
-  if (!active || r >= lv.ovf_cap) return false;  // a full buffer (never, by its sizing) just leaves the lane walking
+  const uint32_t r = base + __popc(wm & lanemask_lt());
+  if (!want || r >= lv.ovf_cap) return false;  // a full buffer (never, by its sizing) just leaves the lane walking
   uint4 *rec = lv.ovf + 3 * (size_t)r;
   rec[0] = make_uint4(id, tv.cur, tv.cend, tv.resume);
   rec[1] = make_uint4(tv.mref, tv.mend, (uint32_t)tv.seen, (uint32_t)(tv.seen >> 32));
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
   const uint32_t node_base = lv.offset[level];
   const uint32_t lane = lane_id();
   bool active = false, exhausted = false;
-  uint32_t node = 0, n_nodes = 0, n_tris = 0, grace = 0;
+  uint32_t node = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0;
 #if CRT_PHASE_CLOCKS
   uint32_t ray_iters = 0;
 #endif
@@ -325,6 +332,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
           closest_begin(cl);
           node = node_base + i;
           active = true;
+          walk_iters = 0;
 #if CRT_PHASE_CLOCKS
           ray_iters = 0;
 #endif
@@ -335,8 +343,9 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
         }
       }
     }
-    if (!COUNT && exhausted && lv.tail_grace) {
-      if (tail_handoff(lv, level, active, grace, node, tv, cl.best_t, cl.best_tri)) active = false;
+    if (!COUNT && lv.tail_iters) {
+      if (!exhausted && (++round & 3u) == 0u) exhausted = queue_dry(work_counter, total);
+      if (exhausted && tail_handoff(lv, level, active && walk_iters + 1u >= lv.tail_iters, node, tv, cl.best_t, cl.best_tri)) active = false;
     }
     if (!__any_sync(CRT_FULL_MASK, active)) {
       if (exhausted) break;
@@ -366,6 +375,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
         if (need) ray_iters++;
 #endif
         if (need) {
+          walk_iters++;
           // conservative culling: beyond the best finite hit; behind the origin once a finite hit exists (crt_device.cuh)
           const bool fin = cl.min_t < CRT_INF;
           need = CRT_NODE_PAIR ? trav_fast2<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t, fin) : trav_fast<COUNT, CULL>(tv, sc, ray, n_nodes, cl.min_t, fin);
@@ -635,7 +645,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
   const uint32_t total = n_hits * sc.n_lights;
   const uint32_t lane = lane_id();
   bool active = false, exhausted = false, occluded = false;
-  uint32_t slot = 0, n_nodes = 0, n_tris = 0, grace = 0;
+  uint32_t slot = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0;
 #if CRT_PHASE_CLOCKS
   uint32_t ray_iters = 0;
 #endif
@@ -668,6 +678,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
         occluded = false;
         slot = hit * sc.n_lights + light;
         active = true;
+        walk_iters = 0;
 #if CRT_PHASE_CLOCKS
         ray_iters = 0;
 #endif
@@ -677,8 +688,9 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
         }
       }
     }
-    if (COUNT == 0 && exhausted && lv.tail_grace) {
-      if (tail_handoff(lv, CRT_MAX_LEVELS, active, grace, slot, tv, 0.0f, CRT_INVALID)) active = false;
+    if (COUNT == 0 && lv.tail_iters) {
+      if (!exhausted && (++round & 3u) == 0u) exhausted = queue_dry(work_counter, total);
+      if (exhausted && tail_handoff(lv, CRT_MAX_LEVELS, active && walk_iters + 1u >= lv.tail_iters, slot, tv, 0.0f, CRT_INVALID)) active = false;
     }
     if (!__any_sync(CRT_FULL_MASK, active)) {
       if (exhausted) break;
@@ -704,7 +716,10 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
 #if CRT_PHASE_CLOCKS
         if (need) ray_iters++;
 #endif
-        if (need) need = CRT_NODE_PAIR ? trav_fast2<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit, true) : trav_fast<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit, true);
+        if (need) {
+          walk_iters++;
+          need = CRT_NODE_PAIR ? trav_fast2<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit, true) : trav_fast<(COUNT != 0), CULL>(tv, sc, ray, n_nodes, t_limit, true);
+        }
       }
       CRT_PC_MARK(2)
       const bool parked = active && tv.tref != tv.tend;
@@ -928,6 +943,7 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS) k_coop(const DScene sc, c
   const uint32_t lane = lane_id();
   const uint32_t launch = SHADOW ? (uint32_t)CRT_MAX_LEVELS : level;
   const uint32_t n_rec = min(lv.ovf_ctl[2u * launch], lv.ovf_cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n_rec) atomicAdd(&lv.stats[SHADOW ? 33 : 32], (unsigned long long)n_rec);
   for (;;) {
     uint32_t r = 0;
     if (lane == 0) r = atomicAdd(&lv.ovf_ctl[2u * launch + 1u], 1u);

@@ -90,9 +90,9 @@ struct crtb200_ctx {
   DevBuf<float4> vtx_normal;
   bool nested_ok = false;    // every child box of the uploaded mesh trees lies inside its parent's and no tree is deeper
                              // than the k_coop LIFO allows: the order-free walk of k_coop and the subtree culling are exact
-  uint32_t tail_lanes = 16;  // tail hand-off (crt_kernels.cuh): hand a warp's walks to k_coop once the queue is dry and at
-  uint32_t tail_grace = 4;   //   most tail_lanes lanes are still walking, or after tail_grace more rounds.  CRT_TAIL_LANES /
-                             //   CRT_TAIL_GRACE override (tools); CRT_TAIL_GRACE=0 switches the hand-off off
+  int tail_iters = 32;       // tail hand-off (crt_kernels.cuh): once a traversal kernel's queue is dry, walks that have taken
+                             // this many node-phase iterations go to k_coop.  CRT_TAIL_ITERS overrides (tools / tests):
+                             // 0 = every walk still running, -1 = off
   DevBuf<uint32_t> top_refs;
   DevBuf<uint4> tri_shade;
   DevBuf<float2> vtx_uv;
@@ -192,8 +192,7 @@ int crtb200_create(int device, crtb200_ctx **out) {
     if (b > 0) c->blocks_closest = c->blocks_shadow = b * c->sm_count;
   }
   if (const char *env = getenv("CRT_L2_PERSIST")) c->l2_persist = atoi(env);
-  if (const char *env = getenv("CRT_TAIL_LANES")) c->tail_lanes = (uint32_t)std::max(0, std::min(32, atoi(env)));
-  if (const char *env = getenv("CRT_TAIL_GRACE")) c->tail_grace = (uint32_t)std::max(0, atoi(env));
+  if (const char *env = getenv("CRT_TAIL_ITERS")) c->tail_iters = std::max(-1, atoi(env));
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
   c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
   if (c->l2_persist && c->l2_persist_max)
@@ -580,7 +579,7 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   CUDA_TRY(cudaMemset(c->frame.p, 0, px * 3 * sizeof(float)));  // colorBuffer starts at (0,0,0), RayTracer.cpp:47-50
   CUDA_TRY(c->frame8.ensure(px * 3));
   CUDA_TRY(cudaMemset(c->frame8.p, 0, px * 3));
-  CUDA_TRY(c->stats_dev.ensure(32));
+  CUDA_TRY(c->stats_dev.ensure(40));
   c->mask_valid = false;
   c->cap_items = 0;
   c->have_scene = true;
@@ -689,8 +688,7 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     q.lv.ovf = q.ovf.p;
     q.lv.ovf_ctl = q.ctl.p + n_counts + n_work;
     q.lv.ovf_cap = (uint32_t)ovf_cap;
-    q.lv.tail_lanes = 0;
-    q.lv.tail_grace = 0;
+    q.lv.tail_iters = 0;
     q.lv.ray_o = q.ray_o.p;
     q.lv.ray_d = q.ray_d.p;
     q.lv.hit_tri = q.hit_tri.p;
@@ -782,7 +780,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   // traversal 0 (default): conservative culling + tail hand-off, both exact and both resting on the nesting property of
   // the uploaded trees; traversal 1 and the visit-all counting mode walk the reference's literal itinerary
   const bool cull = o->traversal == 0 && o->count_work != 1 && c->nested_ok;
-  const bool handoff = o->traversal == 0 && o->count_work == 0 && c->nested_ok && c->tail_grace > 0;
+  const bool handoff = o->traversal == 0 && o->count_work == 0 && c->nested_ok && c->tail_iters >= 0;
   const uint32_t shard_count = o->shard_count ? o->shard_count : 1;
   if (o->shard_index >= shard_count) return fail(CRTB200_ERR_ARG, "shard_index >= shard_count");
   int rc = plan_mask(c, o);
@@ -816,7 +814,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   if (host_done) *host_done = band_copies;
   const int grid_simple = c->sm_count * 8;
 
-  CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 32 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 40 * sizeof(unsigned long long), st));
 #if CRT_PHASE_CLOCKS
   CUDA_TRY(cudaMemsetAsync(c->stats_dev.p + 27, 0xFF, sizeof(unsigned long long), st));  // atomicMin slots
   CUDA_TRY(cudaMemsetAsync(c->stats_dev.p + 31, 0xFF, sizeof(unsigned long long), st));
@@ -837,8 +835,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     fr.item_begin = begin;
     fr.n_items0 = std::min(c->cap_items, shard_items - begin);
     CUDA_TRY(cudaMemsetAsync(q.ctl.p, 0, q.ctl.n * sizeof(uint32_t), qs));
-    q.lv.tail_lanes = handoff ? c->tail_lanes : 0u;
-    q.lv.tail_grace = handoff ? c->tail_grace : 0u;
+    q.lv.tail_iters = handoff ? (uint32_t)(c->tail_iters + 1) : 0u;
     for (uint32_t l = 0; l < levels; l++) {
       if (per_kernel) {
         cudaEventRecord(next_event(c), qs);
@@ -853,6 +850,11 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       else
         launch_closest<false, false>(c, l == 0, fr, q.lv, l, q.work + l, qs);
       if (handoff) {
+        if (per_kernel) {
+          cudaEventRecord(next_event(c), qs);
+          cudaEventRecord(next_event(c), qs);
+          c->kev_kind.push_back(2);
+        }
         if (cull)
           launch_coop_closest<true>(c, l == 0, fr, q.lv, l, qs);
         else
@@ -879,6 +881,11 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     else
       k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
     if (handoff) {
+      if (per_kernel) {
+        cudaEventRecord(next_event(c), qs);
+        cudaEventRecord(next_event(c), qs);
+        c->kev_kind.push_back(3);
+      }
       if (cull)
         k_coop<true, false, true><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, qs>>>(c->sc, fr, q.lv, 0);
       else
@@ -915,7 +922,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
 }
 
 static int collect_stats(crtb200_ctx *c, bool timed) {
-  unsigned long long st[32];
+  unsigned long long st[40];
   CUDA_TRY(cudaMemcpy(st, c->stats_dev.p, sizeof(st), cudaMemcpyDeviceToHost));
 #if CRT_PHASE_CLOCKS
   for (int k = 0; k < 2; k++) {
@@ -969,15 +976,21 @@ static int collect_stats(crtb200_ctx *c, bool timed) {
   c->last.triangle_tests_closest = st[5];
   c->last.node_tests_shadow = st[6];
   c->last.triangle_tests_shadow = st[7];
+  c->last.handoff_closest = st[32];
+  c->last.handoff_shadow = st[33];
   if (timed) {
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
     c->last.device_ms = ms;
-    c->last.closest_ms = c->last.shadow_ms = 0.0;
+    c->last.closest_ms = c->last.shadow_ms = c->last.coop_closest_ms = c->last.coop_shadow_ms = 0.0;
     for (size_t k = 0; k < c->kev_kind.size() && 2 * k + 1 < c->kev_used; k++) {
       float kms = 0.f;
       CUDA_TRY(cudaEventElapsedTime(&kms, c->kev[2 * k], c->kev[2 * k + 1]));
-      (c->kev_kind[k] == 0 ? c->last.closest_ms : c->last.shadow_ms) += kms;
+      // closest_ms / shadow_ms include their k_coop part, which is also reported on its own
+      if (c->kev_kind[k] == 0 || c->kev_kind[k] == 2) c->last.closest_ms += kms;
+      if (c->kev_kind[k] == 1 || c->kev_kind[k] == 3) c->last.shadow_ms += kms;
+      if (c->kev_kind[k] == 2) c->last.coop_closest_ms += kms;
+      if (c->kev_kind[k] == 3) c->last.coop_shadow_ms += kms;
     }
   }
   return CRTB200_OK;

@@ -1,4 +1,5 @@
 // extern "C" wrappers of the C++ front end (include/crtfront.h).
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -55,6 +56,44 @@ int crtfe_scene_load(const char *path, const char *folder, crtfe_scene **out) {
     *out = s.release();
   })
 }
+// Appends n comma-separated numbers to a text file ("%.9g" for binary32 values: shortest text that round-trips through
+// the reference's double-parsing GetFloat(), SceneParser.cpp; decimal for u32).  Used by the synthetic-scene writer: a
+// 10 M-triangle .crtscene holds 45 M numbers.
+static int append_numbers(const char *path, const void *data, uint64_t n, bool is_float) {
+  if (!path || (!data && n)) return fail("null argument");
+  FILE *f = std::fopen(path, "ab");
+  if (!f) return fail(std::string("cannot open ") + path);
+  std::string buf;
+  buf.reserve(1 << 20);
+  char tmp[40];
+  for (uint64_t i = 0; i < n; i++) {
+    int len;
+    if (is_float) {
+      len = std::snprintf(tmp, sizeof(tmp), "%.9g", (double)static_cast<const float *>(data)[i]);
+    } else {
+      uint32_t v = static_cast<const uint32_t *>(data)[i];
+      char *e = tmp + sizeof(tmp), *q = e;
+      do {
+        *--q = (char)('0' + v % 10u);
+        v /= 10u;
+      } while (v);
+      len = (int)(e - q);
+      std::memmove(tmp, q, (size_t)len);
+    }
+    if (i) buf.push_back(',');
+    buf.append(tmp, (size_t)len);
+    if (buf.size() > (1u << 20) - 64) {
+      std::fwrite(buf.data(), 1, buf.size(), f);
+      buf.clear();
+    }
+  }
+  std::fwrite(buf.data(), 1, buf.size(), f);
+  const bool ok = std::fclose(f) == 0;
+  return ok ? 0 : fail("write failed");
+}
+int crtfe_append_f32(const char *path, const float *values, uint64_t n) { return append_numbers(path, values, n, true); }
+int crtfe_append_u32(const char *path, const uint32_t *values, uint64_t n) { return append_numbers(path, values, n, false); }
+
 int crtfe_scene_free(crtfe_scene *s) {
   delete s;
   return 0;

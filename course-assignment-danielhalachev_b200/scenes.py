@@ -148,9 +148,31 @@ def _ffloat(x: float) -> str:
 
 
 def write_crtscene(path: str, scene: dict) -> str:
-    """Serialise a scene dict (see the builders below) to `.crtscene` JSON."""
-    out = io.StringIO()
-    w = out.write
+    """Serialise a scene dict (see the builders below) to `.crtscene` JSON.  Large number arrays go through the front
+    end's native formatter when it is built (same "%.9g" / decimal text, ~30x faster than numpy's char.mod)."""
+    native = None
+    try:
+        from . import front as _front
+        native = _front()
+    except Exception:
+        native = None
+    f = open(path, "w")
+
+    def w(text: str) -> None:
+        f.write(text)
+
+    def numbers(a, is_float: bool) -> None:
+        nonlocal f
+        arr = np.ascontiguousarray(np.asarray(a).reshape(-1), dtype=np.float32 if is_float else np.uint32)
+        if native is None or arr.size < 4096:
+            w(_fmt_floats(arr) if is_float else _fmt_ints(arr))
+            return
+        f.close()
+        fn = native.crtfe_append_f32 if is_float else native.crtfe_append_u32
+        if fn(path.encode(), arr.ctypes.data, arr.size) != 0:
+            raise IOError("native scene writer failed for " + path)
+        f = open(path, "a")
+
     st = scene["settings"]
     w('{"settings":{"background_color":[%s],"image_settings":{"width":%d,"height":%d,"bucket_size":%d}},'
       % (_fmt_floats(st["background_color"]), st["width"], st["height"], st["bucket_size"]))
@@ -190,13 +212,18 @@ def write_crtscene(path: str, scene: dict) -> str:
     for k, o in enumerate(scene["objects"]):
         if k:
             w(",")
-        w('{"material_index":%d,"vertices":[%s],' % (o["material_index"], _fmt_floats(o["vertices"])))
+        w('{"material_index":%d,"vertices":[' % o["material_index"])
+        numbers(o["vertices"], True)
+        w('],')
         if "uvs" in o:
-            w('"uvs":[%s],' % _fmt_floats(o["uvs"]))
-        w('"triangles":[%s]}' % _fmt_ints(o["triangles"]))
+            w('"uvs":[')
+            numbers(o["uvs"], True)
+            w('],')
+        w('"triangles":[')
+        numbers(o["triangles"], False)
+        w(']}')
     w("]}\n")
-    with open(path, "w") as f:
-        f.write(out.getvalue())
+    f.close()
     return path
 
 

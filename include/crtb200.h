@@ -182,6 +182,10 @@ typedef struct crtb200_stats {
   double total_ms;   /* host wall time of the call, copies included                                          */
   uint32_t kernel_launches;
   uint32_t levels;
+  /* tail hand-off: walks finished one warp per ray by k_coop, and the part of closest_ms / shadow_ms  */
+  /* spent there                                                                                                      */
+  uint64_t handoff_closest, handoff_shadow;
+  double coop_closest_ms, coop_shadow_ms;
 } crtb200_stats;
 
 typedef struct crtb200_ctx crtb200_ctx;

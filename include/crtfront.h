@@ -44,6 +44,9 @@ int crtfe_camera_roll(crtb200_camera *camera, float degrees);
 int crtfe_camera_truck(crtb200_camera *camera, const float direction[3]);
 
 int crtfe_write_ppm(const char *path, const float *rgb, uint32_t width, uint32_t height);
+/* scene-file writer helpers (synthetic workloads): append n comma-separated numbers to a text file, "%.9g" / decimal */
+int crtfe_append_f32(const char *path, const float *values, uint64_t n);
+int crtfe_append_u32(const char *path, const uint32_t *values, uint64_t n);
 
 /* RayTracer mirror */
 int crtfe_tracer_create(crtfe_scene *scene, int device, crtfe_tracer **out);

@@ -239,23 +239,23 @@ def _ctx_with_env(built, **env):
 @pytest.fixture(scope="module")
 def gpu_coop_all(built):
     """Every walk is handed to k_coop before its first step (a small frame's queue is dry after the first refill, and
-    tail_lanes = 32 hands off at once): the warp-per-ray walk does ALL the traversal work of the frame."""
-    ctx = _ctx_with_env(built, CRT_TAIL_LANES=32, CRT_TAIL_GRACE=1)
+    a threshold of 0 iterations hands off at once): the warp-per-ray walk does ALL the traversal work of the frame."""
+    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=0)
     yield ctx
     ctx.close()
 
 
 @pytest.fixture(scope="module")
 def gpu_coop_mid(built):
-    """Walks are handed off in mid-flight: two rounds after the queue ran dry, whatever is still walking."""
-    ctx = _ctx_with_env(built, CRT_TAIL_LANES=0, CRT_TAIL_GRACE=2)
+    """Walks are handed off in mid-flight: whatever has taken 3 node-phase iterations when the queue is dry."""
+    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=3)
     yield ctx
     ctx.close()
 
 
 @pytest.fixture(scope="module")
 def gpu_no_handoff(built):
-    ctx = _ctx_with_env(built, CRT_TAIL_GRACE=0)
+    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=-1)
     yield ctx
     ctx.close()
 
@@ -278,6 +278,10 @@ def test_tail_handoff_matches_golden(name, which, gpu_coop_all, gpu_coop_mid, gp
     assert same_f32(hits["t"][h], g["hits"]["t"][h]).all()
     _assert_pixels(name, rgb, g["rgb"], rgb8, g["ppm"])
     assert [st["rays_primary"], st["rays_shadow"], st["rays_reflection"], st["rays_refraction"]] == list(g["rays"])
+    if which == "all" and name not in ("empty_scene",):
+        assert st["handoff_closest"] >= st["rays_primary"]  # every primary walk went through k_coop
+    if which == "off":
+        assert st["handoff_closest"] == 0 and st["handoff_shadow"] == 0
 
 
 def test_tail_handoff_full_size_equals_literal_walk(gpu, gpu_coop_mid, built):

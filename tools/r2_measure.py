@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
 """Round-2 A/B matrix in one process (tools only): device ms per frame (median of N, concurrency 1, L2 flushed) for
   traversal   0 = default (conservative culling + tail hand-off)   1 = literal visit-all walk
-  hand-off    CRT_TAIL_LANES / CRT_TAIL_GRACE settings (read by crtb200_create, so one context per setting)
+  hand-off    CRT_TAIL_ITERS settings (read by crtb200_create, so one context per setting); -1 = off
   shards      whole frame and shard 0 of 2 / 4 / 8 (the per-rank work of a tile-sharded N-GPU frame)
 
-  python tools/r2_measure.py --workloads hw14_dragon_class,synthetic_10M,hw11_room --tails 16:4,32:1,8:8,0:0
+  python tools/r2_measure.py --workloads hw14_dragon_class,synthetic_10M,hw11_room --tails 32,64,-1
 """
 import argparse
 import importlib
@@ -34,7 +34,7 @@ def ctx_with_env(crt, env):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workloads", default="hw14_dragon_class")
-    ap.add_argument("--tails", default="16:4,0:0", help="lanes:grace pairs; grace 0 = hand-off off")
+    ap.add_argument("--tails", default="32,-1", help="CRT_TAIL_ITERS values; -1 = hand-off off")
     ap.add_argument("--shards", default="1,8")
     ap.add_argument("--frames", type=int, default=7)
     ap.add_argument("--json", default="")
@@ -52,8 +52,7 @@ def main():
         for label, trav, tail in configs:
             env = {}
             if tail is not None:
-                lanes, grace = tail.split(":")
-                env = {"CRT_TAIL_LANES": lanes, "CRT_TAIL_GRACE": grace}
+                env = {"CRT_TAIL_ITERS": tail}
             ctx = ctx_with_env(crt, env)
             ctx.upload(flat, keepalive=sf)
             ctx.set_concurrency(1)
@@ -63,7 +62,7 @@ def main():
                     out = torch.zeros((ctx.shard_items(shards), 3), dtype=torch.float32, device="cuda")
                 else:
                     out = torch.zeros((sf.info.height, sf.info.width, 3), dtype=torch.float32, device="cuda")
-                ms, cms, sms = [], [], []
+                ms, cms, sms, ccm, csm = [], [], [], [], []
                 for k in range(args.frames + 2):
                     flush.fill_(k & 0xFF)
                     torch.cuda.synchronize()
@@ -74,12 +73,17 @@ def main():
                         ms.append(st["device_ms"])
                         cms.append(st["closest_ms"])
                         sms.append(st["shadow_ms"])
+                        ccm.append(st["coop_closest_ms"])
+                        csm.append(st["coop_shadow_ms"])
                 row = {"workload": w, "config": label, "shards": shards, "device_ms": statistics.median(ms), "min_ms": min(ms),
                        "closest_ms": statistics.median(cms), "shadow_ms": statistics.median(sms), "rays": st["rays_total"],
+                       "coop_closest_ms": statistics.median(ccm), "coop_shadow_ms": statistics.median(csm),
+                       "handoff_closest": st["handoff_closest"], "handoff_shadow": st["handoff_shadow"],
                        "mrays_s": st["rays_total"] / statistics.median(ms) / 1e3}
                 rows.append(row)
-                print("%-20s %-22s shards %d  frame %7.3f ms (min %7.3f)  closest %7.3f  shadow %7.3f  %8.1f Mrays/s" %
-                      (w, label, shards, row["device_ms"], row["min_ms"], row["closest_ms"], row["shadow_ms"], row["mrays_s"]), flush=True)
+                print("%-18s %-16s shards %d  frame %7.3f ms (min %7.3f)  closest %6.3f (coop %6.3f, %7d walks)  shadow %6.3f (coop %6.3f, %7d walks)  %8.1f Mrays/s" %
+                      (w, label, shards, row["device_ms"], row["min_ms"], row["closest_ms"], row["coop_closest_ms"], row["handoff_closest"],
+                       row["shadow_ms"], row["coop_shadow_ms"], row["handoff_shadow"], row["mrays_s"]), flush=True)
                 del out
             ctx.close()
     if args.json:
