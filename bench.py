@@ -31,6 +31,7 @@ import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -146,64 +147,51 @@ def algorithmic_bytes(rays: int, node_tests: int, tri_tests: int) -> int:
 # ---------------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation (oracle/_ref) on the host cores
 # ---------------------------------------------------------------------------------------------------------------------
-def run_reference_sample(scene_file, folder, tex, depth, kw, budget_s, repeats, builder):
-    """Picks the largest resolution whose `repeats` renders fit budget_s, runs crt_ref --repeat; returns dict."""
+def run_reference_full(scene_file, folder, tex, depth, repeats, out_prefix="-"):
+    """crt_ref on the FULL frame of the workload's .crtscene, `repeats` renders (tree build untimed, like MEASURE_TIME)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import binding as ob
-    scenes = importlib.import_module(PKG + ".scenes")
     if not ob.have_reference(tex):
         return None
-    W, H = kw["width"], kw["height"]
-    # calibration frame at 1/64 of the pixels (tree build is untimed, like MEASURE_TIME)
-    cands = [(W, H), (W // 2, H // 2), (W // 4, H // 4), (W // 8, H // 8)]
-    cal_kw = dict(kw, width=cands[3][0], height=cands[3][1])
-    cal_path = os.path.join(folder, f"cal_{os.path.basename(scene_file)}")
-    if not os.path.exists(cal_path):
-        scenes.write_crtscene(cal_path, scenes.CONFIGS[builder](**cal_kw))
-    cal = ob.run_reference(os.path.basename(cal_path), folder, "-", textured=tex, depth=depth, hits=False, ppm=False)
-    per_px = cal["render_s"] / (cal_kw["width"] * cal_kw["height"])
-    pick = cands[3]
-    for (w, h) in cands:
-        if per_px * w * h * repeats <= budget_s:
-            pick = (w, h)
-            break
-    if pick == (W, H):
-        path = scene_file
-    else:
-        skw = dict(kw, width=pick[0], height=pick[1])
-        path = f"sample_{pick[0]}x{pick[1]}_{os.path.basename(scene_file)}"
-        if not os.path.exists(os.path.join(folder, path)):
-            scenes.write_crtscene(os.path.join(folder, path), scenes.CONFIGS[builder](**skw))
-    out = ob.run_reference(path, folder, "-", textured=tex, depth=depth, hits=False, ppm=False, repeat=repeats)
-    rays = sum(out["rays"].values())
-    out["rays_total"] = rays
-    out["sample"] = (f"{pick[0]}x{pick[1]} frame of the same scene ({out['triangles']} triangles), oracle/_ref/crt_ref "
-                     f"mode BVHBucketsThreadPool, MEASURE_TIME seconds; KD build {out['build_s']:.1f}s untimed")
+    out = ob.run_reference(scene_file, folder, out_prefix, textured=tex, depth=depth, hits=False, ppm=False, repeat=repeats, timeout=3300.0)
+    out["rays_total"] = sum(out["rays"].values())
+    out["sample"] = (f"{repeats} full {out['width']}x{out['height']} frame(s) of the workload ({out['triangles']} triangles), oracle/_ref/crt_ref "
+                     f"(the unmodified reference), mode BVHBucketsThreadPool on {out['threads']} host threads, MEASURE_TIME seconds; "
+                     f"KD build {out['build_s']:.1f}s untimed")
     return out
 
 
 def reference_arm(args):
+    """The reference's own CPU path on the SAME config as our arm: every step is one full frame of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     scene_file, folder, kw, tex, depth = ensure_scene(args.workload, dict(width=args.width, height=args.height))
-    builder = WORKLOADS[args.workload][0]
-    out = run_reference_sample(scene_file, folder, tex, depth, kw, budget_s=150.0, repeats=args.steps + args.warmup, builder=builder)
-    if out is None:
+    # bounded run: full frames only (never a smaller frame); if K + W frames cannot fit the budget, fewer frames are
+    # timed and the line says how many
+    repeats = args.steps + args.warmup
+    budget = float(os.environ.get("CRT_REFERENCE_BUDGET_S", "1200"))
+    cal = run_reference_full(scene_file, folder, tex, depth, 1)
+    if cal is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/crt_ref not built"}))
         return 0
-    times = out["render_all_s"][args.warmup:]
+    per_frame = cal["render_s"]
+    timed_repeats = max(1, min(repeats, int(budget / max(per_frame, 1e-3))))
+    out = run_reference_full(scene_file, folder, tex, depth, timed_repeats) if timed_repeats > 1 else cal
+    warm = min(args.warmup, max(0, timed_repeats - 1))
+    times = out["render_all_s"][warm:]
     sec = sum(times) / len(times)
     v = out["rays_total"] / sec / 1e6
+    sample = out["sample"] + f"; timed {len(times)} step(s) after {warm} warm-up"
     line = {
         "impl": "reference", "metric": "Mrays/s (primary+secondary)", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "width": kw["width"], "height": kw["height"], "triangles": out["triangles"],
-                   "max_depth": depth, "sample": out["sample"]},
-        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": out["threads"], "kind": "reference", "sample": out["sample"]},
+        "config": {"workload": args.workload, "width": out["width"], "height": out["height"], "triangles": out["triangles"],
+                   "max_depth": depth, "rays_per_step": out["rays_total"], "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": out["threads"], "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "rays_per_step": out["rays_total"],
+        "rays_per_step": out["rays_total"], "steps_timed": len(times),
     }
     print(json.dumps(line))
     return 0
@@ -212,6 +200,128 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
+def source_sha16() -> str:
+    """Hash of the CUDA sources: ties the ncu counters in profiles/ncu_counters.json to the binary that is timed."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("crt_kernels.cuh", "crt_device.cuh", "crtb200_core.cu", "crt_powf5.h"):
+        h.update(open(os.path.join(ROOT, PKG, "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_counters(workload: str, kernel: str):
+    """ncu --set full counters of `kernel` on `workload`, captured from this very source (tools/ncu_counters.py writes
+    the file from the .ncu-rep); None when the capture is of other sources."""
+    p = os.path.join(ROOT, "profiles", "ncu_counters.json")
+    try:
+        d = json.load(open(p))
+    except Exception:
+        return None
+    if d.get("source_sha16") != source_sha16():
+        return None
+    return d.get(workload, {}).get(kernel)
+
+
+def roofline_record(workload, cst, cst2, seq, ms_per_step, W, H):
+    """Dominant traversal launch group (K2 = k_closest + its k_coop, or K3 = k_shadow + its k_coop) against the HBM peak.
+    achieved = DRAM bytes the group really moves (ncu dram__bytes_read + write of the same sources, per frame) / its
+    CUDA-event time measured in THIS run; the SURVEY 8(d) byte model (visit-all and executed) is reported beside it."""
+    peak, peak_src = measured_hbm_peak()
+    c_ms = statistics.mean(s["closest_ms"] for s in seq)
+    s_ms = statistics.mean(s["shadow_ms"] for s in seq)
+    closest_rays = cst["rays_primary"] + cst["rays_reflection"] + cst["rays_refraction"]
+    b_closest = algorithmic_bytes(closest_rays, cst["node_tests_closest"], cst["triangle_tests_closest"])
+    b_shadow = algorithmic_bytes(cst["rays_shadow"], cst["node_tests_shadow"], cst["triangle_tests_shadow"])
+    a_closest = algorithmic_bytes(closest_rays, cst2["node_tests_closest"], cst2["triangle_tests_closest"])
+    a_shadow = algorithmic_bytes(cst2["rays_shadow"], cst2["node_tests_shadow"], cst2["triangle_tests_shadow"])
+    dom = ("k_closest", b_closest, c_ms, a_closest) if c_ms >= s_ms else ("k_shadow", b_shadow, s_ms, a_shadow)
+    ncu = ncu_counters(workload, dom[0])
+    visit_all_gbs = dom[1] / (dom[2] * 1e-3) / 1e9
+    executed_gbs = dom[3] / (dom[2] * 1e-3) / 1e9
+    rec = {"bound": "hbm", "kernel": dom[0], "peak": peak, "unit": "GB/s", "peak_source": peak_src, "kernel_ms": dom[2],
+           "closest_ms": c_ms, "shadow_ms": s_ms, "coop_closest_ms": statistics.mean(s["coop_closest_ms"] for s in seq),
+           "coop_shadow_ms": statistics.mean(s["coop_shadow_ms"] for s in seq),
+           "sequential_frame_ms": statistics.mean(s["device_ms"] for s in seq),
+           "byte_model": {"visit_all_bytes_per_launch": dom[1], "visit_all_gbs": visit_all_gbs, "visit_all_frac": visit_all_gbs / peak,
+                          "executed_bytes_per_launch": dom[3], "executed_gbs": executed_gbs, "executed_frac": executed_gbs / peak,
+                          "note": "SURVEY 8(d): 32 B/AABB test + 52 B/triangle test + 64 B/ray.  visit_all = the reference's visit-all work "
+                                  "(count_work=1); executed = the tests this kernel really performs (any-hit shadow rays, one walk per mesh, "
+                                  "conservative culling: all exact).  These are L1/L2-level logical bytes, not HBM traffic."},
+           "node_tests_per_ray": cst["node_tests"] / max(1, cst["rays_total"]),
+           "triangle_tests_per_ray": cst["triangle_tests"] / max(1, cst["rays_total"]),
+           "executed_node_tests_per_ray": cst2["node_tests"] / max(1, cst2["rays_total"]),
+           "frame_GBps_all_kernels_executed": (a_closest + a_shadow + 12 * W * H) / (ms_per_step * 1e-3) / 1e9}
+    if ncu:
+        achieved = ncu["dram_bytes"] / (dom[2] * 1e-3) / 1e9
+        rec.update({"achieved": achieved, "frac": achieved / peak, "traffic": ncu["dram_bytes"],
+                    "limiter": "L2 latency / issue rate of a dependent pointer chase (not HBM): see l2_hit, issue_slot_util, warp_exec_eff",
+                    "l2_hit": ncu.get("l2_hit"), "l1_hit": ncu.get("l1_hit"), "issue_slot_util": ncu.get("issue_slot_util"),
+                    "warp_exec_eff": ncu.get("warp_exec_eff"), "achieved_occupancy": ncu.get("achieved_occupancy"),
+                    "ncu_source_sha16": source_sha16(), "ncu_kernel_ms": ncu.get("kernel_ms"), "ncu_file": ncu.get("file")})
+    else:
+        rec.update({"achieved": executed_gbs, "frac": executed_gbs / peak, "traffic": None,
+                    "limiter": "no ncu capture of these exact sources is committed: achieved falls back to the executed byte model (logical bytes)"})
+    return rec
+
+
+def config5_record(crt, torch, args, dev):
+    """BASELINE.json config 5 on this GPU: synthetic_10M (10 002 830 triangles, the HBM-streaming regime), 1920x1080 --
+    a static frame, and the 60-frame orbit of app/animation.cpp:24-38 through the batched C-ABI call."""
+    scenes = importlib.import_module(PKG + ".scenes")
+    t0 = time.time()
+    scene_file, folder, kw, tex, depth = ensure_scene("synthetic_10M", {})
+    sf = crt.SceneFile(scene_file, folder)
+    flat = sf.flatten()
+    ctx = crt.Context(dev.index)
+    ctx.upload(flat, keepalive=sf)
+    t_setup = time.time() - t0
+    W, H = sf.info.width, sf.info.height
+    stream = torch.cuda.current_stream().cuda_stream
+    frame = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    opt = crt.make_options(max_depth=depth, traversal=args.traversal)
+    ms = []
+    for k in range(3 + 5):
+        flush.fill_(k)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ctx.render_device(sf.camera(), opt, d_rgb=frame.data_ptr(), stream=stream)
+        b.record()
+        torch.cuda.synchronize()
+        if k >= 3:
+            ms.append(a.elapsed_time(b))
+    st = ctx.last_stats()
+    static = {"ms_per_frame": statistics.mean(ms), "value": st["rays_total"] / (statistics.mean(ms) * 1e-3) / 1e6, "unit": "Mrays/s",
+              "rays_per_frame": st["rays_total"], "frames_timed": len(ms)}
+    F = 60
+    cams = [crt.Camera.make(p, r) for p, r in scenes.orbit_cameras(F, radius=5.12, center_z=-3.0)]
+    rays = 0
+    for cam in cams:  # untimed: ray count of the sequence (also the warm-up)
+        ctx.render_device(cam, opt, d_rgb=frame.data_ptr(), stream=stream)
+        torch.cuda.synchronize()
+        rays += ctx.last_stats()["rays_total"]
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for cam in cams:
+        ctx.render_device(cam, opt, d_rgb=frame.data_ptr(), stream=stream)
+    b.record()
+    torch.cuda.synchronize()
+    seq_ms = a.elapsed_time(b)
+    # e2e: crtb200_render_frames, PPMColor frames into pinned host memory (what exportPPM consumes), copies inside
+    host8 = torch.empty((F, H, W, 3), dtype=torch.uint8).pin_memory()
+    t = time.perf_counter()
+    ctx.render_frames_into(cams, opt, rgb8_out=host8.numpy())
+    e2e_ms = (time.perf_counter() - t) * 1e3
+    orbit = {"frames": F, "ms_per_sequence": seq_ms, "ms_per_frame": seq_ms / F, "value": rays / (seq_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+             "rays_per_sequence": rays,
+             "e2e": {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_sequence": e2e_ms, "ms_per_frame": e2e_ms / F,
+                     "d2h_bytes_per_sequence": F * W * H * 3, "api": "crtb200_render_frames(host cameras -> pinned host PPMColor frames)"}}
+    ctx.close()
+    return {"workload": "synthetic_10M", "width": W, "height": H, "triangles": int(sf.info.n_triangles), "max_depth": depth,
+            "setup_s": t_setup, "static_frame": static, "orbit_60": orbit,
+            "note": "scene working set (~0.6 GB of nodes / references / triangles) exceeds the 126 MB L2: the HBM-streaming regime"}
+
+
 def ours_arm(args):
     import numpy as np
     import torch
@@ -257,80 +367,127 @@ def ours_arm(args):
 
     # one counting pass (untimed): ray counts and visit-all traversal work = the algorithmic bytes; and a few frames
     # with the chunks strictly sequential (concurrency 1) so the per-kernel CUDA-event timers are not inflated by overlap
+    cst = cst2 = None
+    seq = []
     if world == 1:
         _, _, _, cst = ctx.render(cam, crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, count_work=1), want_rgb=False)
-        # and the tests the kernels really execute (exact shortcuts on: any-hit termination of shadow rays, one walk per mesh)
-        _, _, _, cst2 = ctx.render(cam, crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, count_work=2), want_rgb=False)
+        # and the tests the kernels really execute (any-hit shadow rays, one walk per mesh, conservative culling: all exact)
+        _, _, _, cst2 = ctx.render(cam, crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, count_work=2, traversal=args.traversal), want_rgb=False)
         ctx.set_concurrency(1)
-        seq = []
         for k in range(4):
             flush.fill_(k)
             torch.cuda.synchronize()
-            _, _, _, s1 = ctx.render(cam, crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects), want_rgb=False)
+            _, _, _, s1 = ctx.render(cam, crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, traversal=args.traversal), want_rgb=False)
             if k:
                 seq.append(s1)
-        ctx.set_concurrency(args.concurrency)
-    else:
-        cst = None
-        ctx.set_concurrency(args.concurrency)
+    ctx.set_concurrency(args.concurrency)
 
-    frames_mode = world > 1 and args.parallelism == "frames"
+    parallelism = args.parallelism
+    if parallelism == "auto":
+        parallelism = "tiles"  # BASELINE.json config 4: "tile-sharded over 1/2/4/8 GPUs" -- one frame, strong scaling
     opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, traversal=args.traversal)
-    if world > 1 and not frames_mode:
+    sharded = None
+    tiles_check = None
+    if world > 1:
         mg = importlib.import_module(PKG + ".multigpu")
         sharded = mg.ShardedRenderer(crt, ctx, torch, dist, dev)
-    if frames_mode:
-        # frame-parallel ("frames round-robin over GPUs"): per step every rank renders ONE frame of the
-        # sequence (a static-camera sequence here, so per-GPU work equals the N = 1 case) and its PPMColor bytes are
-        # gathered to rank 0 over NCCL, double-buffered so the gather of frame k overlaps the render of frame k + 1.
+        # the assembled N-GPU frame must be bit-equal to the frame one GPU renders alone (rank 0 renders both)
+        sharded.render(cam, max_depth=depth, traversal=args.traversal, frame=frame if rank == 0 else None, frame8=frame8 if rank == 0 else None)
+        torch.cuda.synchronize()
+        if rank == 0:
+            single = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+            single8 = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
+            ctx.render_device(cam, opt, d_rgb=single.data_ptr(), d_rgb8=single8.data_ptr(), stream=stream)
+            torch.cuda.synchronize()
+            neq = ((frame.view(torch.int32) != single.view(torch.int32)) & ~(torch.isnan(frame) & torch.isnan(single))).any(dim=2)
+            tiles_check = {"pixels_differing_from_single_gpu_frame": int(neq.sum().item()), "rgb8_equal": bool(torch.equal(frame8, single8)),
+                           "pixels": W * H}
+            del single, single8
+            if tiles_check["pixels_differing_from_single_gpu_frame"] or not tiles_check["rgb8_equal"]:
+                raise SystemExit(f"[bench] tile-sharded frame differs from the single-GPU frame: {tiles_check}")
+        dist.barrier()
+
+    # frames partition (weak scaling, kept as an extra key at N > 1): every rank renders one frame of a static-camera
+    # sequence per step, PPMColor frames gathered to rank 0 with one NCCL gather, double-buffered
+    bufs8 = gflat = gls = None
+    works = [None, None]
+    if world > 1:
         bufs8 = [torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
         gflat = [torch.zeros((world, H, W, 3), dtype=torch.uint8, device=dev) if rank == 0 else None for _ in range(2)]
         gls = [[gflat[b][i] for i in range(world)] for b in range(2)] if rank == 0 else [None, None]
-        host8 = [torch.empty((world, H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else [None, None]
-        works = [None, None]
     host_frame = torch.empty((H, W, 3), dtype=torch.float32).pin_memory() if (world > 1 and rank == 0) else None
-    copy_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
-    def to_host_async(dst, src):
-        # device -> pinned host on a side stream, so rank 0's copy engine works while its SMs render the next frame
-        copy_stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(copy_stream):
-            dst.copy_(src, non_blocking=True)
+    def step_tiles(to_host=False):
+        sharded.render(cam, max_depth=depth, traversal=args.traversal, frame=frame if rank == 0 else None,
+                       frame8=frame8 if rank == 0 else None)
+        if to_host and rank == 0:
+            host_frame.copy_(frame, non_blocking=True)
 
-    def step(k=0, to_host=False):
-        # to_host (e2e legs, N > 1): the step's result also lands in pinned host memory on rank 0
-        if frames_mode:
-            b = k & 1
+    def step_frames(k):
+        b = k & 1
+        if works[b] is not None:
+            works[b].wait()
+        ctx.render_device(cam, opt, d_rgb=frame.data_ptr(), d_rgb8=bufs8[b].data_ptr(), stream=stream)
+        works[b] = dist.gather(bufs8[b], gls[b], dst=0, async_op=True)
+
+    def drain_frames():
+        for b in range(2):
             if works[b] is not None:
                 works[b].wait()
-                if to_host and rank == 0:
-                    to_host_async(host8[b], gflat[b])
-            ctx.render_device(cam, opt, d_rgb=frame.data_ptr(), d_rgb8=bufs8[b].data_ptr(), stream=stream)
-            if to_host and rank == 0:
-                torch.cuda.current_stream().wait_stream(copy_stream)  # gflat[b] is about to be overwritten by the gather
-            works[b] = dist.gather(bufs8[b], gls[b], dst=0, async_op=True)
-        elif world > 1:
-            sharded.render(cam, max_depth=depth, traversal=args.traversal, frame=frame if rank == 0 else None,
-                           frame8=frame8 if rank == 0 else None)
-            if to_host and rank == 0:
-                host_frame.copy_(frame, non_blocking=True)
-        else:
-            ctx.render_device(cam, opt, d_rgb=frame.data_ptr(), d_rgb8=frame8.data_ptr(), stream=stream)
+                works[b] = None
 
-    def drain(to_host=False):
-        if frames_mode:
-            for b in range(2):
-                if works[b] is not None:
-                    works[b].wait()
-                    if to_host and rank == 0:
-                        to_host_async(host8[b], gflat[b])
-                    works[b] = None
-            if to_host and rank == 0:
-                torch.cuda.current_stream().wait_stream(copy_stream)
+    def step_single():
+        ctx.render_device(cam, opt, d_rgb=frame.data_ptr(), d_rgb8=frame8.data_ptr(), stream=stream)
 
+    tiles_mode = world > 1 and parallelism == "tiles"
+    frames_mode = world > 1 and parallelism == "frames"
+
+    def timed_per_step(step_fn, steps):
+        """flush L2, barrier, event pair per step; returns per-step ms of this rank"""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        st = []
+        for k in range(steps):
+            flush.fill_(k & 0xFF)  # L2 flush (256 MiB > 126 MB L2), outside the timed events
+            if world > 1:
+                dist.barrier()
+            ev[k][0].record()
+            step_fn()
+            ev[k][1].record()
+            torch.cuda.synchronize()
+            st.append(ctx.last_stats())
+        return [a.elapsed_time(b) for a, b in ev], st
+
+    def timed_frames(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        a.record()
+        for k in range(steps):
+            step_frames(k)
+        drain_frames()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    main_step = step_tiles if tiles_mode else (step_single if world == 1 else None)
     for k in range(max(args.warmup, 3)):
-        step(k)
-    drain()
+        if frames_mode:
+            step_frames(k)
+        else:
+            main_step()
+    if frames_mode:
+        drain_frames()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -338,66 +495,43 @@ def ours_arm(args):
     if rank == 0:
         sampler.start()
     torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kstats = []
     if frames_mode:
-        # one event pair around all K steps (the pipelined gathers cross step boundaries); every frame streams ~1 GB of
-        # ray / hit queues through the 126 MB L2, so consecutive frames do not find their inputs cached
-        dist.barrier()
-        ev[0][0].record()
-        for k in range(args.steps):
-            step(k)
-        drain()
-        ev[0][1].record()
-        torch.cuda.synchronize()
-        kstats.append(ctx.last_stats())
-        dist.barrier()
-        step_ms = [ev[0][0].elapsed_time(ev[0][1]) / args.steps] * args.steps
+        per = timed_frames(args.steps)
+        step_ms = [per] * args.steps
+        kstats = [ctx.last_stats()]
     else:
-        for k in range(args.steps):
-            flush.fill_(k & 0xFF)  # L2 flush (256 MiB > 126 MB L2), outside the timed events
-            if world > 1:
-                dist.barrier()
-            ev[k][0].record()
-            step(k)
-            ev[k][1].record()
-            torch.cuda.synchronize()
-            kstats.append(ctx.last_stats())
-        if world > 1:
-            dist.barrier()
-        step_ms = [a.elapsed_time(b) for a, b in ev]
+        step_ms, kstats = timed_per_step(main_step, args.steps)
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+    total_ms = max_over_ranks(sum(step_ms))
+    ms_per_step = total_ms / args.steps
+    # ray count of one step: identical every step; tiles: sum of the shards; frames: the N frames of a step
+    rays_step = sum_over_ranks(kstats[-1]["rays_total"])
+    value = rays_step / (ms_per_step * 1e-3) / 1e6
 
-    # N > 1 end to end: the same K steps, with every step's gathered result copied to pinned host memory on rank 0 inside
-    # the timed region (all ranks take part: the gather is a collective); device events, max over ranks
+    # N > 1 end to end: the same K steps, every step's gathered frame copied to pinned host memory on rank 0 inside the
+    # timed region (all ranks take part: the gather is a collective); device events, max over ranks
     e2e_multi_ms = None
-    if world > 1:
+    frames_extra = None
+    if tiles_mode:
         a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
         torch.cuda.synchronize()
         a.record()
         for k in range(args.steps):
-            step(k, to_host=True)
-        drain(to_host=True)
+            step_tiles(to_host=True)
         b2.record()
         torch.cuda.synchronize()
         dist.barrier()
-        t = torch.tensor([a.elapsed_time(b2)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_multi_ms = float(t.item()) / args.steps
-
-    # ray count of one frame: identical every step; with shards, sum over ranks
-    rays_local = torch.tensor([kstats[-1]["rays_total"]], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(rays_local, op=dist.ReduceOp.SUM)  # tiles: rays of the shards; frames: rays of the N frames of a step
-    rays_frame = int(rays_local.item())
-    ms_per_step = total_ms / args.steps
-    value = rays_frame / (ms_per_step * 1e-3) / 1e6
+        e2e_multi_ms = max_over_ranks(a.elapsed_time(b2)) / args.steps
+        # extra key: the frames partition on the same ranks (weak scaling: N frames per step)
+        for k in range(3):
+            step_frames(k)
+        drain_frames()
+        per = max_over_ranks(timed_frames(args.steps))
+        rays_frames = sum_over_ranks(ctx.last_stats()["rays_total"])
+        frames_extra = {"value": rays_frames / (per * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": per, "scaling": "weak",
+                        "note": f"frames partition: {world} frames per step (one per GPU, static camera), PPMColor frames gathered to rank 0 over NCCL, overlapped"}
 
     if rank != 0:
         if world > 1:
@@ -406,100 +540,72 @@ def ours_arm(args):
         return 0
 
     # ---- e2e through crtb200_render with pinned host buffers (N = 1) / host copy of the gathered frame (N > 1) ----
-    host_rgb = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
-    e2e_ms = []
     if world == 1:
-        e_opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, traversal=args.traversal)
+        host_rgb = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+        e2e_ms = []
         for k in range(args.steps + 1):
             flush.fill_(k & 0xFF)
             torch.cuda.synchronize()
             t = time.perf_counter()
-            ctx.render(cam, e_opt, rgb_out=host_rgb.numpy())
+            ctx.render(cam, opt, rgb_out=host_rgb.numpy())
             dt = (time.perf_counter() - t) * 1e3
             if k:
                 e2e_ms.append(dt)
-        e2e = {"value": rays_frame / (statistics.mean(e2e_ms) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": statistics.mean(e2e_ms),
+        e2e = {"value": rays_step / (statistics.mean(e2e_ms) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": statistics.mean(e2e_ms),
                "h2d_bytes_per_step": 48 + 40 + 16 * n_rects, "d2h_bytes_per_step": W * H * 12,
                "api": "crtb200_render(host camera/options -> pinned host float RGB)"}
+    elif tiles_mode:
+        e2e = {"value": rays_step / (e2e_multi_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_multi_ms,
+               "h2d_bytes_per_step": (48 + 40 + 16 * n_rects) * world, "d2h_bytes_per_step": W * H * 12,
+               "api": "crtb200_render_device shard per rank -> NCCL gather -> crtb200_assemble_shards -> pinned host float RGB on rank 0"}
     else:
-        e2e = {"value": rays_frame / (e2e_multi_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_multi_ms,
-               "h2d_bytes_per_step": (48 + 40 + 16 * n_rects) * world,
-               "d2h_bytes_per_step": (world * W * H * 3) if frames_mode else W * H * 12,
-               "api": ("crtb200_render_device per rank -> NCCL gather of the PPMColor frames -> pinned host memory on rank 0" if frames_mode
-                       else "crtb200_render_device shard per rank -> NCCL gather -> crtb200_assemble_shards -> pinned host float RGB on rank 0")}
+        e2e = None
 
-    peak, peak_src = measured_hbm_peak()
-    roofline = None
-    if cst is not None:
-        c_ms = statistics.mean(s["closest_ms"] for s in seq)
-        s_ms = statistics.mean(s["shadow_ms"] for s in seq)
-        closest_rays = cst["rays_primary"] + cst["rays_reflection"] + cst["rays_refraction"]
-        b_closest = algorithmic_bytes(closest_rays, cst["node_tests_closest"], cst["triangle_tests_closest"])
-        b_shadow = algorithmic_bytes(cst["rays_shadow"], cst["node_tests_shadow"], cst["triangle_tests_shadow"])
-        a_closest = algorithmic_bytes(closest_rays, cst2["node_tests_closest"], cst2["triangle_tests_closest"])
-        a_shadow = algorithmic_bytes(cst2["rays_shadow"], cst2["node_tests_shadow"], cst2["triangle_tests_shadow"])
-        dom = ("k_closest", b_closest, c_ms, a_closest) if c_ms >= s_ms else ("k_shadow_accumulate", b_shadow, s_ms, a_shadow)
-        achieved = dom[1] / (dom[2] * 1e-3) / 1e9
-        actual = dom[3] / (dom[2] * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(args.workload, {}).get(dom[0])
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[1], "kernel_ms": dom[2],
-                    "achieved_actual": actual, "frac_actual": actual / peak, "executed_bytes_per_launch": dom[3],
-                    "note": ("achieved = the reference's visit-all work (SURVEY 8(d) byte model) / kernel time; achieved_actual = the tests "
-                             "this kernel executes (shadow rays stop at the first occluder, a mesh is walked once per ray: both exact). "
-                             "traffic (ncu DRAM bytes) is far below either when the scene is L2-resident: the kernel is then L2-latency / "
-                             "issue bound, not HBM bound, and frac can exceed 1"),
-                    "closest_ms": c_ms, "shadow_ms": s_ms, "sequential_frame_ms": statistics.mean(s["device_ms"] for s in seq), "closest_bytes": b_closest, "shadow_bytes": b_shadow,
-                    "frame_GBps_all_kernels": (b_closest + b_shadow + 12 * W * H) / (ms_per_step * 1e-3) / 1e9,
-                    "node_tests_per_ray": (cst["node_tests"]) / max(1, cst["rays_total"]),
-                    "triangle_tests_per_ray": (cst["triangle_tests"]) / max(1, cst["rays_total"])}
+    roofline = roofline_record(args.workload, cst, cst2, seq, ms_per_step, W, H) if cst is not None else None
 
-    # opt-in culled traversal (mode 1), reported beside the exact headline together with its pixel difference to it
-    culled = None
+    literal = None
     if world == 1 and args.traversal == 0:
+        # the reference's literal visit-all itinerary (traversal = 1) beside the default, and their pixel difference (0)
         try:
             ex = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
-            cu = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+            li = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
             ctx.render_device(cam, opt, d_rgb=ex.data_ptr(), stream=stream)
-            c_opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, traversal=1)
+            l_opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, traversal=1)
             for _ in range(3):
-                ctx.render_device(cam, c_opt, d_rgb=cu.data_ptr(), stream=stream)
-            cms = []
-            for k in range(args.steps):
+                ctx.render_device(cam, l_opt, d_rgb=li.data_ptr(), stream=stream)
+            lms = []
+            for k in range(min(args.steps, 5)):
                 flush.fill_(k & 0xFF)
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                ctx.render_device(cam, c_opt, d_rgb=cu.data_ptr(), stream=stream)
+                ctx.render_device(cam, l_opt, d_rgb=li.data_ptr(), stream=stream)
                 b.record()
                 torch.cuda.synchronize()
-                cms.append(a.elapsed_time(b))
-            diff = ((ex.view(torch.int32) != cu.view(torch.int32)) & ~(torch.isnan(ex) & torch.isnan(cu))).any(dim=2)
-            culled = {"value": rays_frame / (statistics.mean(cms) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": statistics.mean(cms),
-                      "pixels_differing_from_exact": int(diff.sum().item()), "pixels": W * H,
-                      "note": "traversal=1: subtrees wholly behind the origin / beyond the best hit are skipped; not the headline"}
-            del ex, cu
+                lms.append(a.elapsed_time(b))
+            diff = ((ex.view(torch.int32) != li.view(torch.int32)) & ~(torch.isnan(ex) & torch.isnan(li))).any(dim=2)
+            literal = {"value": rays_step / (statistics.mean(lms) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": statistics.mean(lms),
+                       "pixels_differing_from_default": int(diff.sum().item()), "pixels": W * H,
+                       "note": "traversal=1: the reference's visit-all itinerary with no culling and no hand-off (round-1 default)"}
+            del ex, li
         except Exception as e:
-            culled = {"error": str(e)}
+            literal = {"error": str(e)}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            builder = WORKLOADS[args.workload][0]
-            ref = run_reference_sample(scene_file, folder, tex, depth, kw, budget_s=25.0, repeats=1, builder=builder)
-            if ref is not None:
-                cpu_baseline = {"value": ref["rays_total"] / ref["render_s"] / 1e6, "unit": "Mrays/s", "cores": ref["threads"],
-                                "kind": "reference", "sample": ref["sample"], "seconds": ref["render_s"]}
-            else:
+            with tempfile.TemporaryDirectory() as td:
+                ref = run_reference_full(scene_file, folder, tex, depth, 1, out_prefix=os.path.join(td, "ref"))
+                if ref is not None:
+                    ours = host_rgb.numpy()
+                    same = (ours.view(np.uint32) == ref["rgb"].view(np.uint32)) | (np.isnan(ours) & np.isnan(ref["rgb"]))
+                    cpu_baseline = {"value": ref["rays_total"] / ref["render_s"] / 1e6, "unit": "Mrays/s", "cores": ref["threads"],
+                                    "kind": "reference", "sample": ref["sample"], "seconds": ref["render_s"],
+                                    "rays": ref["rays_total"], "rays_equal_ours": bool(ref["rays_total"] == rays_step),
+                                    "pixels_differing_from_ours": int((~same).any(axis=2).sum()), "pixels": W * H}
+            if cpu_baseline is None:
                 sys.path.insert(0, os.path.join(ROOT, "oracle"))
                 import binding as ob
-                # bounded sample for the port: the top-left 1/16 of the frame's bucket grid
-                nb = max(1, n_rects // 16)
+                nb = max(1, n_rects // 16)  # bounded sample for the port: 1/16 of the frame's bucket grid
                 t = time.perf_counter()
                 _, _, ost = ob.render(flat, cam, crt.make_options(max_depth=depth, rects=rects, n_rects=nb), want_hits=False)
                 dt = time.perf_counter() - t
@@ -508,19 +614,30 @@ def ours_arm(args):
         except Exception as e:  # the baseline is a report, never a reason to lose the bench line
             cpu_baseline = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
 
-    launches = (kstats[-1]["kernel_launches"] + (1 if (world > 1 and not frames_mode) else 0)) * (world if frames_mode else 1)
+    config5 = None
+    if world == 1 and not args.no_config5:
+        try:
+            ctx.close()
+            del frame, frame8
+            config5 = config5_record(crt, torch, args, dev)
+        except Exception as e:
+            config5 = {"error": str(e)}
+
+    per_frame_launches = kstats[-1]["kernel_launches"]
+    launches = (per_frame_launches + (1 if tiles_mode else 0)) * (world if frames_mode else 1)
     line = {
         "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak" if (frames_mode or world == 1) else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "width": W, "height": H, "triangles": int(sf.info.n_triangles), "max_depth": depth,
-                   "traversal": "exact (reference visit-all order)" if args.traversal == 0 else "fast (ordered+culled)",
+                   "traversal": ("default: conservative culling + tail hand-off (results identical to the reference)" if args.traversal == 0
+                                 else "literal visit-all itinerary"),
                    "parallelism": (f"frames{world}: one frame per GPU per step, rgb8 gathered to rank 0 (NCCL, overlapped)" if frames_mode
-                                   else f"tiles{world}: 8x4 tiles round-robin, float slabs gathered to rank 0" if world > 1 else "single"),
+                                   else f"tiles{world}: one frame, 8x4 tiles round-robin over {world} GPUs, float slabs gathered to rank 0 (NCCL) and assembled" if world > 1 else "single"),
                    "l2": ("each frame streams ~1 GB of queues through the 126 MB L2 (inputs larger than L2)" if frames_mode
                           else "flushed between steps (256 MiB fill)"),
-                   "rays_per_step": rays_frame, "chunks_in_flight": args.concurrency},
+                   "rays_per_step": rays_step, "chunks_in_flight": args.concurrency},
         "clocks": clocks, "gpu_launches": launches * args.steps, "step_ms": step_ms,
     }
     if e2e:
@@ -529,8 +646,14 @@ def ours_arm(args):
         line["roofline"] = roofline
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
-    if culled:
-        line["culled_mode"] = culled
+    if literal:
+        line["literal_walk"] = literal
+    if tiles_check:
+        line["tiles_check"] = tiles_check
+    if frames_extra:
+        line["frames_mode"] = frames_extra
+    if config5:
+        line["config5"] = config5
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -688,8 +811,9 @@ def main():
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--traversal", type=int, default=0)
-    ap.add_argument("--parallelism", default="frames", choices=["frames", "tiles"],
-                    help="N > 1: frames = one frame per GPU per step (weak scaling); tiles = one frame split by tiles (strong)")
+    ap.add_argument("--parallelism", default="auto", choices=["auto", "frames", "tiles"],
+                    help="N > 1: tiles (default) = one frame split by 8x4 tiles (strong scaling, config 4); frames = one frame per GPU per step (weak)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the synthetic_10M sub-record (N = 1)")
     ap.add_argument("--concurrency", type=int, default=6, help="chunks of a frame in flight on separate streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--animation", type=int, default=0, help="F > 0: a step is the F-frame orbit animation (config 5), frames round-robin over GPUs")

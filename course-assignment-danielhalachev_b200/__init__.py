@@ -155,6 +155,10 @@ def core() -> C.CDLL:
         lib.crtb200_render_frames.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_uint32, C.POINTER(Options), C.c_void_p, C.c_void_p, C.POINTER(Stats)]
         lib.crtb200_upload_scene.argtypes = [C.c_void_p, C.POINTER(Scene)]
         lib.crtb200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        lib.crtb200_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        lib.crtb200_device_list.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+        lib.crtb200_last_error_ctx.argtypes = [C.c_void_p]
+        lib.crtb200_last_error_ctx.restype = C.c_char_p
         lib.crtb200_destroy.argtypes = [C.c_void_p]
         lib.crtb200_set_queue_budget.argtypes = [C.c_void_p, C.c_uint64]
         lib.crtb200_set_concurrency.argtypes = [C.c_void_p, C.c_uint32]
@@ -292,11 +296,27 @@ def make_options(max_depth: int = 5, rects=None, n_rects: int = 0, traversal: in
 class Context:
     """One GPU context of libcrtb200 (RayTracer's device-side state)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: one CUDA device index, or a sequence of them (crtb200_create_multi: every frame is split by tiles
+        over the GPUs, the scene is replicated, results are identical to a single GPU's)."""
         self._h = C.c_void_p()
-        _check_core(core().crtb200_create(device, C.byref(self._h)))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            _check_core(core().crtb200_create_multi(ids, len(device), C.byref(self._h)))
+        else:
+            _check_core(core().crtb200_create(int(device), C.byref(self._h)))
         self.width = self.height = 0
         self._scene_keepalive = None
+
+    def devices(self):
+        n = C.c_int(0)
+        _check_core(core().crtb200_device_list(self._h, None, 0, C.byref(n)))
+        ids = (C.c_int * n.value)()
+        _check_core(core().crtb200_device_list(self._h, ids, n.value, C.byref(n)))
+        return list(ids)
+
+    def last_error(self) -> str:
+        return core().crtb200_last_error_ctx(self._h).decode(errors="replace")
 
     def upload(self, scene_ptr, keepalive=None) -> None:
         _check_core(core().crtb200_upload_scene(self._h, scene_ptr))
@@ -334,6 +354,17 @@ class Context:
                                                  rgb.ctypes.data if rgb is not None else None,
                                                  rgb8.ctypes.data if rgb8 is not None else None, C.byref(st)))
         return rgb, rgb8, st.as_dict()
+
+    def render_frames_into(self, cameras: Sequence[Camera], options: Options, rgb_out: Optional[np.ndarray] = None,
+                           rgb8_out: Optional[np.ndarray] = None) -> dict:
+        """crtb200_render_frames into caller-owned (ideally pinned) host arrays of shape (n, H, W, 3)."""
+        n = len(cameras)
+        arr = (Camera * n)(*cameras)
+        st = Stats()
+        _check_core(core().crtb200_render_frames(self._h, arr, n, C.byref(options),
+                                                 rgb_out.ctypes.data if rgb_out is not None else None,
+                                                 rgb8_out.ctypes.data if rgb8_out is not None else None, C.byref(st)))
+        return st.as_dict()
 
     def render_device(self, camera: Camera, options: Options, d_rgb: int = 0, d_rgb8: int = 0, stream: int = 0) -> None:
         """Asynchronous; d_rgb / d_rgb8 are raw device pointers (e.g. torch.Tensor.data_ptr())."""
@@ -392,7 +423,8 @@ class RayTracer:
     """Python view of the C++ `crt::RayTracer` mirror class (csrc/frontend/crt_raytracer.hpp):
     RayTracer(scene) -> setCamera -> render(pathToImage, mode, maxDepth)."""
 
-    def __init__(self, scene: SceneFile, device: int = 0):
+    def __init__(self, scene: SceneFile, device: int = -1):
+        """device >= 0: that GPU; -1 (default, like the C++ class): every visible GPU, each frame split by tiles."""
         self.scene = scene
         self._h = C.c_void_p()
         _check_front(front().crtfe_tracer_create(scene.handle, device, C.byref(self._h)))
@@ -405,11 +437,11 @@ class RayTracer:
         _check_front(front().crtfe_tracer_get_camera(self._h, C.byref(cam)))
         return cam
 
-    def render(self, path_to_image: str = "", mode: int = MODE_B200_WAVEFRONT, max_depth: int = 5, fast: bool = False):
+    def render(self, path_to_image: str = "", mode: int = MODE_B200_WAVEFRONT, max_depth: int = 5, literal: bool = False):
         h, w = self.scene.info.height, self.scene.info.width
         rgb = np.zeros((h, w, 3), np.float32)
         st = Stats()
-        _check_front(front().crtfe_tracer_render(self._h, path_to_image.encode(), mode, max_depth, 1 if fast else 0,
+        _check_front(front().crtfe_tracer_render(self._h, path_to_image.encode(), mode, max_depth, 1 if literal else 0,
                                                  rgb.ctypes.data, C.byref(st)))
         return rgb, st.as_dict()
 

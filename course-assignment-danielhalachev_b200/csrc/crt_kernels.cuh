@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K2b / K3b: k_coop -- one WARP per handed-off walk (records written by tail_handoff).
+// K2b / K3b: k_coop -- a GROUP of lanes per handed-off walk (records written by tail_handoff).
 //
 // Why any order is allowed.  The reference's child boxes are the exact halves of the parent box (BoundingBox.h:60-69: one
 // plane replaced by min + (max - min) / 2, which lies in [min, max] in binary32) and BoundingBox::hasIntersection is
@@ -770,15 +770,27 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
 //                 t < +inf and (b) the candidate with the smallest key, and folds them into the ray's running Closest
 //                 exactly as the in-order sequence of closest_offer calls would have.
 //
-// The walk.  The warp keeps a LIFO of node indices in shared memory.  One iteration pops up to 32 nodes, one per lane;
-// a lane loads its node, drops it when its whole subtree lies before the hand-off cursor (already walked), tests the
-// box (node_test: the reference's slab test + the conservative culling of crt_device.cuh), and pushes both children of
-// a passing inner node (first child = index + 1, second child = the node's `b` word).  The passing leaves of an
-// iteration are tested together, their triangle lists packed 32 slots at a time like tri_phase.  After a 5-iteration
-// ramp a ray's walk advances 32 boxes per iteration instead of one.
+// The walk.  A group of GW lanes (8 by default: four walks per warp) keeps a LIFO of node indices in shared memory.
+// One iteration pops up to GW nodes, one per lane; a lane loads its node, drops it when its whole subtree lies before
+// the hand-off cursor (already walked), tests the box (node_test: the reference's slab test + the conservative culling
+// of crt_device.cuh) and pushes both children of a passing inner node (first child = index + 1, second child = the
+// node's `b` word).  The passing leaves of an iteration are tested together, their triangle lists packed GW slots at a
+// time like tri_phase.  One iteration costs about two dependent memory round trips whatever its width, and a single
+// ray's frontier is rarely wider than a dozen nodes (a walk's critical path is the tree's depth), so a whole warp per
+// walk left most lanes idle: groups of 8 run four walks side by side at the same latency (measured: profiles/r2_tuning.md).
+// Every group runs the same loop; group-uniform branches use the group's own lane mask for their shuffles and votes.
 // ------------------------------------------------------------------------------------------------------------
-#define CRT_COOP_CAP 512    // LIFO entries per warp (2 KB)
+#define CRT_COOP_CAP 512    // LIFO entries per warp (2 KB), shared out between its groups
 #define CRT_COOP_WARPS 4    // warps per CTA
+#ifndef CRT_COOP_MIN_BLOCKS
+#define CRT_COOP_MIN_BLOCKS 6  // resident CTAs per SM the register allocation is bounded for (24 warps = 96 walks per SM)
+#endif
+#ifndef CRT_COOP_STATS
+#define CRT_COOP_STATS 0  // debug builds (tools/): iterations, box tests and triangle tests of k_coop into stats[34..39]
+#endif
+#ifndef CRT_COOP_GROUP
+#define CRT_COOP_GROUP 8    // lanes per walk
+#endif
 struct __align__(16) WarpCoop {
   uint32_t stack[CRT_COOP_CAP];
   uint32_t refbase[32], owner[32], leafidx[32];
@@ -794,129 +806,30 @@ struct CoopBest {            // per-lane partial result of one mesh walk (closes
 };
 #define CRT_KEY_NONE 0xFFFFFFFFFFFFFFFFull
 
-// Walks the nodes of mesh tree [root, end) that lie at or after `from` (visiting order) with the whole warp.
-// SHADOW: returns true as soon as a candidate within `dist` is found.  CLOSEST: candidates go to cb; `lim` (warp-uniform)
-// is the best finite t known so far and tightens as the walk finds closer candidates.
-template <bool SHADOW, bool CULL>
-CRT_DI bool coop_walk(const DScene &sc, WarpCoop &wc, const Ray &ray, const float dist, const uint32_t root, const uint32_t from,
-                      const float mu, float &lim, CoopBest &cb) {
-  const uint32_t lane = lane_id();
-  uint32_t sp = 1;
-  if (lane == 0) wc.stack[0] = root;
-  __syncwarp();
-  while (sp) {
-    // pop up to 32 entries; close to capacity fall back to one at a time (then the LIFO grows by at most one entry per step)
-    const uint32_t n = (CRT_COOP_CAP - sp < 72u) ? 1u : (sp < 32u ? sp : 32u);
-    const bool have = lane < n;
-    uint32_t j = 0;
-    if (have) j = wc.stack[sp - 1u - lane];
-    sp -= n;
-    __syncwarp();
-    bool leaf_hit = false;
-    uint32_t a = 0, b = CRT_INVALID, cnt = 0;
-    if (have) {
-      const float4 lo = __ldg(&sc.nodes[2 * (size_t)j]), hi = __ldg(&sc.nodes[2 * (size_t)j + 1]);
-      a = __float_as_uint(lo.w);
-      b = __float_as_uint(hi.w);
-      const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
-      const uint32_t endj = leaf ? j + 1u : a;
-      if (endj > from && node_test<CULL>(lo, hi, ray, mu, lim, SHADOW || lim < CRT_INF)) {
-        leaf_hit = leaf;
-        if (!leaf) cnt = (b != CRT_INVALID) ? 2u : 1u;
-      }
-    }
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t v = __shfl_up_sync(CRT_FULL_MASK, incl, d);
-      if (lane >= (uint32_t)d) incl += v;
-    }
-    const uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
-    uint32_t at = sp + incl - cnt;
-    if (cnt == 2u) wc.stack[at++] = b;   // second child below the first: the first child's subtree is taken first
-    if (cnt) wc.stack[at] = j + 1u;
-    sp += total;
-    __syncwarp();
-    // triangles of the leaves that passed in this iteration, packed across the warp (cf. tri_phase)
-    if (__any_sync(CRT_FULL_MASK, leaf_hit)) {
-      const uint32_t tcnt = leaf_hit ? (a & ~CRT_LEAF_FLAG) : 0u;
-      uint32_t tincl = tcnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(CRT_FULL_MASK, tincl, d);
-        if (lane >= (uint32_t)d) tincl += v;
-      }
-      const uint32_t ttotal = __shfl_sync(CRT_FULL_MASK, tincl, 31);
-      const uint32_t tstart = tincl - tcnt;
-      if (tcnt) {
-        wc.refbase[lane] = b - tstart;
-        wc.leafidx[lane] = j;
-      }
-      for (uint32_t base = 0; base < ttotal; base += 32u) {
-        const bool in_win = tcnt && tstart < base + 32u && tstart + tcnt > base;
-        const uint32_t hp = (in_win && tstart > base) ? tstart - base : 0u;
-        const uint32_t heads = __reduce_or_sync(CRT_FULL_MASK, in_win ? (1u << hp) : 0u);
-        if (in_win) wc.owner[hp] = lane;
-        __syncwarp();
-        const uint32_t g = base + lane;
-        bool hit = false;
-        float t = 0.0f;
-        if (g < ttotal) {
-          const uint32_t own = wc.owner[31 - __clz(heads & (CRT_FULL_MASK >> (31u - lane)))];
-          const uint32_t ref = wc.refbase[own] + g;
-          const uint32_t tri = __ldg(&sc.leaf_refs[ref]);
-          const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
-          const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
-          const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
-          V3 p;
-          hit = triangle_test(g0, g1, g2, ray, t, p);
-          if (SHADOW) {
-            hit = hit && vlen(vsub(p, ray.o)) <= dist;
-          } else if (hit) {
-            const unsigned long long key = ((unsigned long long)wc.leafidx[own] << 32) | ref;
-            if (key < cb.fkey) {
-              cb.fkey = key;
-              cb.ft = t;
-              cb.ftri = tri;
-            }
-            if (t < CRT_INF && (t < cb.t || (t == cb.t && key < cb.key))) {
-              cb.t = t;
-              cb.key = key;
-              cb.tri = tri;
-            }
-          }
-        }
-        if (SHADOW) {
-          if (__any_sync(CRT_FULL_MASK, hit)) return true;
-        } else if (CULL) {
-          // tighten the culling limit: smallest finite t of this window (t >= 0, so the int order is the float order; -0.0
-          // sorts first, which is still a correct bound)
-          const int m = __reduce_min_sync(CRT_FULL_MASK, (hit && t < CRT_INF) ? __float_as_int(t) : 0x7f800000);
-          const float tm = __int_as_float(m);
-          if (tm < lim) lim = tm;
-        }
-        __syncwarp();
-      }
-    }
-  }
-  return false;
+CRT_DI void coop_best_reset(CoopBest &cb) {
+  cb.t = CRT_INF;
+  cb.key = cb.fkey = CRT_KEY_NONE;
+  cb.tri = cb.ftri = CRT_INVALID;
+  cb.ft = 0.0f;
 }
 
-// fold the lanes' partial results of one mesh walk into the ray's running Closest (all lanes end with the same cl)
-CRT_DI void coop_fold(CoopBest &cb, Closest &cl) {
+// fold the lanes' partial results of one mesh walk into the ray's running Closest (all lanes of the group end with the
+// same cl); gm = the group's lane mask
+template <int GW>
+CRT_DI void coop_fold(const uint32_t gm, CoopBest &cb, Closest &cl) {
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    const float t = __shfl_xor_sync(CRT_FULL_MASK, cb.t, d);
-    const unsigned long long key = __shfl_xor_sync(CRT_FULL_MASK, cb.key, d);
-    const uint32_t tri = __shfl_xor_sync(CRT_FULL_MASK, cb.tri, d);
+  for (int d = GW / 2; d > 0; d >>= 1) {
+    const float t = __shfl_xor_sync(gm, cb.t, d);
+    const unsigned long long key = __shfl_xor_sync(gm, cb.key, d);
+    const uint32_t tri = __shfl_xor_sync(gm, cb.tri, d);
     if (t < cb.t || (t == cb.t && key < cb.key)) {
       cb.t = t;
       cb.key = key;
       cb.tri = tri;
     }
-    const unsigned long long fkey = __shfl_xor_sync(CRT_FULL_MASK, cb.fkey, d);
-    const float ft = __shfl_xor_sync(CRT_FULL_MASK, cb.ft, d);
-    const uint32_t ftri = __shfl_xor_sync(CRT_FULL_MASK, cb.ftri, d);
+    const unsigned long long fkey = __shfl_xor_sync(gm, cb.fkey, d);
+    const float ft = __shfl_xor_sync(gm, cb.ft, d);
+    const uint32_t ftri = __shfl_xor_sync(gm, cb.ftri, d);
     if (fkey < cb.fkey) {
       cb.fkey = fkey;
       cb.ft = ft;
@@ -936,78 +849,109 @@ CRT_DI void coop_fold(CoopBest &cb, Closest &cl) {
   }
 }
 
-template <bool SHADOW, bool PRIMARY, bool CULL>
-__global__ void __launch_bounds__(32 * CRT_COOP_WARPS) k_coop(const DScene sc, const Frame fr, const Levels lv, const uint32_t level) {
+template <bool SHADOW, bool PRIMARY, bool CULL, int GW>
+__global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_coop(const DScene sc, const Frame fr, const Levels lv, const uint32_t level) {
+  constexpr uint32_t NG = 32u / GW;            // walks per warp
+  constexpr uint32_t CAP = CRT_COOP_CAP / NG;  // LIFO entries per walk
+  static_assert(GW == 8 || GW == 16 || GW == 32, "group width");
   __shared__ WarpCoop s_wc[CRT_COOP_WARPS];
   WarpCoop &wc = s_wc[threadIdx.x >> 5];
-  const uint32_t lane = lane_id();
+  const uint32_t lane = lane_id(), gl = lane & (GW - 1u), g0 = lane & ~(GW - 1u);
+  const uint32_t gm = (GW == 32 ? CRT_FULL_MASK : ((1u << GW) - 1u)) << g0;  // lanes of this group
+  uint32_t *const stack = wc.stack + (g0 / GW) * CAP;
+  uint32_t *const refbase = wc.refbase + g0, *const owner = wc.owner + g0, *const leafidx = wc.leafidx + g0;
   const uint32_t launch = SHADOW ? (uint32_t)CRT_MAX_LEVELS : level;
   const uint32_t n_rec = min(lv.ovf_ctl[2u * launch], lv.ovf_cap);
   if (blockIdx.x == 0 && threadIdx.x == 0 && n_rec) atomicAdd(&lv.stats[SHADOW ? 33 : 32], (unsigned long long)n_rec);
+
+  // group state: identical in all lanes of a group, except cb (per-lane partial results)
+  bool busy = false, drained = false, in_mesh = false, occluded = false;
+  uint32_t id = 0, sp = 0, from = 0;
+  uint32_t cur = 0, cend = 0, resume = 0, mref = 0, mend = 0, below = 0;
+  unsigned long long seen = 0ull;
+  float dist = 0.0f, mu = CRT_INF, lim = CRT_INF;
+  Ray ray;
+  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
+  ray.flags = 0;
+  Closest cl;
+  closest_begin(cl);
+  CoopBest cb;
+  coop_best_reset(cb);
+
+#if CRT_COOP_STATS
+  unsigned long long dbg_iters = 0, dbg_nodes = 0, dbg_tris = 0;
+#endif
   for (;;) {
-    uint32_t r = 0;
-    if (lane == 0) r = atomicAdd(&lv.ovf_ctl[2u * launch + 1u], 1u);
-    r = __shfl_sync(CRT_FULL_MASK, r, 0);
-    if (r >= n_rec) break;
-    const uint4 r0 = lv.ovf[3 * (size_t)r], r1 = lv.ovf[3 * (size_t)r + 1], r2 = lv.ovf[3 * (size_t)r + 2];
-    const uint32_t id = r0.x;
-    Ray ray;
-    float dist = 0.0f;
-    if (SHADOW) {
-      const uint32_t hit = id / sc.n_lights, light = id - hit * sc.n_lights;
-      const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
-      float contrib;
-      shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
-    } else if (PRIMARY) {
-      uint32_t row, col;
-      item_pixel(fr, sc, fr.item_begin + (id - lv.offset[0]), row, col);  // valid: the main kernel started this ray
-      primary_ray(fr.cam, sc.width, sc.height, row, col, ray.o, ray.d);
-    } else {
-      const float4 o = lv.ray_o[id - lv.offset[1]], d = lv.ray_d[id - lv.offset[1]];
-      ray.o = mk(o.x, o.y, o.z);
-      ray.d = mk(d.x, d.y, d.z);
+    // ---- 1. an idle group takes the next record ----
+    if (!busy && !drained) {
+      uint32_t r = 0;
+      if (gl == 0) r = atomicAdd(&lv.ovf_ctl[2u * launch + 1u], 1u);
+      r = __shfl_sync(gm, r, 0, GW);
+      if (r >= n_rec) {
+        drained = true;
+      } else {
+        const uint4 r0 = lv.ovf[3 * (size_t)r], r1 = lv.ovf[3 * (size_t)r + 1], r2 = lv.ovf[3 * (size_t)r + 2];
+        id = r0.x;
+        if (SHADOW) {
+          const uint32_t hit = id / sc.n_lights, light = id - hit * sc.n_lights;
+          const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
+          float contrib;
+          shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
+        } else if (PRIMARY) {
+          uint32_t row, col;
+          item_pixel(fr, sc, fr.item_begin + (id - lv.offset[0]), row, col);  // valid: the main kernel started this ray
+          primary_ray(fr.cam, sc.width, sc.height, row, col, ray.o, ray.d);
+        } else {
+          const float4 o = lv.ray_o[id - lv.offset[1]], d = lv.ray_d[id - lv.offset[1]];
+          ray.o = mk(o.x, o.y, o.z);
+          ray.d = mk(d.x, d.y, d.z);
+        }
+        ray_prepare(ray, PRIMARY);
+        // the walk's state where the main kernel left it
+        cur = r0.y;
+        cend = r0.z;
+        resume = r0.w;
+        mref = r1.x;
+        mend = r1.y;
+        seen = (unsigned long long)r1.z | ((unsigned long long)r1.w << 32);
+        below = r2.x;
+        mu = __uint_as_float(r2.y);
+        cl.best_t = __uint_as_float(r2.z);
+        cl.best_tri = r2.w;
+        cl.min_t = (cl.best_tri != CRT_INVALID && cl.best_t < CRT_INF) ? cl.best_t : CRT_INF;
+        lim = SHADOW ? shadow_limit(ray, dist) : cl.min_t;
+        occluded = false;
+        in_mesh = false;
+        busy = true;
+      }
     }
-    ray_prepare(ray, PRIMARY);
-    // the walk's state where the main kernel left it (all warp-uniform from here on)
-    uint32_t cur = r0.y, cend = r0.z, resume = r0.w, mref = r1.x, mend = r1.y, below = r2.x;
-    unsigned long long seen = (unsigned long long)r1.z | ((unsigned long long)r1.w << 32);
-    float mu = __uint_as_float(r2.y);
-    Closest cl;
-    cl.best_t = __uint_as_float(r2.z);
-    cl.best_tri = r2.w;
-    cl.min_t = (cl.best_tri != CRT_INVALID && cl.best_t < CRT_INF) ? cl.best_t : CRT_INF;
-    float lim = SHADOW ? shadow_limit(ray, dist) : cl.min_t;
-    bool occluded = false;
-    for (;;) {
+    if (!__any_sync(CRT_FULL_MASK, busy)) break;  // idle groups have just found the record list empty
+
+    // ---- 2. between mesh walks: one step of the ray's itinerary (trav_step's order of events, per group) ----
+    if (busy && !in_mesh) {
       if (cur < cend) {
         if (below) {
-          // the rest of a mesh tree: [cur, cend) of the tree whose range contains cur
+          // (the rest of) a mesh tree: start at the root of the tree whose node range contains cur; subtrees that end at
+          // or before cur are dropped by the walk
           uint32_t root = CRT_INVALID;
-          for (uint32_t m0 = 0; root == CRT_INVALID; m0 += 32u) {  // cur lies in exactly one mesh's node range
-            const uint32_t m = m0 + lane;
+          for (uint32_t m0 = 0; m0 < sc.n_meshes && root == CRT_INVALID; m0 += GW) {
+            const uint32_t m = m0 + gl;
             uint32_t nb = CRT_INVALID;
             if (m < sc.n_meshes) {
               const DMesh me = sc.meshes[m];
               if (cur >= me.node_begin && cur < me.node_end) nb = me.node_begin;
             }
-            root = __reduce_min_sync(CRT_FULL_MASK, nb);
-            if (m0 + 32u >= sc.n_meshes) break;
+            root = __reduce_min_sync(gm, nb);
           }
-          if (root != CRT_INVALID) {
-            CoopBest cb;
-            cb.t = CRT_INF;
-            cb.key = cb.fkey = CRT_KEY_NONE;
-            cb.tri = cb.ftri = CRT_INVALID;
-            cb.ft = 0.0f;
-            occluded = coop_walk<SHADOW, CULL>(sc, wc, ray, dist, root, cur, mu, lim, cb);
-            if (SHADOW) {
-              if (occluded) break;
-            } else {
-              coop_fold(cb, cl);
-              lim = cl.min_t;
-            }
-          }
+          from = cur;
           cur = cend;
+          coop_best_reset(cb);
+          if (root != CRT_INVALID) {
+            if (gl == 0) stack[0] = root;
+            sp = 1u;
+            in_mesh = true;
+            __syncwarp(gm);
+          }
         } else {
           // one step in the top-level tree (a handful of nodes: every lane does the same step; never culled)
           const float4 lo = __ldg(&sc.nodes[2 * (size_t)cur]), hi = __ldg(&sc.nodes[2 * (size_t)cur + 1]);
@@ -1023,9 +967,7 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS) k_coop(const DScene sc, c
             below = 1u;
           }
         }
-        continue;
-      }
-      if (mref != mend) {
+      } else if (mref != mend) {
         const uint32_t m = __ldg(&sc.top_refs[mref++]);
         const DMesh me = sc.meshes[m];
         bool skip = SHADOW && sc.materials[me.material].type == 3u;  // shadow rays ignore refractive meshes (AccelerationStructure.cpp:67-71)
@@ -1039,22 +981,148 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS) k_coop(const DScene sc, c
           cend = me.node_end;
           mu = CULL ? cull_margin_for(ray, me.cull_margin) : CRT_INF;
         }
-        continue;
-      }
-      if (!below) break;
-      below = 0u;
-      cur = resume;
-      cend = sc.top_end;
-    }
-    if (lane == 0) {
-      if (SHADOW) {
-        lv.vis[id] = occluded ? 0 : 1;
+      } else if (below) {
+        below = 0u;
+        cur = resume;
+        cend = sc.top_end;
       } else {
-        lv.hit_tri[id] = cl.best_tri;
-        lv.hit_t[id] = cl.best_t;
+        // itinerary complete
+        if (gl == 0) {
+          if (SHADOW) {
+            lv.vis[id] = 1;
+          } else {
+            lv.hit_tri[id] = cl.best_tri;
+            lv.hit_t[id] = cl.best_t;
+          }
+        }
+        busy = false;
+      }
+    }
+
+    // ---- 3. one iteration of the mesh walk ----
+    if (busy && in_mesh) {
+      // pop up to GW entries; close to capacity fall back to one at a time (then the LIFO grows by at most one per step)
+      const uint32_t n = (CAP - sp < 2u * GW + 40u) ? 1u : (sp < GW ? sp : GW);
+      const bool have = gl < n;
+      uint32_t j = 0;
+      if (have) j = stack[sp - 1u - gl];
+      sp -= n;
+      __syncwarp(gm);
+#if CRT_COOP_STATS
+      if (gl == 0) dbg_iters++;
+      if (have) dbg_nodes++;
+#endif
+      bool leaf_hit = false;
+      uint32_t a = 0, b = CRT_INVALID, cnt = 0;
+      if (have) {
+        const float4 lo = __ldg(&sc.nodes[2 * (size_t)j]), hi = __ldg(&sc.nodes[2 * (size_t)j + 1]);
+        a = __float_as_uint(lo.w);
+        b = __float_as_uint(hi.w);
+        const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
+        const uint32_t endj = leaf ? j + 1u : a;
+        if (endj > from && node_test<CULL>(lo, hi, ray, mu, lim, SHADOW || lim < CRT_INF)) {
+          leaf_hit = leaf;
+          if (!leaf) cnt = (b != CRT_INVALID) ? 2u : 1u;
+        }
+      }
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int d = 1; d < GW; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(gm, incl, d, GW);
+        if (gl >= (uint32_t)d) incl += v;
+      }
+      const uint32_t total = __shfl_sync(gm, incl, GW - 1, GW);
+      uint32_t at = sp + incl - cnt;
+      if (cnt == 2u) stack[at++] = b;  // second child below the first: the first child's subtree is taken first
+      if (cnt) stack[at] = j + 1u;
+      sp += total;
+      __syncwarp(gm);
+      // triangles of the leaves that passed in this iteration, packed across the group (cf. tri_phase)
+      if (__ballot_sync(gm, leaf_hit)) {
+        const uint32_t tcnt = leaf_hit ? (a & ~CRT_LEAF_FLAG) : 0u;
+        uint32_t tincl = tcnt;
+#pragma unroll
+        for (int d = 1; d < GW; d <<= 1) {
+          const uint32_t v = __shfl_up_sync(gm, tincl, d, GW);
+          if (gl >= (uint32_t)d) tincl += v;
+        }
+        const uint32_t ttotal = __shfl_sync(gm, tincl, GW - 1, GW);
+        const uint32_t tstart = tincl - tcnt;
+        if (tcnt) {
+          refbase[gl] = b - tstart;
+          leafidx[gl] = j;
+        }
+        for (uint32_t base = 0; base < ttotal; base += GW) {
+          const bool in_win = tcnt && tstart < base + GW && tstart + tcnt > base;
+          const uint32_t hp = (in_win && tstart > base) ? tstart - base : 0u;
+          const uint32_t heads = __reduce_or_sync(gm, in_win ? (1u << hp) : 0u);
+          if (in_win) owner[hp] = gl;
+          __syncwarp(gm);
+          const uint32_t slot = base + gl;
+          bool hit = false;
+          float t = 0.0f;
+          if (slot < ttotal) {
+#if CRT_COOP_STATS
+            dbg_tris++;
+#endif
+            const uint32_t own = owner[31 - __clz(heads & (CRT_FULL_MASK >> (31u - gl)))];  // slot 0 of a window is always a head
+            const uint32_t ref = refbase[own] + slot;
+            const uint32_t tri = __ldg(&sc.leaf_refs[ref]);
+            const float4 t0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
+            const float4 t1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
+            const float4 t2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+            V3 p;
+            hit = triangle_test(t0, t1, t2, ray, t, p);
+            if (SHADOW) {
+              hit = hit && vlen(vsub(p, ray.o)) <= dist;
+            } else if (hit) {
+              const unsigned long long key = ((unsigned long long)leafidx[own] << 32) | ref;
+              if (key < cb.fkey) {
+                cb.fkey = key;
+                cb.ft = t;
+                cb.ftri = tri;
+              }
+              if (t < CRT_INF && (t < cb.t || (t == cb.t && key < cb.key))) {
+                cb.t = t;
+                cb.key = key;
+                cb.tri = tri;
+              }
+            }
+          }
+          if (SHADOW) {
+            if (__ballot_sync(gm, hit)) {
+              occluded = true;
+              break;
+            }
+          } else if (CULL) {
+            // tighten the culling limit: smallest finite t of this window (t >= 0, so the int order is the float order;
+            // -0.0 sorts first, which is still a correct bound)
+            const int m = __reduce_min_sync(gm, (hit && t < CRT_INF) ? __float_as_int(t) : 0x7f800000);
+            const float tm = __int_as_float(m);
+            if (tm < lim) lim = tm;
+          }
+          __syncwarp(gm);
+        }
+      }
+      if (SHADOW && occluded) {  // the first occluder ends the record
+        if (gl == 0) lv.vis[id] = 0;
+        busy = false;
+        in_mesh = false;
+        __syncwarp(gm);
+      } else if (sp == 0u) {     // mesh walk complete
+        if (!SHADOW) {
+          coop_fold<GW>(gm, cb, cl);
+          lim = cl.min_t;
+        }
+        in_mesh = false;
       }
     }
   }
+#if CRT_COOP_STATS
+  atomicAdd(&lv.stats[SHADOW ? 37 : 34], dbg_iters);
+  atomicAdd(&lv.stats[SHADOW ? 38 : 35], dbg_nodes);
+  atomicAdd(&lv.stats[SHADOW ? 39 : 36], dbg_tris);
+#endif
 }
 
 // K3b: the light loop of RayTracer::calculateDiffusion (RayTracer.cpp:308-330): per diffuse hit, walk the lights IN

@@ -5,6 +5,11 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -25,11 +30,62 @@ using namespace crtd;
 #define CRT_LOOP_MODE 2  // 0 = while-while, 1 = merged loop, 2 = node phase + warp-cooperative triangle phase (crt_kernels.cuh)
 #endif
 
+struct crtb200_ctx;
 static thread_local std::string g_error;
+static thread_local crtb200_ctx *g_error_ctx = nullptr;  // context of the ABI call running on this thread (ErrScope)
+static void note_ctx_error(crtb200_ctx *c, const std::string &msg);
 static int fail(int code, const std::string &msg) {
   g_error = msg;
+  if (g_error_ctx) note_ctx_error(g_error_ctx, msg);
   return code;
 }
+struct ErrScope {
+  crtb200_ctx *prev;
+  explicit ErrScope(crtb200_ctx *c) : prev(g_error_ctx) { g_error_ctx = c; }
+  ~ErrScope() { g_error_ctx = prev; }
+};
+
+// One helper thread per peer GPU of a multi-GPU context: launches are asynchronous, but issuing a frame's ~20 launches
+// takes the host ~0.1 ms per GPU, which eight GPUs cannot afford serially when a shard renders in ~0.5 ms.
+struct Worker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<void()> job;
+  bool has = false, quit = false;
+  Worker() {
+    th = std::thread([this] {
+      std::unique_lock<std::mutex> lk(m);
+      for (;;) {
+        cv.wait(lk, [this] { return has || quit; });
+        if (quit) return;
+        lk.unlock();
+        job();
+        lk.lock();
+        has = false;
+        cv.notify_all();
+      }
+    });
+  }
+  void post(std::function<void()> f) {
+    std::unique_lock<std::mutex> lk(m);
+    job = std::move(f);
+    has = true;
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [this] { return !has; });
+  }
+  ~Worker() {
+    {
+      std::unique_lock<std::mutex> lk(m);
+      quit = true;
+      cv.notify_all();
+    }
+    th.join();
+  }
+};
 #define CUDA_TRY(expr)                                                                                       \
   do {                                                                                                       \
     cudaError_t e_ = (expr);                                                                                 \
@@ -107,6 +163,12 @@ struct crtb200_ctx {
   // frame
   DevBuf<float> frame;   // persistent colour buffer (RayTracer::colorBuffer, RayTracer.h:69)
   DevBuf<uint8_t> frame8;
+  // crtb200_render_frames: frames alternate between (frame, frame8) and (frame_b, frame8_b); the device->host copy of
+  // frame f runs on copy_stream while frame f + 1 is rendered into the other pair
+  DevBuf<float> frame_b;
+  DevBuf<uint8_t> frame8_b;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
   DevBuf<HitRec> hits;
   DevBuf<uint8_t> mask;
   std::vector<crtb200_rect> mask_rects;
@@ -142,7 +204,19 @@ struct crtb200_ctx {
   int blocks_closest = 0, blocks_shadow = 0, blocks_coop = 0;
   crtb200_stats last{};
   bool last_pending = false;
+
+  // multi-GPU (crtb200_create_multi): this context is the primary (device_ids[0]).  A frame's 8x4-pixel tiles are dealt
+  // round-robin over primary + peers (scene replicated); every GPU's k_store writes its pixels STRAIGHT into the
+  // primary's frame buffers through peer-mapped pointers (NVLink / NVSwitch), so no slab, gather or assemble pass exists.
+  std::vector<crtb200_ctx *> peers;
+  std::vector<std::unique_ptr<Worker>> workers;
+  std::vector<int> worker_rc;
+  std::vector<std::string> worker_msg;
+  cudaEvent_t multi_fork = nullptr;  // primary stream position the peers must wait for before touching the frame
+  cudaEvent_t multi_done = nullptr;  // (on a peer) its shard is stored
+  std::string error;                 // last error of a call on this context (crtb200_last_error_ctx)
 };
+static void note_ctx_error(crtb200_ctx *c, const std::string &msg) { c->error = msg; }
 
 extern "C" {
 
@@ -185,7 +259,7 @@ int crtb200_create(int device, crtb200_ctx **out) {
   c->blocks_closest = std::max(1, occ) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_coop<true, false, true>, 32 * CRT_COOP_WARPS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_coop<true, false, true, CRT_COOP_GROUP>, 32 * CRT_COOP_WARPS, 0);
   c->blocks_coop = std::max(1, occ) * c->sm_count;
   if (const char *env = getenv("CRT_BLOCKS_PER_SM")) {  // tuning only (tools/): resident persistent CTAs per SM
     const int b = atoi(env);
@@ -204,14 +278,80 @@ int crtb200_create(int device, crtb200_ctx **out) {
   return CRTB200_OK;
 }
 
+const char *crtb200_last_error_ctx(const crtb200_ctx *c) { return c ? c->error.c_str() : g_error.c_str(); }
+
+int crtb200_create_multi(const int *device_ids, int n, crtb200_ctx **out) {
+  if (!out) return fail(CRTB200_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!device_ids || n < 1 || n > 64) return fail(CRTB200_ERR_ARG, "device list is null or its length is not in 1..64");
+  crtb200_ctx *c = nullptr;
+  int rc = crtb200_create(device_ids[0], &c);
+  if (rc) return rc;
+  for (int i = 1; i < n; i++) {
+    crtb200_ctx *p = nullptr;
+    rc = crtb200_create(device_ids[i], &p);
+    if (rc == CRTB200_OK && p->device != c->device) {
+      // the peer's kernels store into the primary's frame: map the primary's memory into the peer's address space
+      int can = 0;
+      cudaSetDevice(p->device);
+      cudaError_t e = cudaDeviceCanAccessPeer(&can, p->device, c->device);
+      if (e == cudaSuccess && !can) e = cudaErrorPeerAccessUnsupported;
+      if (e == cudaSuccess) e = cudaDeviceEnablePeerAccess(c->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        e = cudaSuccess;
+      }
+      if (e != cudaSuccess)
+        rc = fail(CRTB200_ERR_CUDA, std::string("peer access from device ") + std::to_string(p->device) + " to device " +
+                                        std::to_string(c->device) + ": " + cudaGetErrorString(e));
+    }
+    if (rc == CRTB200_OK && cudaEventCreateWithFlags(&p->multi_done, cudaEventDisableTiming) != cudaSuccess)
+      rc = fail(CRTB200_ERR_CUDA, "cudaEventCreate failed");
+    if (rc) {
+      if (p) crtb200_destroy(p);
+      crtb200_destroy(c);
+      return rc;
+    }
+    c->peers.push_back(p);
+    c->workers.emplace_back(new Worker());
+  }
+  c->worker_rc.assign(c->peers.size(), 0);
+  c->worker_msg.assign(c->peers.size(), std::string());
+  cudaSetDevice(c->device);
+  if (!c->peers.empty() && cudaEventCreateWithFlags(&c->multi_fork, cudaEventDisableTiming) != cudaSuccess) {
+    crtb200_destroy(c);
+    return fail(CRTB200_ERR_CUDA, "cudaEventCreate failed");
+  }
+  *out = c;
+  return CRTB200_OK;
+}
+
+int crtb200_device_list(const crtb200_ctx *c, int *device_ids, int capacity, int *count) {
+  if (!c || !count) return fail(CRTB200_ERR_ARG, "null argument");
+  *count = 1 + (int)c->peers.size();
+  if (device_ids)
+    for (int i = 0; i < capacity && i < *count; i++) device_ids[i] = i == 0 ? c->device : c->peers[i - 1]->device;
+  return CRTB200_OK;
+}
+
 int crtb200_destroy(crtb200_ctx *c) {
   if (!c) return CRTB200_OK;
+  c->workers.clear();  // joins the helper threads
+  for (crtb200_ctx *p : c->peers) crtb200_destroy(p);
+  c->peers.clear();
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->multi_fork) cudaEventDestroy(c->multi_fork);
+  if (c->multi_done) cudaEventDestroy(c->multi_done);
   c->arena.release(); c->vtx_normal.release(); c->top_refs.release();
   c->tri_shade.release(); c->vtx_uv.release(); c->meshes.release(); c->materials.release(); c->textures.release();
   c->texels.release(); c->lights.release(); c->frame.release(); c->frame8.release(); c->hits.release();
-  c->mask.release();
+  c->mask.release(); c->frame_b.release(); c->frame8_b.release();
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (int k = 0; k < 2; k++) {
+    if (c->rendered[k]) cudaEventDestroy(c->rendered[k]);
+    if (c->copied[k]) cudaEventDestroy(c->copied[k]);
+  }
   for (auto &q : c->sets) {
     q.release();
     if (q.stream) cudaStreamDestroy(q.stream);
@@ -228,18 +368,22 @@ int crtb200_destroy(crtb200_ctx *c) {
 }
 
 int crtb200_set_concurrency(crtb200_ctx *c, uint32_t chunks_in_flight) {
+  ErrScope scope(c);
   if (!c) return fail(CRTB200_ERR_ARG, "ctx is null");
   if (chunks_in_flight < 1 || chunks_in_flight > 16) return fail(CRTB200_ERR_ARG, "concurrency must be 1..16");
   c->concurrency = chunks_in_flight;
   c->cap_items = 0;
+  for (crtb200_ctx *p : c->peers) crtb200_set_concurrency(p, chunks_in_flight);
   return CRTB200_OK;
 }
 
 int crtb200_set_queue_budget(crtb200_ctx *c, uint64_t bytes) {
+  ErrScope scope(c);
   if (!c) return fail(CRTB200_ERR_ARG, "ctx is null");
   if (bytes < (64ull << 20)) return fail(CRTB200_ERR_ARG, "queue budget must be at least 64 MiB");
   c->queue_budget = bytes;
   c->cap_items = 0;
+  for (crtb200_ctx *p : c->peers) crtb200_set_queue_budget(p, bytes);
   return CRTB200_OK;
 }
 
@@ -391,8 +535,41 @@ static float mesh_cull_margin(const crtb200_scene *s, const crtb200_mesh &me, bo
   return (std::isfinite(mu) && mu < 1e30) ? (float)(mu * (1.0 + 1e-6)) : inf;
 }
 
+}  // extern "C"
+
+static int upload_one(crtb200_ctx *c, const crtb200_scene *s);
+
+// runs fn(peer index, peer) on every peer's helper thread and fn0 on the calling thread; first error wins
+template <typename F0, typename F>
+static int on_all_devices(crtb200_ctx *c, F0 fn0, F fn) {
+  for (size_t i = 0; i < c->peers.size(); i++) {
+    c->workers[i]->post([c, i, &fn] {
+      ErrScope scope(c->peers[i]);
+      c->worker_rc[i] = fn(i, c->peers[i]);
+      c->worker_msg[i] = c->worker_rc[i] ? g_error : std::string();
+    });
+  }
+  int rc = fn0();
+  for (size_t i = 0; i < c->peers.size(); i++) {
+    c->workers[i]->wait();
+    if (rc == CRTB200_OK && c->worker_rc[i]) rc = fail(c->worker_rc[i], "device " + std::to_string(c->peers[i]->device) + ": " + c->worker_msg[i]);
+  }
+  return rc;
+}
+
+extern "C" {
+
 int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   if (!c || !s) return fail(CRTB200_ERR_ARG, "null argument");
+  ErrScope scope(c);
+  if (c->peers.empty()) return upload_one(c, s);
+  // scene replicated on every GPU; the host relayout runs once per GPU, in parallel
+  return on_all_devices(c, [&] { return upload_one(c, s); }, [&](size_t, crtb200_ctx *p) { return upload_one(p, s); });
+}
+
+}  // extern "C"
+
+static int upload_one(crtb200_ctx *c, const crtb200_scene *s) {
   if (s->abi_version != CRTB200_ABI_VERSION) return fail(CRTB200_ERR_ARG, "crtb200_scene.abi_version mismatch");
   if (s->width == 0 || s->height == 0) return fail(CRTB200_ERR_SCENE, "image size is zero");
   if ((uint64_t)s->width * s->height > 0x7FFFFFFFull / 4) return fail(CRTB200_ERR_SCENE, "image too large");
@@ -446,7 +623,7 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
     uint32_t depth = 0;
     if (!relayout_tree(s->mesh_nodes + me.first_node, me.n_nodes, node_cursor, me.first_leaf_ref, me.n_leaf_refs, nodes, err, &depth))
       return fail(CRTB200_ERR_SCENE, err);
-    if (depth > 64) nested_ok = false;  // k_coop's LIFO is sized for trees up to this deep (the reference's limit is far below)
+    if (depth > 40) nested_ok = false;  // k_coop's LIFOs are sized for trees up to this deep (the reference's limit is 26 levels)
     const uint32_t placed = (uint32_t)(nodes.size() / 2 - before);
     meshes[m].node_begin = node_cursor;
     meshes[m].node_end = node_cursor + placed;
@@ -585,8 +762,6 @@ int crtb200_upload_scene(crtb200_ctx *c, const crtb200_scene *s) {
   c->have_scene = true;
   return CRTB200_OK;
 }
-
-}  // extern "C"
 
 // ---- frame planning ------------------------------------------------------------------------------------------
 static uint32_t branching_sum(const crtb200_ctx *c, uint32_t max_depth, uint64_t *per_level) {
@@ -755,9 +930,9 @@ static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const 
 template <bool CULL>
 static void launch_coop_closest(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, cudaStream_t st) {
   if (primary)
-    k_coop<false, true, CULL><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
+    k_coop<false, true, CULL, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
   else
-    k_coop<false, false, CULL><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
+    k_coop<false, false, CULL, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
 }
 
 // Host destinations of crtb200_render: each chunk's band of rows is copied back on the chunk's own stream right after
@@ -771,7 +946,7 @@ struct HostOut {
 // Enqueue one frame on `st`.  d_rgb / d_rgb8 / d_hits / d_slab are device pointers (any may be null).
 static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_options *o, float *d_rgb,
                          uint8_t *d_rgb8, HitRec *d_hits, float *d_slab, cudaStream_t st, bool timed,
-                         const HostOut *host = nullptr, bool *host_done = nullptr) {
+                         const HostOut *host = nullptr, bool *host_done = nullptr, bool batch_continuation = false) {
   if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
   if (o->max_depth > 31) return fail(CRTB200_ERR_ARG, "max_depth > 31 is not supported");
   if (o->n_rects && !o->rects) return fail(CRTB200_ERR_ARG, "n_rects > 0 but rects is null");
@@ -814,18 +989,19 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   if (host_done) *host_done = band_copies;
   const int grid_simple = c->sm_count * 8;
 
-  CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 40 * sizeof(unsigned long long), st));
+  // frames after the first of a batch (crtb200_render_frames) keep accumulating into the same counters and time span
+  if (!batch_continuation) CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 40 * sizeof(unsigned long long), st));
 #if CRT_PHASE_CLOCKS
   CUDA_TRY(cudaMemsetAsync(c->stats_dev.p + 27, 0xFF, sizeof(unsigned long long), st));  // atomicMin slots
   CUDA_TRY(cudaMemsetAsync(c->stats_dev.p + 31, 0xFF, sizeof(unsigned long long), st));
 #endif
   c->kev_used = 0;
   c->kev_kind.clear();
-  if (timed) CUDA_TRY(cudaEventRecord(c->ev[0], st));
+  if (timed && !batch_continuation) CUDA_TRY(cudaEventRecord(c->ev[0], st));
   // fork: every set's stream waits for the caller's stream, chunks go round-robin, the caller's stream joins at the end.
   // Per-kernel event pairs are only recorded without concurrency (overlapping kernels would inflate each other).
   const uint32_t n_sets = c->cap_sets;
-  const bool per_kernel = timed && n_sets == 1;
+  const bool per_kernel = timed && n_sets == 1 && !batch_continuation;
   CUDA_TRY(cudaEventRecord(c->fork_ev, st));
   for (uint32_t k = 0; k < n_sets; k++) CUDA_TRY(cudaStreamWaitEvent(c->sets[k].stream, c->fork_ev, 0));
   uint32_t launches = 0, chunk = 0;
@@ -887,9 +1063,9 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
         c->kev_kind.push_back(3);
       }
       if (cull)
-        k_coop<true, false, true><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, qs>>>(c->sc, fr, q.lv, 0);
+        k_coop<true, false, true, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, qs>>>(c->sc, fr, q.lv, 0);
       else
-        k_coop<true, false, false><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, qs>>>(c->sc, fr, q.lv, 0);
+        k_coop<true, false, false, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, qs>>>(c->sc, fr, q.lv, 0);
       launches++;
     }
     if (per_kernel) cudaEventRecord(next_event(c), qs);
@@ -921,7 +1097,71 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   return CRTB200_OK;
 }
 
+// Multi-GPU frame (crtb200_create_multi): shard i of n goes to GPU i; every GPU stores into the SAME destination
+// buffers (device memory of the primary, peer-mapped on the others).  The peers start after `st` has reached this point
+// (earlier consumers of the frame on the primary's stream are done) and `st` continues after every peer has stored.
+static int enqueue_any(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_options *o, float *d_rgb, uint8_t *d_rgb8,
+                       HitRec *d_hits, float *d_slab, cudaStream_t st, bool timed, const HostOut *host = nullptr,
+                       bool *host_done = nullptr, bool batch_continuation = false) {
+  if (c->peers.empty() || o->shard_count > 1)
+    return enqueue_frame(c, cam, o, d_rgb, d_rgb8, d_hits, d_slab, st, timed, host, host_done, batch_continuation);
+  if (host_done) *host_done = false;  // the caller copies the assembled frame after the join
+  const uint32_t n = 1u + (uint32_t)c->peers.size();
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaEventRecord(c->multi_fork, st));
+  crtb200_options o0 = *o;
+  o0.shard_index = 0;
+  o0.shard_count = n;
+  int rc = on_all_devices(
+      c, [&] { return enqueue_frame(c, cam, &o0, d_rgb, d_rgb8, d_hits, nullptr, st, timed, nullptr, nullptr, batch_continuation); },
+      [&](size_t i, crtb200_ctx *p) {
+        crtb200_options oi = *o;
+        oi.shard_index = (uint32_t)i + 1u;
+        oi.shard_count = n;
+        CUDA_TRY(cudaSetDevice(p->device));
+        CUDA_TRY(cudaStreamWaitEvent(p->stream, c->multi_fork, 0));
+        int r = enqueue_frame(p, cam, &oi, d_rgb, d_rgb8, d_hits, nullptr, p->stream, true, nullptr, nullptr, batch_continuation);
+        if (r) return r;
+        p->last_pending = true;
+        CUDA_TRY(cudaEventRecord(p->multi_done, p->stream));
+        return (int)CRTB200_OK;
+      });
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (rc) return rc;
+  for (crtb200_ctx *p : c->peers) CUDA_TRY(cudaStreamWaitEvent(st, p->multi_done, 0));
+  if (timed) CUDA_TRY(cudaEventRecord(c->ev[1], st));  // the frame ends when the last GPU has stored its shard
+  return CRTB200_OK;
+}
+
+static int collect_stats_one(crtb200_ctx *c, bool timed);
+// counters of the primary plus those of the peers (rays, tests, launches); times are the primary's (fork to join)
 static int collect_stats(crtb200_ctx *c, bool timed) {
+  int rc = collect_stats_one(c, timed);
+  if (rc) return rc;
+  for (crtb200_ctx *p : c->peers) {
+    if (!p->last_pending) continue;
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    rc = collect_stats_one(p, false);
+    p->last_pending = false;
+    if (rc) return rc;
+    c->last.rays_primary += p->last.rays_primary;
+    c->last.rays_shadow += p->last.rays_shadow;
+    c->last.rays_reflection += p->last.rays_reflection;
+    c->last.rays_refraction += p->last.rays_refraction;
+    c->last.node_tests_closest += p->last.node_tests_closest;
+    c->last.triangle_tests_closest += p->last.triangle_tests_closest;
+    c->last.node_tests_shadow += p->last.node_tests_shadow;
+    c->last.triangle_tests_shadow += p->last.triangle_tests_shadow;
+    c->last.handoff_closest += p->last.handoff_closest;
+    c->last.handoff_shadow += p->last.handoff_shadow;
+    c->last.kernel_launches += p->last.kernel_launches;
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  return CRTB200_OK;
+}
+
+static int collect_stats_one(crtb200_ctx *c, bool timed) {
   unsigned long long st[40];
   CUDA_TRY(cudaMemcpy(st, c->stats_dev.p, sizeof(st), cudaMemcpyDeviceToHost));
 #if CRT_PHASE_CLOCKS
@@ -978,6 +1218,10 @@ static int collect_stats(crtb200_ctx *c, bool timed) {
   c->last.triangle_tests_shadow = st[7];
   c->last.handoff_closest = st[32];
   c->last.handoff_shadow = st[33];
+#if CRT_COOP_STATS
+  fprintf(stderr, "[coop stats] closest: %llu walks, %llu iterations, %llu box tests, %llu triangle tests | shadow: %llu walks, %llu iterations, %llu box tests, %llu triangle tests\n",
+          st[32], st[34], st[35], st[36], st[33], st[37], st[38], st[39]);
+#endif
   if (timed) {
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
@@ -1000,6 +1244,7 @@ extern "C" {
 
 int crtb200_render(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_options *o, float *rgb_out,
                    uint8_t *rgb8_out, crtb200_hit *hits_out, crtb200_stats *stats) {
+  ErrScope scope(c);
   if (!c || !cam || !o) return fail(CRTB200_ERR_ARG, "null argument");
   const auto t0 = std::chrono::steady_clock::now();
   CUDA_TRY(cudaSetDevice(c->device));
@@ -1019,8 +1264,8 @@ int crtb200_render(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_opti
   if (rc) return rc;
   const bool want_bands = !shard && !c->mask_needed && (rgb_out || rgb8_out || hits_out);
   bool banded = false;
-  rc = enqueue_frame(c, cam, o, c->frame.p, rgb8_out ? c->frame8.p : nullptr, hits_out ? c->hits.p : nullptr, nullptr,
-                     c->stream, true, want_bands ? &host : nullptr, &banded);
+  rc = enqueue_any(c, cam, o, c->frame.p, rgb8_out ? c->frame8.p : nullptr, hits_out ? c->hits.p : nullptr, nullptr,
+                   c->stream, true, want_bands ? &host : nullptr, &banded);
   if (rc) return rc;
   if (!banded) {
     if (rgb_out) CUDA_TRY(cudaMemcpyAsync(rgb_out, c->frame.p, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1035,39 +1280,92 @@ int crtb200_render(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_opti
   return CRTB200_OK;
 }
 
+static void add_stats(crtb200_stats &total, const crtb200_stats &s) {
+  total.rays_primary += s.rays_primary;
+  total.rays_shadow += s.rays_shadow;
+  total.rays_reflection += s.rays_reflection;
+  total.rays_refraction += s.rays_refraction;
+  total.node_tests_closest += s.node_tests_closest;
+  total.triangle_tests_closest += s.triangle_tests_closest;
+  total.node_tests_shadow += s.node_tests_shadow;
+  total.triangle_tests_shadow += s.triangle_tests_shadow;
+  total.handoff_closest += s.handoff_closest;
+  total.handoff_shadow += s.handoff_shadow;
+  total.device_ms += s.device_ms;
+  total.closest_ms += s.closest_ms;
+  total.shadow_ms += s.shadow_ms;
+  total.coop_closest_ms += s.coop_closest_ms;
+  total.coop_shadow_ms += s.coop_shadow_ms;
+  total.kernel_launches += s.kernel_launches;
+  total.levels = s.levels;
+}
+
+// The animation loop of app/animation.cpp:24-38 (setCamera + render per frame), batched and pipelined: no host
+// synchronisation between frames, two frames in flight -- frame f + 1 is rendered while frame f's pixels travel to the
+// host on a copy stream.  Rectangle lists that leave pixels uncovered need colorBuffer persistence from frame to frame
+// (one buffer, in order), and tile shards write no full frame: those take the frame-by-frame path.
 int crtb200_render_frames(crtb200_ctx *c, const crtb200_camera *cams, uint32_t n_frames, const crtb200_options *o,
                           float *rgb_out, uint8_t *rgb8_out, crtb200_stats *stats) {
+  ErrScope scope(c);
   if (!c || !cams || !o) return fail(CRTB200_ERR_ARG, "null argument");
   if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
+  CUDA_TRY(cudaSetDevice(c->device));
   const size_t px = (size_t)c->sc.width * c->sc.height;
-  crtb200_stats total{};
   const auto t0 = std::chrono::steady_clock::now();
-  for (uint32_t f = 0; f < n_frames; f++) {
-    crtb200_stats s{};
-    int rc = crtb200_render(c, cams + f, o, rgb_out ? rgb_out + f * px * 3 : nullptr, rgb8_out ? rgb8_out + f * px * 3 : nullptr,
-                            nullptr, &s);
-    if (rc) return rc;
-    total.rays_primary += s.rays_primary;
-    total.rays_shadow += s.rays_shadow;
-    total.rays_reflection += s.rays_reflection;
-    total.rays_refraction += s.rays_refraction;
-    total.node_tests_closest += s.node_tests_closest;
-    total.triangle_tests_closest += s.triangle_tests_closest;
-    total.node_tests_shadow += s.node_tests_shadow;
-    total.triangle_tests_shadow += s.triangle_tests_shadow;
-    total.device_ms += s.device_ms;
-    total.closest_ms += s.closest_ms;
-    total.shadow_ms += s.shadow_ms;
-    total.kernel_launches += s.kernel_launches;
-    total.levels = s.levels;
+  int rc = plan_mask(c, o);
+  if (rc) return rc;
+  if (c->mask_needed || o->shard_count > 1 || o->count_work != 0 || n_frames < 2) {
+    crtb200_stats total{};
+    for (uint32_t f = 0; f < n_frames; f++) {
+      crtb200_stats s{};
+      rc = crtb200_render(c, cams + f, o, rgb_out ? rgb_out + f * px * 3 : nullptr, rgb8_out ? rgb8_out + f * px * 3 : nullptr, nullptr, &s);
+      if (rc) return rc;
+      add_stats(total, s);
+    }
+    total.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = total;
+    return CRTB200_OK;
   }
-  total.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  if (stats) *stats = total;
+  CUDA_TRY(c->frame_b.ensure(px * 3));
+  if (rgb8_out) CUDA_TRY(c->frame8_b.ensure(px * 3));
+  if (!c->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; k++) {
+    if (!c->rendered[k]) CUDA_TRY(cudaEventCreateWithFlags(&c->rendered[k], cudaEventDisableTiming));
+    if (!c->copied[k]) CUDA_TRY(cudaEventCreateWithFlags(&c->copied[k], cudaEventDisableTiming));
+  }
+  c->last = crtb200_stats{};
+  uint32_t launches = 0;
+  for (uint32_t f = 0; f < n_frames; f++) {
+    const int k = (int)(f & 1u);
+    float *d_rgb = k ? c->frame_b.p : c->frame.p;
+    uint8_t *d_rgb8 = rgb8_out ? (k ? c->frame8_b.p : c->frame8.p) : nullptr;
+    if (f >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->copied[k], 0));  // this pair's previous frame has left the device
+    rc = enqueue_any(c, cams + f, o, d_rgb, d_rgb8, nullptr, nullptr, c->stream, true, nullptr, nullptr, f > 0);
+    if (rc) return rc;
+    launches += c->last.kernel_launches;
+    CUDA_TRY(cudaEventRecord(c->rendered[k], c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->rendered[k], 0));
+    if (rgb_out) CUDA_TRY(cudaMemcpyAsync(rgb_out + f * px * 3, d_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (rgb8_out) CUDA_TRY(cudaMemcpyAsync(rgb8_out + f * px * 3, d_rgb8, px * 3, cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_TRY(cudaEventRecord(c->copied[k], c->copy_stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+  if ((n_frames & 1u) == 0u) {  // the last frame went into the second pair: it is the persistent colour buffer now
+    std::swap(c->frame, c->frame_b);
+    std::swap(c->frame8, c->frame8_b);
+  }
+  rc = collect_stats(c, true);
+  if (rc) return rc;
+  c->last.kernel_launches = launches;
+  c->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) *stats = c->last;
   return CRTB200_OK;
 }
 
 int crtb200_render_device(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_options *o, float *d_rgb_out,
                           uint8_t *d_rgb8_out, void *stream) {
+  ErrScope scope(c);
   if (!c || !cam || !o) return fail(CRTB200_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(c->device));
   const uint32_t shard_count = o->shard_count ? o->shard_count : 1;
@@ -1078,10 +1376,11 @@ int crtb200_render_device(crtb200_ctx *c, const crtb200_camera *cam, const crtb2
     if (d_rgb8_out) return fail(CRTB200_ERR_ARG, "sharded rendering writes a float slab only");
     return enqueue_frame(c, cam, o, nullptr, nullptr, nullptr, d_rgb_out, (cudaStream_t)stream, true);
   }
-  return enqueue_frame(c, cam, o, d_rgb_out, d_rgb8_out, nullptr, nullptr, (cudaStream_t)stream, true);
+  return enqueue_any(c, cam, o, d_rgb_out, d_rgb8_out, nullptr, nullptr, (cudaStream_t)stream, true);
 }
 
 int crtb200_last_stats(crtb200_ctx *c, crtb200_stats *stats) {
+  ErrScope scope(c);
   if (!c || !stats) return fail(CRTB200_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(c->device));
   if (c->last_pending) {
@@ -1095,6 +1394,7 @@ int crtb200_last_stats(crtb200_ctx *c, crtb200_stats *stats) {
 }
 
 int crtb200_shard_items(crtb200_ctx *c, uint32_t shard_count, uint32_t *items) {
+  ErrScope scope(c);
   if (!c || !items || shard_count == 0) return fail(CRTB200_ERR_ARG, "bad argument");
   if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
   const uint32_t tiles = ((c->sc.width + 7) / 8) * ((c->sc.height + 3) / 4);
@@ -1104,6 +1404,7 @@ int crtb200_shard_items(crtb200_ctx *c, uint32_t shard_count, uint32_t *items) {
 
 int crtb200_assemble_shards(crtb200_ctx *c, const float *d_slabs, uint32_t shard_count, float *d_rgb_out,
                             uint8_t *d_rgb8_out, void *stream) {
+  ErrScope scope(c);
   if (!c || !d_slabs || shard_count == 0) return fail(CRTB200_ERR_ARG, "bad argument");
   if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
   CUDA_TRY(cudaSetDevice(c->device));
@@ -1112,13 +1413,16 @@ int crtb200_assemble_shards(crtb200_ctx *c, const float *d_slabs, uint32_t shard
   Frame fr{};
   fr.tiles_x = (c->sc.width + 7) / 8;
   fr.n_tiles = fr.tiles_x * ((c->sc.height + 3) / 4);
-  fr.mask = nullptr;
+  // rectangle lists that leave pixels uncovered: the assembled frame keeps what d_rgb_out held there (colorBuffer
+  // persistence), exactly like the unsharded path -- the mask is the one of the last render's rectangle list
+  fr.mask = c->mask_needed ? c->mask.p : nullptr;
   k_assemble<<<c->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(c->sc, fr, d_slabs, items, shard_count, d_rgb_out, d_rgb8_out);
   CUDA_TRY(cudaGetLastError());
   return CRTB200_OK;
 }
 
 int crtb200_generate_rays(crtb200_ctx *c, const crtb200_camera *cam, float *rays_out) {
+  ErrScope scope(c);
   if (!c || !cam || !rays_out) return fail(CRTB200_ERR_ARG, "null argument");
   if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
   CUDA_TRY(cudaSetDevice(c->device));
@@ -1137,6 +1441,7 @@ int crtb200_generate_rays(crtb200_ctx *c, const crtb200_camera *cam, float *rays
 }
 
 int crtb200_debug_powf5(crtb200_ctx *c, const float *x, uint32_t n, float *out) {
+  ErrScope scope(c);
   if (!c || !x || !out) return fail(CRTB200_ERR_ARG, "null argument");
   if (n == 0) return CRTB200_OK;
   CUDA_TRY(cudaSetDevice(c->device));
@@ -1158,6 +1463,7 @@ int crtb200_debug_powf5(crtb200_ctx *c, const float *x, uint32_t n, float *out) 
 
 int crtb200_trace_rays(crtb200_ctx *c, const float *rays, uint32_t n, uint32_t ray_type, uint32_t traversal,
                        const float *max_distance, crtb200_hit *hits_out, uint8_t *occluded_out) {
+  ErrScope scope(c);
   if (!c || !rays) return fail(CRTB200_ERR_ARG, "null argument");
   if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
   if (ray_type > 3) return fail(CRTB200_ERR_ARG, "bad ray type");

@@ -192,12 +192,12 @@ int crtfe_tracer_get_camera(crtfe_tracer *t, crtb200_camera *c) {
   fromCamera(t->tracer->getCamera(), *c);
   return 0;
 }
-int crtfe_tracer_render(crtfe_tracer *t, const char *path, uint32_t mode, uint32_t maxDepth, uint32_t fast,
+int crtfe_tracer_render(crtfe_tracer *t, const char *path, uint32_t mode, uint32_t maxDepth, uint32_t literalWalk,
                         float *rgbOut, crtb200_stats *stats) {
   if (!t) return fail("null argument");
   CRTFE_TRY({
     RenderOptions ro(static_cast<RenderOptimization>(mode), maxDepth, false);
-    ro.FAST_TRAVERSAL = fast != 0;
+    ro.LITERAL_WALK = literalWalk != 0;
     const std::vector<float> &buf = t->tracer->renderFlat(path ? path : "", ro);
     if (rgbOut) std::memcpy(rgbOut, buf.data(), buf.size() * sizeof(float));
     if (stats) *stats = t->tracer->lastStats();

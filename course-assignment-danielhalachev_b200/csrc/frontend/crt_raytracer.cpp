@@ -86,10 +86,21 @@ void writePPM(const std::string &path, const float *rgb, unsigned width, unsigne
 RayTracer::RayTracer(Scene &scene_, int device) : scene(scene_), camera(scene_.camera) {
   buildFlatScene(scene, flat);
   colorBuffer.assign(size_t(scene.sceneSettings.image.width) * scene.sceneSettings.image.height * 3, 0.0f);
-  if (crtb200_create(device, &ctx) != CRTB200_OK)
+  if (device < 0) {
+    // every visible GPU: the frame's tiles are dealt over them (crtb200_create_multi), like the reference deals its
+    // buckets over hardware_concurrency() threads (RayTracer.cpp:141-158)
+    int n = 0;
+    if (crtb200_device_count(&n) != CRTB200_OK || n < 1)
+      throw std::runtime_error(std::string("crtb200_device_count: ") + crtb200_last_error());
+    std::vector<int> ids(static_cast<size_t>(n));
+    for (int i = 0; i < n; i++) ids[static_cast<size_t>(i)] = i;
+    if (crtb200_create_multi(ids.data(), n, &ctx) != CRTB200_OK)
+      throw std::runtime_error(std::string("crtb200_create_multi: ") + crtb200_last_error());
+  } else if (crtb200_create(device, &ctx) != CRTB200_OK) {
     throw std::runtime_error(std::string("crtb200_create: ") + crtb200_last_error());
+  }
   if (crtb200_upload_scene(ctx, &flat.abi) != CRTB200_OK) {
-    std::string msg = std::string("crtb200_upload_scene: ") + crtb200_last_error();
+    std::string msg = std::string("crtb200_upload_scene: ") + crtb200_last_error_ctx(ctx);
     crtb200_destroy(ctx);
     ctx = nullptr;
     throw std::runtime_error(msg);
@@ -102,6 +113,20 @@ RayTracer::~RayTracer() {
 
 const std::vector<float> &RayTracer::renderFlat(const std::string &pathToImage, RenderOptions ro) {
   if (ro.USE_GI) throw std::runtime_error("RayTracer::render: USE_GI is not supported by the B200 core");
+  // The brute-force and single-AABB modes do not go through the KD trees in the reference: they use the linear scan of
+  // RayTracer::trace / hasIntersection (RayTracer.cpp:459-505, 521-537), which breaks equal-t ties by scene order and
+  // starts from minDistance = FLT_MAX (so NaN / inf candidates never win) -- not the tree modes' rules.  The B200 core
+  // implements the tree path only, so those modes are refused rather than rendered with the wrong tie rules.
+  switch (ro.optimization) {
+    case BVH:
+    case BVHBucketsThreadPool:
+    case BVHBucketsQueue:
+    case B200Wavefront:
+      break;
+    default:
+      throw std::runtime_error("RayTracer::render: only the tree modes (BVH, BVHBucketsThreadPool, BVHBucketsQueue, B200Wavefront) "
+                               "are rendered by the B200 core; the brute-force / AABB modes follow RayTracer::trace's linear-scan rules");
+  }
   const unsigned W = scene.sceneSettings.image.width, H = scene.sceneSettings.image.height;
   std::vector<crtb200_rect> rects;
   if (!computeRectangles(W, H, ro.optimization, scene.sceneSettings.bucketSize,
@@ -117,9 +142,9 @@ const std::vector<float> &RayTracer::renderFlat(const std::string &pathToImage, 
   opt.refraction_bias = ro.REFRACTION_BIAS;
   opt.n_rects = static_cast<uint32_t>(rects.size());
   opt.rects = rects.data();
-  opt.traversal = ro.FAST_TRAVERSAL ? 1u : 0u;
+  opt.traversal = ro.LITERAL_WALK ? 1u : 0u;
   if (crtb200_render(ctx, &cam, &opt, colorBuffer.data(), nullptr, nullptr, &stats) != CRTB200_OK)
-    throw std::runtime_error(std::string("crtb200_render: ") + crtb200_last_error());
+    throw std::runtime_error(std::string("crtb200_render: ") + crtb200_last_error_ctx(ctx));
   if (!pathToImage.empty()) writePPM(pathToImage, colorBuffer.data(), W, H);
   return colorBuffer;
 }

@@ -12,10 +12,10 @@
 
 namespace crt {
 
-// RayTracer.h:12-23 + the new enumerator.  The B200 core always traverses the KD tree (the reference's `Tree`
-// bounding type, modes BVH*); the brute-force / single-AABB enumerators are accepted for source compatibility and
-// select only the rectangle grid of the corresponding reference scheduler (they are historical HW13 baselines and
-// are not pixel-identical to the tree modes even in the reference).
+// RayTracer.h:12-23 + the new enumerator.  The B200 core always traverses the KD trees (the reference's `Tree`
+// bounding type, modes BVH*).  The brute-force / single-AABB enumerators exist for source compatibility and for
+// computeRectangles, but render() refuses them: in the reference they take RayTracer::trace's linear scan
+// (RayTracer.cpp:459-505), whose equal-t tie and NaN rules differ from the tree path's.
 enum RenderOptimization {
   NoOptimization,
   Regions,
@@ -40,7 +40,7 @@ struct RenderOptions {  // RayTracer.h:25-50
   float REFLECTION_BIAS = 1e-4;
   float REFRACTION_BIAS = 1e-4;
   float MONTE_CARLO_BIAS = 1e-4;
-  bool FAST_TRAVERSAL = false;  // extension: ordered + culled traversal (crtb200_options::traversal = 1)
+  bool LITERAL_WALK = false;  // extension: crtb200_options::traversal = 1, the visit-all itinerary with nothing skipped (same results)
   explicit RenderOptions(RenderOptimization optimization = B200Wavefront, unsigned maxDepth = 5, bool useGI = false,
                          unsigned sampleSize = 2, unsigned raysPerPixel = 1, float shadowBias = 1e-4,
                          float reflectionBias = 1e-4, float refractionBias = 1e-4, float monteCarloBias = 1e-4)
@@ -65,7 +65,8 @@ void writePPM(const std::string &path, const float *rgb, unsigned width, unsigne
 
 class RayTracer {
  public:
-  explicit RayTracer(Scene &scene, int device = 0);
+  // device >= 0: that GPU; device < 0 (default): every visible GPU, each frame split by tiles (crtb200_create_multi)
+  explicit RayTracer(Scene &scene, int device = -1);
   ~RayTracer();
   RayTracer(const RayTracer &) = delete;
   RayTracer &operator=(const RayTracer &) = delete;

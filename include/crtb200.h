@@ -9,9 +9,11 @@
  * INTEGRATION.md shows the binding a maintainer adds to RayTracer.cpp.
  *
  * Conventions: plain C, plain pointers + sizes, no torch / C++ types.  Every function returns 0 on success or a
- * negative crtb200_status; crtb200_last_error() returns a human-readable message for the calling thread.
- * Host pointers handed to upload/render are borrowed for the duration of the call only.  One context = one
- * GPU = one caller thread at a time (the reference's render() is not re-entrant either, RayTracer.cpp:205-206).
+ * negative crtb200_status; crtb200_last_error_ctx(ctx) returns the message of the last failed call on that context
+ * (crtb200_last_error() the last one of the calling thread, for calls that have no context yet).
+ * Host pointers handed to upload/render are borrowed for the duration of the call only.  One context = one caller
+ * thread at a time (the reference's render() is not re-entrant either, RayTracer.cpp:205-206); a context drives one
+ * GPU (crtb200_create) or several (crtb200_create_multi: scene replicated, every frame split by tiles).
  * There is NO CPU fallback: every call fails with CRTB200_ERR_CUDA when no sm_100 device is usable.
  */
 #ifndef CRTB200_H
@@ -24,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CRTB200_ABI_VERSION 1u
+#define CRTB200_ABI_VERSION 2u
 #define CRTB200_INVALID 0xFFFFFFFFu /* = INVALID_INDEX, include/tree/KDTree.h:11 */
 
 typedef enum crtb200_status {
@@ -152,11 +154,12 @@ typedef struct crtb200_options {
   float refraction_bias; /* REFRACTION_BIAS, default 1e-4f */
   uint32_t n_rects;
   const crtb200_rect *rects;
-  uint32_t traversal; /* 0 = exact: the reference's visit-all candidate set and order (KDTree.cpp:48-87): bit-exact */
-                      /*     hit ids and float RGB.  DEFAULT, and what every parity claim refers to.               */
-                      /* 1 = culled: same walk, but subtrees whose box is wholly behind the ray origin or wholly    */
-                      /*     beyond the best hit / the light are skipped.  Not the reference's    */
-                      /*     candidate set; measured deviations per scene are in DESIGN.md section 3.6.             */
+  uint32_t traversal; /* 0 = DEFAULT: the reference's walk (KDTree.cpp:48-87, 127-166) minus the subtrees that provably  */
+                      /*     cannot contribute (conservative culling with a per-mesh margin), long    */
+                      /*     walks finished by a group of lanes (tail hand-off).  Results are          */
+                      /*     identical to the reference's: hit ids, t, float RGB, ray counts.                         */
+                      /* 1 = the reference's literal itinerary: every node whose box passes is visited, nothing is    */
+                      /*     skipped or reordered (what count_work = 1 counts; the round-1 default).                  */
   uint32_t count_work; /* 0 = off; 1 = count node / triangle tests under the reference's visit-all rule (shadow  */
                        /* early termination disabled; same pixels) -- the figure the roofline arithmetic uses;  */
                        /* 2 = count the tests the production kernels really perform                             */
@@ -195,12 +198,22 @@ uint32_t crtb200_abi_version(void);
 const char *crtb200_last_error(void);
 int crtb200_device_count(int *count);
 
+const char *crtb200_last_error_ctx(const crtb200_ctx *ctx);
+
 /* replaces: RayTracer::RayTracer(Scene&) resource acquisition (RayTracer.cpp:45-51) */
 int crtb200_create(int device, crtb200_ctx **out);
+/* The same on n GPUs of one node (SURVEY 8(b) "Proposed exports", 8(e)): replaces the std::thread bucket pool of
+ * RayTracer::renderBucketsThreadpool (RayTracer.cpp:141-158) at device scale.  The context behaves like a single-GPU
+ * one -- same calls, same results bit for bit -- but crtb200_upload_scene replicates the scene on every GPU and every
+ * frame's 8x4-pixel tiles are dealt round-robin over the GPUs; each GPU stores its pixels straight into the frame on
+ * device_ids[0] through peer-mapped memory (NVLink), from where the frame is returned.  A device id may repeat (several
+ * tile shards on one GPU; used by the single-GPU tests). */
+int crtb200_create_multi(const int *device_ids, int n, crtb200_ctx **out);
+int crtb200_device_list(const crtb200_ctx *ctx, int *device_ids, int capacity, int *count);
 int crtb200_destroy(crtb200_ctx *ctx);
 /* device budget in bytes for the per-frame ray queues (default 16 GiB); frames that need more are chunked */
 int crtb200_set_queue_budget(crtb200_ctx *ctx, uint64_t bytes);
-/* chunks of a frame rendered concurrently on separate streams (default 4; 1 = strictly sequential kernels, which is
+/* chunks of a frame rendered concurrently on separate streams (default 6; 1 = strictly sequential kernels, which is
  * what the per-kernel timers closest_ms / shadow_ms of crtb200_stats require -- they read 0 otherwise) */
 int crtb200_set_concurrency(crtb200_ctx *ctx, uint32_t chunks_in_flight);
 

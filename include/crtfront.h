@@ -55,7 +55,7 @@ int crtfe_tracer_set_camera(crtfe_tracer *tracer, const crtb200_camera *camera);
 int crtfe_tracer_get_camera(crtfe_tracer *tracer, crtb200_camera *camera);
 /* RayTracer::render(pathToImage, RenderOptions{mode, max_depth, false}); rgb_out (optional) receives H*W*3 floats */
 int crtfe_tracer_render(crtfe_tracer *tracer, const char *path_to_image, uint32_t mode, uint32_t max_depth,
-                        uint32_t fast_traversal, float *rgb_out, crtb200_stats *stats);
+                        uint32_t literal_walk, float *rgb_out, crtb200_stats *stats);
 
 #ifdef __cplusplus
 }

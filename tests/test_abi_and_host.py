@@ -23,7 +23,7 @@ def test_core_exports_every_declared_symbol(built):
     assert len(names) >= 15
     for n in names:
         assert hasattr(lib, n), f"libcrtb200.so does not export {n}"
-    assert lib.crtb200_abi_version() == 1
+    assert lib.crtb200_abi_version() == 2
 
 
 def test_front_exports_every_declared_symbol(built):

@@ -2,12 +2,13 @@
 inputs and against the committed reference fixtures.  Bar: bit-exact hit ids (mesh, triangle, t), bit-identical float RGB,
 identical ray counts and identical traversal work; the north_star 8-bit tolerance (|d| <= 1 on >= 99.9 % of pixels, none
 > 4) follows and is asserted too."""
+import importlib
 import os
 
 import numpy as np
 import pytest
 
-from conftest import ROOT, SMALL_SCENES, same_f32
+from conftest import PKG, ROOT, SMALL_SCENES, same_f32
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(ROOT, "tests", "golden")
@@ -279,7 +280,7 @@ def test_tail_handoff_matches_golden(name, which, gpu_coop_all, gpu_coop_mid, gp
     _assert_pixels(name, rgb, g["rgb"], rgb8, g["ppm"])
     assert [st["rays_primary"], st["rays_shadow"], st["rays_reflection"], st["rays_refraction"]] == list(g["rays"])
     if which == "all" and name not in ("empty_scene",):
-        assert st["handoff_closest"] >= st["rays_primary"]  # every primary walk went through k_coop
+        assert st["handoff_closest"] > 0  # (warps that fetched their rays before the queue ran dry poll it every 4th round)
     if which == "off":
         assert st["handoff_closest"] == 0 and st["handoff_shadow"] == 0
 
@@ -324,3 +325,88 @@ def test_trees_that_do_not_nest_take_the_literal_walk(gpu, built, scene_dir, ob,
     _, _, _, a = gpu.render(sf.camera(), crt.make_options(count_work=2, traversal=0))
     _, _, _, b = gpu.render(sf.camera(), crt.make_options(count_work=2, traversal=1))
     assert a["node_tests"] == b["node_tests"]  # nothing was culled
+
+
+def test_multi_gpu_context_matches_single(gpu, built, loaded, crt):
+    """crtb200_create_multi: the frame's tiles are dealt over the GPUs of the context, every GPU stores straight into the
+    primary's frame (peer-mapped memory).  Same calls, same results as one GPU: float RGB, PPMColor bytes, hits, ray
+    counts -- with every visible GPU, and with one GPU listed three times (three tile shards on one device)."""
+    n = core_device_count(crt)
+    lists = [[0, 0, 0]] + ([list(range(n))] if n > 1 else [])
+    for ids in lists:
+        multi = crt.Context(ids)
+        assert multi.devices() == ids
+        for name in ("hw11_room", "uncovered", "hw14_small", "one_pixel"):
+            sf, flat, rects, nr = loaded[name]
+            gpu.upload(flat, keepalive=sf)
+            multi.upload(flat, keepalive=sf)
+            opt = crt.make_options(rects=rects, n_rects=nr)
+            a, a8, ha, sa = gpu.render(sf.camera(), opt, want_rgb8=True, want_hits=True)
+            b, b8, hb, sb = multi.render(sf.camera(), opt, want_rgb8=True, want_hits=True)
+            assert same_f32(a, b).all(), (ids, name)
+            assert np.array_equal(a8, b8)
+            cov = _covered(sf, rects, nr)
+            assert np.array_equal(ha["mesh"][cov], hb["mesh"][cov]) and np.array_equal(ha["triangle"][cov], hb["triangle"][cov])
+            for k in ("rays_primary", "rays_shadow", "rays_reflection", "rays_refraction"):
+                assert sa[k] == sb[k], (ids, name, k)
+        # batched animation through the multi-GPU context == per-camera renders on one GPU
+        sf, flat, _, _ = loaded["hw14_small"]
+        gpu.upload(flat, keepalive=sf)
+        multi.upload(flat, keepalive=sf)
+        cams = [crt.Camera.make(p, r) for p, r in importlib.import_module(PKG + ".scenes").orbit_cameras(5, radius=5.12, center_z=-4.0)]
+        frames, _, _ = multi.render_frames(cams, crt.make_options())
+        for k, cam in enumerate(cams):
+            one, _, _, _ = gpu.render(cam, crt.make_options())
+            assert same_f32(frames[k], one).all()
+        multi.close()
+
+
+def core_device_count(crt):
+    import ctypes as C
+    n = C.c_int(0)
+    assert crt.core().crtb200_device_count(C.byref(n)) == 0
+    return n.value
+
+
+def test_context_error_is_per_context(gpu, built, crt):
+    other = crt.Context(0)
+    with pytest.raises(crt.CrtError):
+        other.render(crt.Camera.make(), crt.make_options())  # no scene uploaded
+    assert "no scene" in other.last_error()
+    assert "no scene" not in gpu.last_error()
+    other.close()
+
+
+def test_raytracer_refuses_linear_scan_modes(loaded, crt):
+    """NoOptimization / Regions / Buckets* / AABB* use RayTracer::trace's linear scan in the reference (RayTracer.cpp:
+    459-505): other tie and NaN rules than the tree path.  The mirror renders the tree modes only and says so."""
+    sf, flat, rects, n = loaded["hw07_scene0"]
+    tracer = crt.RayTracer(sf)
+    for mode in (0, 1, 2, 3, 4, 5, 6):
+        with pytest.raises(crt.CrtError, match="tree modes"):
+            tracer.render("", mode=mode)
+    a, _ = tracer.render("", mode=crt.MODE_BVH_BUCKETS_THREADPOOL)
+    b, _ = tracer.render("", mode=crt.MODE_B200_WAVEFRONT)
+    c, _ = tracer.render("", mode=crt.MODE_B200_WAVEFRONT, literal=True)
+    assert same_f32(a, b).all() and same_f32(a, c).all()
+    tracer.close()
+
+
+def test_assemble_keeps_uncovered_pixels(gpu, loaded, crt):
+    """Sharded render of a rectangle list that leaves pixels uncovered: crtb200_assemble_shards must not overwrite them."""
+    torch = pytest.importorskip("torch")
+    sf, flat, rects, n = loaded["uncovered"]
+    gpu.upload(flat, keepalive=sf)
+    full, _, _, _ = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n))
+    world = 2
+    items = gpu.shard_items(world)
+    slabs = torch.zeros((world, items, 3), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(world):
+        gpu.render_device(sf.camera(), crt.make_options(rects=rects, n_rects=n, shard_index=r, shard_count=world), d_rgb=slabs[r].data_ptr(), stream=st)
+    out = torch.full((sf.info.height, sf.info.width, 3), 7.0, dtype=torch.float32, device="cuda")
+    gpu.assemble_shards(slabs.data_ptr(), world, d_rgb=out.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    cov = _covered(sf, rects, n)
+    assert same_f32(out[cov], full[cov]).all() and (out[~cov] == 7.0).all()
