@@ -52,8 +52,9 @@ struct Levels {
   // ovf[] (3 x uint4 per record) and finished one WARP per ray; tail_grace = 0 switches this off
   uint4 *ovf;
   uint32_t *ovf_ctl;  // per traversal launch L (level, or CRT_MAX_LEVELS for the shadow pass): [2L] written, [2L+1] taken
-  uint32_t ovf_cap;
-  uint32_t tail_iters;  // 0 = off; else once the queue is dry a walk that has taken tail_iters - 1 node-phase iterations is handed off
+  uint32_t ovf_cap;     // walks k_coop can take per launch (about two per resident k_coop warp): hand-off stops there
+  uint32_t tail_iters;  // 0 = off; else tail_iters - 1 = the floor of the hand-off threshold (see tail_threshold)
+  uint32_t tail_start;  // the threshold's value when the queue has just run dry (1024)
 };
 
 enum { COMB_FINAL = 0, COMB_REFLECT = 1, COMB_FRESNEL = 2, COMB_COPY = 3 };
@@ -235,29 +236,39 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, const
 // Tail hand-off.  A ray is walked by one lane, and 2-3 % of the rays of a large-mesh frame need hundreds of node-phase
 // iterations: once the queue is dry a traversal kernel used to wait 0.3-0.8 ms for its last few lanes.
 // Now, once the queue is dry (every warp polls the global cursor, so a warp full of long walks learns it too), a lane
-// whose walk has already taken lv.tail_iters node-phase iterations hands it to k_coop, where a whole warp finishes it;
-// young walks keep going here (most end within a few iterations; the rest reach the threshold and follow).  So a
-// traversal kernel ends at most ~tail_iters iterations after its queue ran dry, and k_coop only sees walks that are
-// long enough to amortise its ramp.  A walk's state goes into one 48-byte record
+// whose walk has taken more node-phase iterations than a falling threshold (tail_threshold) hands it to k_coop, where
+// a group of lanes finishes it; young walks keep going here (most end within a few iterations).  k_coop's capacity
+// bounds how many walks are handed off per launch.  A walk's state goes into one 48-byte record
 //   r0 = {ray id (queue node / visibility slot), cur, cend, resume}     r1 = {mref, mend, seen lo, seen hi}
 //   r2 = {below, bits(mu), bits(best_t), best_tri}
 // written at the top of a round, where no lane has a pending triangle range.  min_t is implied: best_t when that is
 // below +inf, else +inf (closest_offer keeps it so).
 // ------------------------------------------------------------------------------------------------------------
+// Hand-off threshold `dry_rounds` rounds after the warp learned that the queue is dry: 1024 node-phase iterations at
+// first, halved every 4 rounds (~20 us) down to the floor.  The longest walks therefore go first, and because k_coop's
+// capacity (Levels::ovf_cap) closes the hand-off, they are the ones that get the warp-wide treatment -- a walk costs
+// k_coop about five times the instructions it costs here (profiles/r2_tuning.md), so it must be kept for the walks
+// whose serial latency would otherwise set the kernel's end.
+CRT_DI uint32_t tail_threshold(const Levels &lv, const uint32_t dry_rounds) {
+  const uint32_t sh = dry_rounds >> 2, t = sh < 31u ? (lv.tail_start >> sh) : 0u;
+  return t > lv.tail_iters - 1u ? t : lv.tail_iters - 1u;
+}
 CRT_DI bool queue_dry(const uint32_t *work_counter, const uint32_t total) {
   uint32_t v = 0;
   if (lane_id() == 0) v = *reinterpret_cast<const volatile uint32_t *>(work_counter);
   return __shfl_sync(CRT_FULL_MASK, v, 0) >= total;
 }
+// `closed` (warp-uniform) is set once the record buffer is full: the warp stops asking
 CRT_DI bool tail_handoff(const Levels &lv, const uint32_t launch, const bool want, const uint32_t id, const Trav &tv,
-                         const float best_t, const uint32_t best_tri) {
+                         const float best_t, const uint32_t best_tri, bool &closed) {
   const uint32_t wm = __ballot_sync(CRT_FULL_MASK, want);
   if (!wm) return false;
   uint32_t base = 0;
   if (lane_id() == 0) base = atomicAdd(&lv.ovf_ctl[2u * launch], (uint32_t)__popc(wm));
   base = __shfl_sync(CRT_FULL_MASK, base, 0);
   const uint32_t r = base + __popc(wm & lanemask_lt());
-  if (!want || r >= lv.ovf_cap) return false;  // a full buffer (never, by its sizing) just leaves the lane walking
+  if (base + (uint32_t)__popc(wm) >= lv.ovf_cap) closed = true;
+  if (!want || r >= lv.ovf_cap) return false;  // k_coop's capacity is used up: the lane keeps walking here
   uint4 *rec = lv.ovf + 3 * (size_t)r;
   rec[0] = make_uint4(id, tv.cur, tv.cend, tv.resume);
   rec[1] = make_uint4(tv.mref, tv.mend, (uint32_t)tv.seen, (uint32_t)(tv.seen >> 32));
@@ -289,8 +300,8 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
   const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
   const uint32_t node_base = lv.offset[level];
   const uint32_t lane = lane_id();
-  bool active = false, exhausted = false;
-  uint32_t node = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0;
+  bool active = false, exhausted = false, closed = false;
+  uint32_t node = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0, dry_rounds = 0;
 #if CRT_PHASE_CLOCKS
   uint32_t ray_iters = 0;
 #endif
@@ -345,7 +356,10 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
     }
     if (!COUNT && lv.tail_iters) {
       if (!exhausted && (++round & 3u) == 0u) exhausted = queue_dry(work_counter, total);
-      if (exhausted && tail_handoff(lv, level, active && walk_iters + 1u >= lv.tail_iters, node, tv, cl.best_t, cl.best_tri)) active = false;
+      if (exhausted && !closed) {
+        const uint32_t thr = tail_threshold(lv, dry_rounds++);
+        if (tail_handoff(lv, level, active && walk_iters >= thr, node, tv, cl.best_t, cl.best_tri, closed)) active = false;
+      }
     }
     if (!__any_sync(CRT_FULL_MASK, active)) {
       if (exhausted) break;
@@ -644,8 +658,8 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
   const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];
   const uint32_t total = n_hits * sc.n_lights;
   const uint32_t lane = lane_id();
-  bool active = false, exhausted = false, occluded = false;
-  uint32_t slot = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0;
+  bool active = false, exhausted = false, occluded = false, closed = false;
+  uint32_t slot = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0, dry_rounds = 0;
 #if CRT_PHASE_CLOCKS
   uint32_t ray_iters = 0;
 #endif
@@ -690,7 +704,10 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
     }
     if (COUNT == 0 && lv.tail_iters) {
       if (!exhausted && (++round & 3u) == 0u) exhausted = queue_dry(work_counter, total);
-      if (exhausted && tail_handoff(lv, CRT_MAX_LEVELS, active && walk_iters + 1u >= lv.tail_iters, slot, tv, 0.0f, CRT_INVALID)) active = false;
+      if (exhausted && !closed) {
+        const uint32_t thr = tail_threshold(lv, dry_rounds++);
+        if (tail_handoff(lv, CRT_MAX_LEVELS, active && walk_iters >= thr, slot, tv, 0.0f, CRT_INVALID, closed)) active = false;
+      }
     }
     if (!__any_sync(CRT_FULL_MASK, active)) {
       if (exhausted) break;
@@ -789,7 +806,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
 #define CRT_COOP_STATS 0  // debug builds (tools/): iterations, box tests and triangle tests of k_coop into stats[34..39]
 #endif
 #ifndef CRT_COOP_GROUP
-#define CRT_COOP_GROUP 8    // lanes per walk
+#define CRT_COOP_GROUP 32   // lanes per walk (8 and 16 measured: same throughput, longer walks; profiles/r2_tuning.md)
 #endif
 struct __align__(16) WarpCoop {
   uint32_t stack[CRT_COOP_CAP];

@@ -146,9 +146,13 @@ struct crtb200_ctx {
   DevBuf<float4> vtx_normal;
   bool nested_ok = false;    // every child box of the uploaded mesh trees lies inside its parent's and no tree is deeper
                              // than the k_coop LIFO allows: the order-free walk of k_coop and the subtree culling are exact
-  int tail_iters = 32;       // tail hand-off (crt_kernels.cuh): once a traversal kernel's queue is dry, walks that have taken
-                             // this many node-phase iterations go to k_coop.  CRT_TAIL_ITERS overrides (tools / tests):
-                             // 0 = every walk still running, -1 = off
+  int tail_iters = 16;       // tail hand-off (crt_kernels.cuh): once a traversal kernel's queue is dry, walks longer than a
+                             // falling threshold (1024 node-phase iterations, halved every 4 rounds, never below this
+                             // floor) go to k_coop.  CRT_TAIL_ITERS overrides (tools / tests): 0 = every walk still
+                             // running (the threshold still falls from 1024), -1 = off
+  int tail_start = 1024;     // CRT_TAIL_START (tests): the threshold's starting value
+  int tail_cap = 2;          // hand-off capacity per launch, in walks per resident k_coop warp (CRT_TAIL_CAP; tests use
+                             // a huge value so that every walk goes through k_coop)
   DevBuf<uint32_t> top_refs;
   DevBuf<uint4> tri_shade;
   DevBuf<float2> vtx_uv;
@@ -267,6 +271,8 @@ int crtb200_create(int device, crtb200_ctx **out) {
   }
   if (const char *env = getenv("CRT_L2_PERSIST")) c->l2_persist = atoi(env);
   if (const char *env = getenv("CRT_TAIL_ITERS")) c->tail_iters = std::max(-1, atoi(env));
+  if (const char *env = getenv("CRT_TAIL_CAP")) c->tail_cap = std::max(1, atoi(env));
+  if (const char *env = getenv("CRT_TAIL_START")) c->tail_start = std::max(0, atoi(env));
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
   c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
   if (c->l2_persist && c->l2_persist_max)
@@ -862,8 +868,9 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     q.work = q.ctl.p + n_counts;
     q.lv.ovf = q.ovf.p;
     q.lv.ovf_ctl = q.ctl.p + n_counts + n_work;
-    q.lv.ovf_cap = (uint32_t)ovf_cap;
+    q.lv.ovf_cap = (uint32_t)std::min<uint64_t>(ovf_cap, (uint64_t)c->tail_cap * c->blocks_coop * CRT_COOP_WARPS);
     q.lv.tail_iters = 0;
+    q.lv.tail_start = 1024;
     q.lv.ray_o = q.ray_o.p;
     q.lv.ray_d = q.ray_d.p;
     q.lv.hit_tri = q.hit_tri.p;
@@ -1012,6 +1019,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     fr.n_items0 = std::min(c->cap_items, shard_items - begin);
     CUDA_TRY(cudaMemsetAsync(q.ctl.p, 0, q.ctl.n * sizeof(uint32_t), qs));
     q.lv.tail_iters = handoff ? (uint32_t)(c->tail_iters + 1) : 0u;
+    q.lv.tail_start = (uint32_t)c->tail_start;
     for (uint32_t l = 0; l < levels; l++) {
       if (per_kernel) {
         cudaEventRecord(next_event(c), qs);

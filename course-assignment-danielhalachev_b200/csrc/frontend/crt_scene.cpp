@@ -69,6 +69,8 @@ static bool loadPng(const std::vector<unsigned char> &file, int &w, int &h, int 
                     std::string &err) {
   size_t pos = 8;
   int bitDepth = 0, colorType = 0, interlace = 0;
+  bool haveHeader = false;
+  w = h = 0;
   std::vector<unsigned char> idat, palette;
   while (pos + 12 <= file.size()) {
     unsigned len = be32(&file[pos]);
@@ -76,8 +78,18 @@ static bool loadPng(const std::vector<unsigned char> &file, int &w, int &h, int 
     const unsigned char *data = &file[pos + 8];
     if (pos + 12 + len > file.size()) break;
     if (!std::memcmp(tag, "IHDR", 4)) {
-      w = int(be32(data));
-      h = int(be32(data + 4));
+      if (len < 13) {
+        err = "PNG: truncated IHDR";
+        return false;
+      }
+      const unsigned uw = be32(data), uh = be32(data + 4);
+      if (uw == 0 || uh == 0 || uw > 32768u || uh > 32768u) {
+        err = "PNG: image size out of range (1..32768)";
+        return false;
+      }
+      haveHeader = true;
+      w = int(uw);
+      h = int(uh);
       bitDepth = data[8];
       colorType = data[9];
       interlace = data[12];
@@ -89,6 +101,10 @@ static bool loadPng(const std::vector<unsigned char> &file, int &w, int &h, int 
       break;
     }
     pos += 12 + len;
+  }
+  if (!haveHeader) {
+    err = "PNG: no IHDR chunk";
+    return false;
   }
   if (bitDepth != 8 || interlace != 0) {
     err = "PNG: only 8-bit non-interlaced images are supported";

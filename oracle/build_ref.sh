@@ -11,6 +11,8 @@
 # Two flavours, because USE_TEXTURES changes struct layouts (Vertex.h:10-19, Material.h:10-25):
 #   oracle/_ref/crt_ref      plain           (configs 1, 2, 4, 5)
 #   oracle/_ref/crt_ref_tex  -DUSE_TEXTURES=1 (config 3)
+# and INTEGRATION.md section B compiled for real (oracle/ref_b200_binding.cpp):
+#   oracle/_ref/crt_ref_b200 the reference's loader, tree build and PPM writer around crtb200_render (needs libcrtb200.so)
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${CRT_REFERENCE_ROOT:-/root/reference}/SourceCode"
@@ -37,5 +39,10 @@ WRAP="-Wl,--wrap=_ZNK6KDTreeI19ObjectKDTreeSubTreeE9intersectERK3Ray -Wl,--wrap=
 COMMON="-std=gnu++20 -O3 -DNDEBUG -DMEASURE_TIME -ffp-contract=off -w -include $HERE/ref_shim.h -I$REF/include -I$REF/external -I$RJ"
 g++ $COMMON                  "$HERE/ref_driver.cpp" $SRCS $WRAP -lpthread -o "$OUT/crt_ref" &
 g++ $COMMON -DUSE_TEXTURES=1 "$HERE/ref_driver.cpp" $SRCS $WRAP -lpthread -o "$OUT/crt_ref_tex" &
+CSRC="$HERE/../course-assignment-danielhalachev_b200/csrc"
+if [ -f "$CSRC/libcrtb200.so" ]; then
+  g++ $COMMON "$HERE/ref_b200_binding.cpp" $SRCS -L"$CSRC" -lcrtb200 -Wl,-rpath,'$ORIGIN/../../course-assignment-danielhalachev_b200/csrc' \
+      -lpthread -o "$OUT/crt_ref_b200" &
+fi
 wait
-echo "build_ref: built $OUT/crt_ref and $OUT/crt_ref_tex"
+echo "build_ref: built $OUT/crt_ref, $OUT/crt_ref_tex$([ -f "$OUT/crt_ref_b200" ] && echo ", $OUT/crt_ref_b200")"

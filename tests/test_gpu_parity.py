@@ -241,7 +241,7 @@ def _ctx_with_env(built, **env):
 def gpu_coop_all(built):
     """Every walk is handed to k_coop before its first step (a small frame's queue is dry after the first refill, and
     a threshold of 0 iterations hands off at once): the warp-per-ray walk does ALL the traversal work of the frame."""
-    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=0)
+    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=0, CRT_TAIL_START=0, CRT_TAIL_CAP=1000000)
     yield ctx
     ctx.close()
 
@@ -249,7 +249,7 @@ def gpu_coop_all(built):
 @pytest.fixture(scope="module")
 def gpu_coop_mid(built):
     """Walks are handed off in mid-flight: whatever has taken 3 node-phase iterations when the queue is dry."""
-    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=3)
+    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=3, CRT_TAIL_START=3, CRT_TAIL_CAP=1000000)
     yield ctx
     ctx.close()
 
@@ -410,3 +410,24 @@ def test_assemble_keeps_uncovered_pixels(gpu, loaded, crt):
     out = out.cpu().numpy()
     cov = _covered(sf, rects, n)
     assert same_f32(out[cov], full[cov]).all() and (out[~cov] == 7.0).all()
+
+
+@pytest.mark.parametrize("name", ["hw11_room", "hw14_small", "uncovered", "many_meshes"])
+def test_reference_binary_with_b200_binding_writes_the_same_ppm(name, built, ob, scene_dir, tmp_path):
+    """INTEGRATION.md section B compiled for real: oracle/_ref/crt_ref_b200 = the UNMODIFIED reference's SceneParser,
+    RayTracer constructor (AABB + KDTree::build) and exportPPM around crtb200_render (oracle/ref_b200_binding.cpp flattens
+    the reference's own Scene / KDTree objects into the C ABI).  Its PPM must equal, byte for byte, the one the reference
+    writes when it renders on the CPU (crt_ref), for one GPU and for three tile shards."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "crt_ref_b200")
+    if not (os.path.exists(exe) and ob.have_reference(False)):
+        pytest.skip("oracle/_ref binaries not present")
+    ref = ob.run_reference(name + ".crtscene", scene_dir, str(tmp_path / "cpu"), hits=False)
+    want = open(ref["ppm_path"], "rb").read()
+    for devices in (1, 3):  # 3 > visible GPUs on a one-GPU box is refused by crtb200_create_multi ...
+        out = str(tmp_path / f"gpu{devices}.ppm")
+        r = subprocess.run([exe, name + ".crtscene", scene_dir, out, "--devices", str(devices)], capture_output=True, text=True, timeout=600)
+        if devices > 1 and r.returncode != 0 and "no such CUDA device" in r.stderr:
+            continue  # ... which is the right answer there
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert open(out, "rb").read() == want, f"{name}: PPM of the reference + B200 binding differs from the reference's own"

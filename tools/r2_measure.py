@@ -51,8 +51,13 @@ def main():
         configs = [("literal", 1, None)] + [(f"default tail {t}", 0, t) for t in args.tails.split(",")]
         for label, trav, tail in configs:
             env = {}
-            if tail is not None:
-                env = {"CRT_TAIL_ITERS": tail}
+            if tail is not None:  # "floor" or "floor:cap" or "floor:cap:start"
+                parts = tail.split(":")
+                env = {"CRT_TAIL_ITERS": parts[0]}
+                if len(parts) > 1:
+                    env["CRT_TAIL_CAP"] = parts[1]
+                if len(parts) > 2:
+                    env["CRT_TAIL_START"] = parts[2]
             ctx = ctx_with_env(crt, env)
             ctx.upload(flat, keepalive=sf)
             ctx.set_concurrency(1)
