@@ -26,6 +26,9 @@ using namespace crtd;
 #ifndef CRT_REFILL
 #define CRT_REFILL 8  // refill a warp when at least this many lanes are idle
 #endif
+#ifndef CRT_COOP_KIND
+#define CRT_COOP_KIND 1  // hand-off pass: 0 = k_coop (a group of lanes per walk), 1 = k_wave (eight walks per warp share a frontier)
+#endif
 #ifndef CRT_LOOP_MODE
 #define CRT_LOOP_MODE 2  // 0 = while-while, 1 = merged loop, 2 = node phase + warp-cooperative triangle phase (crt_kernels.cuh)
 #endif
@@ -151,7 +154,8 @@ struct crtb200_ctx {
                              // floor) go to k_coop.  CRT_TAIL_ITERS overrides (tools / tests): 0 = every walk still
                              // running (the threshold still falls from 1024), -1 = off
   int tail_start = 1024;     // CRT_TAIL_START (tests): the threshold's starting value
-  int tail_cap = 2;          // hand-off capacity per launch, in walks per resident k_coop warp (CRT_TAIL_CAP; tests use
+  int tail_small = 32768;    // CRT_TAIL_SMALL: launches of at most this many rays hand off at the floor from the start
+  int tail_cap = 8;          // hand-off capacity per launch, in walks per resident k_coop warp (CRT_TAIL_CAP; tests use
                              // a huge value so that every walk goes through k_coop)
   DevBuf<uint32_t> top_refs;
   DevBuf<uint4> tri_shade;
@@ -263,7 +267,11 @@ int crtb200_create(int device, crtb200_ctx **out) {
   c->blocks_closest = std::max(1, occ) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
+#if CRT_COOP_KIND == 1
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<true, false, true>, 32 * CRT_WAVE_WARPS, 0);
+#else
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_coop<true, false, true, CRT_COOP_GROUP>, 32 * CRT_COOP_WARPS, 0);
+#endif
   c->blocks_coop = std::max(1, occ) * c->sm_count;
   if (const char *env = getenv("CRT_BLOCKS_PER_SM")) {  // tuning only (tools/): resident persistent CTAs per SM
     const int b = atoi(env);
@@ -273,6 +281,7 @@ int crtb200_create(int device, crtb200_ctx **out) {
   if (const char *env = getenv("CRT_TAIL_ITERS")) c->tail_iters = std::max(-1, atoi(env));
   if (const char *env = getenv("CRT_TAIL_CAP")) c->tail_cap = std::max(1, atoi(env));
   if (const char *env = getenv("CRT_TAIL_START")) c->tail_start = std::max(0, atoi(env));
+  if (const char *env = getenv("CRT_TAIL_SMALL")) c->tail_small = std::max(0, atoi(env));
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
   c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
   if (c->l2_persist && c->l2_persist_max)
@@ -871,6 +880,7 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     q.lv.ovf_cap = (uint32_t)std::min<uint64_t>(ovf_cap, (uint64_t)c->tail_cap * c->blocks_coop * CRT_COOP_WARPS);
     q.lv.tail_iters = 0;
     q.lv.tail_start = 1024;
+    q.lv.tail_small = 0;
     q.lv.ray_o = q.ray_o.p;
     q.lv.ray_d = q.ray_d.p;
     q.lv.hit_tri = q.hit_tri.p;
@@ -936,10 +946,25 @@ static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const 
 
 template <bool CULL>
 static void launch_coop_closest(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, cudaStream_t st) {
+#if CRT_COOP_KIND == 1
+  if (primary)
+    k_wave<false, true, CULL><<<c->blocks_coop, 32 * CRT_WAVE_WARPS, 0, st>>>(c->sc, fr, lv, level);
+  else
+    k_wave<false, false, CULL><<<c->blocks_coop, 32 * CRT_WAVE_WARPS, 0, st>>>(c->sc, fr, lv, level);
+#else
   if (primary)
     k_coop<false, true, CULL, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
   else
     k_coop<false, false, CULL, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
+#endif
+}
+template <bool CULL>
+static void launch_coop_shadow(crtb200_ctx *c, const Frame &fr, const Levels &lv, cudaStream_t st) {
+#if CRT_COOP_KIND == 1
+  k_wave<true, false, CULL><<<c->blocks_coop, 32 * CRT_WAVE_WARPS, 0, st>>>(c->sc, fr, lv, 0);
+#else
+  k_coop<true, false, CULL, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, 0);
+#endif
 }
 
 // Host destinations of crtb200_render: each chunk's band of rows is copied back on the chunk's own stream right after
@@ -1020,6 +1045,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     CUDA_TRY(cudaMemsetAsync(q.ctl.p, 0, q.ctl.n * sizeof(uint32_t), qs));
     q.lv.tail_iters = handoff ? (uint32_t)(c->tail_iters + 1) : 0u;
     q.lv.tail_start = (uint32_t)c->tail_start;
+    q.lv.tail_small = (uint32_t)c->tail_small;
     for (uint32_t l = 0; l < levels; l++) {
       if (per_kernel) {
         cudaEventRecord(next_event(c), qs);
@@ -1071,9 +1097,9 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
         c->kev_kind.push_back(3);
       }
       if (cull)
-        k_coop<true, false, true, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, qs>>>(c->sc, fr, q.lv, 0);
+        launch_coop_shadow<true>(c, fr, q.lv, qs);
       else
-        k_coop<true, false, false, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, qs>>>(c->sc, fr, q.lv, 0);
+        launch_coop_shadow<false>(c, fr, q.lv, qs);
       launches++;
     }
     if (per_kernel) cudaEventRecord(next_event(c), qs);

@@ -241,7 +241,7 @@ def _ctx_with_env(built, **env):
 def gpu_coop_all(built):
     """Every walk is handed to k_coop before its first step (a small frame's queue is dry after the first refill, and
     a threshold of 0 iterations hands off at once): the warp-per-ray walk does ALL the traversal work of the frame."""
-    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=0, CRT_TAIL_START=0, CRT_TAIL_CAP=1000000)
+    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=0, CRT_TAIL_START=0, CRT_TAIL_SMALL=100000000, CRT_TAIL_CAP=1000000)
     yield ctx
     ctx.close()
 
@@ -249,7 +249,7 @@ def gpu_coop_all(built):
 @pytest.fixture(scope="module")
 def gpu_coop_mid(built):
     """Walks are handed off in mid-flight: whatever has taken 3 node-phase iterations when the queue is dry."""
-    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=3, CRT_TAIL_START=3, CRT_TAIL_CAP=1000000)
+    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=3, CRT_TAIL_START=3, CRT_TAIL_SMALL=100000000, CRT_TAIL_CAP=1000000)
     yield ctx
     ctx.close()
 

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--shards", default="1,8")
     ap.add_argument("--frames", type=int, default=7)
     ap.add_argument("--json", default="")
+    ap.add_argument("--chunks", default="", help="CRT_DEVICE_CHUNKS values to sweep (device-only frames split over k streams)")
     args = ap.parse_args()
     import torch
     crt = importlib.import_module(bench.PKG)
@@ -49,8 +50,14 @@ def main():
         sf = crt.SceneFile(f, folder)
         flat = sf.flatten()
         configs = [("literal", 1, None)] + [(f"default tail {t}", 0, t) for t in args.tails.split(",")]
-        for label, trav, tail in configs:
+        if args.chunks:
+            configs = [(f"{lab} chunks {ch}", trav, tail, ch) for (lab, trav, tail) in configs[1:] for ch in args.chunks.split(",")]
+        else:
+            configs = [(lab, trav, tail, "") for (lab, trav, tail) in configs]
+        for label, trav, tail, chunks in configs:
             env = {}
+            if chunks:
+                os.environ["CRT_DEVICE_CHUNKS"] = chunks
             if tail is not None:  # "floor" or "floor:cap" or "floor:cap:start"
                 parts = tail.split(":")
                 env = {"CRT_TAIL_ITERS": parts[0]}
@@ -58,6 +65,8 @@ def main():
                     env["CRT_TAIL_CAP"] = parts[1]
                 if len(parts) > 2:
                     env["CRT_TAIL_START"] = parts[2]
+                if len(parts) > 3:
+                    env["CRT_TAIL_SMALL"] = parts[3]
             ctx = ctx_with_env(crt, env)
             ctx.upload(flat, keepalive=sf)
             ctx.set_concurrency(1)
