@@ -804,14 +804,16 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
 //                 t < +inf and (b) the candidate with the smallest key, and folds them into the ray's running Closest
 //                 exactly as the in-order sequence of closest_offer calls would have.
 //
-// The walk.  A group of GW lanes (8 by default: four walks per warp) keeps a LIFO of node indices in shared memory.
+// The walk.  A group of GW lanes (GW = 32, a warp, by default) keeps a LIFO of node indices in shared memory.
 // One iteration pops up to GW nodes, one per lane; a lane loads its node, drops it when its whole subtree lies before
 // the hand-off cursor (already walked), tests the box (node_test: the reference's slab test + the conservative culling
 // of crt_device.cuh) and pushes both children of a passing inner node (first child = index + 1, second child = the
 // node's `b` word).  The passing leaves of an iteration are tested together, their triangle lists packed GW slots at a
 // time like tri_phase.  One iteration costs about two dependent memory round trips whatever its width, and a single
 // ray's frontier is rarely wider than a dozen nodes (a walk's critical path is the tree's depth), so a whole warp per
-// walk left most lanes idle: groups of 8 run four walks side by side at the same latency (measured: profiles/r2_tuning.md).
+// walk leaves most lanes idle.  Narrower groups (GW = 8 / 16: four / two walks per warp side by side) and a variant in
+// which eight walks of a warp shared one frontier were built and measured: neither raised the throughput, both
+// lengthened single walks (profiles/r2_tuning.md 2.1), so a walk gets the whole warp (GW = 32).
 // Every group runs the same loop; group-uniform branches use the group's own lane mask for their shuffles and votes.
 // ------------------------------------------------------------------------------------------------------------
 #define CRT_COOP_CAP 512    // LIFO entries per warp (2 KB), shared out between its groups
@@ -1157,353 +1159,6 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_co
   atomicAdd(&lv.stats[SHADOW ? 38 : 35], dbg_nodes);
   atomicAdd(&lv.stats[SHADOW ? 39 : 36], dbg_tris);
 #endif
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// K2c / K3c: k_wave -- k_coop's successor: EIGHT handed-off walks per warp share ONE frontier.
-//
-// A single walk's frontier is 4-8 nodes wide (profiles/r2_tuning.md 2.1), so a warp per walk leaves most lanes idle and
-// pays ~40 warp instructions per box test.  Here the warp's LIFO holds (walk slot, node) entries of up to CRT_WAVE_SLOTS
-// walks at once; one iteration pops 32 entries whatever walk they belong to, each lane tests its node against ITS
-// entry's ray (ray table in shared memory) and pushes that node's children tagged with the same slot.  The lanes run
-// one code path -- no divergence between walks -- and the frontier of eight walks fills the warp.  Exactness is the
-// same argument as k_coop's: by the nesting property the set of tested leaves does not depend on the order, shadow
-// answers are an OR, closest-hit candidates are ordered by their (leaf node, leaf reference) key within a mesh and the
-// meshes of a walk are taken one after the other.
-//   slot s is managed by lane s: it keeps the walk's itinerary (trav_step's order of events), its running Closest and
-//   the keyed partial result of the mesh in flight in registers, fetches the next record when the walk is done, and is
-//   the only writer of the slot's ray table.  A mesh walk of slot s is over when pending[s] (entries pushed - popped)
-//   returns to 0.  An occluded shadow walk is marked dead: its remaining entries are dropped as they are popped.
-// ------------------------------------------------------------------------------------------------------------
-#ifndef CRT_WAVE_SLOTS
-#define CRT_WAVE_SLOTS 8
-#endif
-#define CRT_WAVE_CAP 512     // LIFO entries per warp
-#define CRT_WAVE_WARPS 4
-#ifndef CRT_WAVE_MIN_BLOCKS
-#define CRT_WAVE_MIN_BLOCKS 6
-#endif
-#define CRT_WAVE_NODE_MASK 0x1FFFFFFFu  // 29 bits of node index, 3 bits of slot
-struct __align__(16) WarpWave {
-  uint32_t stack[CRT_WAVE_CAP];
-  float4 ro[CRT_WAVE_SLOTS];   // origin, w = distance to the light (shadow rays)
-  float4 rd[CRT_WAVE_SLOTS];   // direction, w = culling margin of the mesh in flight
-  float4 ri[CRT_WAVE_SLOTS];   // 1 / direction, w = culling limit (best finite t / the light)
-  uint4 meta[CRT_WAVE_SLOTS];  // x = ray flags, y = nodes of the mesh before this index are already walked, z = alive
-  int pending[CRT_WAVE_SLOTS];
-  uint32_t refbase[32], owner[32], leafidx[32];
-};
-
-template <bool SHADOW, bool PRIMARY, bool CULL>
-__global__ void __launch_bounds__(32 * CRT_WAVE_WARPS, CRT_WAVE_MIN_BLOCKS) k_wave(const DScene sc, const Frame fr, const Levels lv, const uint32_t level) {
-  constexpr uint32_t R = CRT_WAVE_SLOTS;
-  static_assert(R == 8, "3 slot bits in a LIFO entry");
-  __shared__ WarpWave s_ww[CRT_WAVE_WARPS];
-  WarpWave &ww = s_ww[threadIdx.x >> 5];
-  const uint32_t lane = lane_id();
-  const bool mgr = lane < R;
-  const uint32_t launch = SHADOW ? (uint32_t)CRT_MAX_LEVELS : level;
-  const uint32_t n_rec = min(lv.ovf_ctl[2u * launch], lv.ovf_cap);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && n_rec) atomicAdd(&lv.stats[SHADOW ? 33 : 32], (unsigned long long)n_rec);
-  if (mgr) {
-    ww.pending[lane] = 0;
-    ww.meta[lane] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  __syncwarp();
-
-  // manager state (meaningful in lanes < R)
-  bool busy = false, drained = false, in_mesh = false;
-  uint32_t id = 0, cur = 0, cend = 0, resume = 0, mref = 0, mend = 0, below = 0;
-  unsigned long long seen = 0ull;
-  float dist = 0.0f;
-  Ray ray;
-  ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
-  ray.flags = 0;
-  Closest cl;
-  closest_begin(cl);
-  CoopBest cb;
-  coop_best_reset(cb);
-  uint32_t sp = 0;  // warp-uniform
-
-  for (;;) {
-    // ---- A. managers: at most one step of their walk's life cycle ----
-    uint32_t root_push = CRT_INVALID;
-    if (mgr) {
-      if (!busy && !drained) {
-        const uint32_t r = atomicAdd(&lv.ovf_ctl[2u * launch + 1u], 1u);
-        if (r >= n_rec) {
-          drained = true;
-        } else {
-          const uint4 r0 = lv.ovf[3 * (size_t)r], r1 = lv.ovf[3 * (size_t)r + 1], r2 = lv.ovf[3 * (size_t)r + 2];
-          id = r0.x;
-          if (SHADOW) {
-            const uint32_t hit = id / sc.n_lights, light = id - hit * sc.n_lights;
-            const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
-            float contrib;
-            shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
-          } else if (PRIMARY) {
-            uint32_t row, col;
-            item_pixel(fr, sc, fr.item_begin + (id - lv.offset[0]), row, col);  // valid: the main kernel started this ray
-            primary_ray(fr.cam, sc.width, sc.height, row, col, ray.o, ray.d);
-          } else {
-            const float4 o = lv.ray_o[id - lv.offset[1]], d = lv.ray_d[id - lv.offset[1]];
-            ray.o = mk(o.x, o.y, o.z);
-            ray.d = mk(d.x, d.y, d.z);
-          }
-          ray_prepare(ray, PRIMARY);
-          cur = r0.y;
-          cend = r0.z;
-          resume = r0.w;
-          mref = r1.x;
-          mend = r1.y;
-          seen = (unsigned long long)r1.z | ((unsigned long long)r1.w << 32);
-          below = r2.x;
-          cl.best_t = __uint_as_float(r2.z);
-          cl.best_tri = r2.w;
-          cl.min_t = (cl.best_tri != CRT_INVALID && cl.best_t < CRT_INF) ? cl.best_t : CRT_INF;
-          const float lim = SHADOW ? shadow_limit(ray, dist) : cl.min_t;
-          ww.ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, dist);
-          ww.rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(r2.y));
-          ww.ri[lane] = make_float4(ray.inv.x, ray.inv.y, ray.inv.z, lim);
-          ww.meta[lane] = make_uint4(ray.flags, 0u, 1u, 0u);
-          in_mesh = false;
-          busy = true;
-        }
-      } else if (busy) {
-        if (in_mesh && ww.pending[lane] == 0) {  // the mesh walk of this slot is over
-          in_mesh = false;
-          if (SHADOW) {
-            if (ww.meta[lane].z == 0u) {  // an occluder was found: the first one ends the walk
-              lv.vis[id] = 0;
-              busy = false;
-            }
-          } else {
-            // = closest_offer over the mesh's candidates in key order (cf. coop_fold; cb is complete in this lane)
-            if (cb.fkey != CRT_KEY_NONE && cl.best_tri == CRT_INVALID) {
-              cl.best_tri = cb.ftri;
-              cl.best_t = cb.ft;
-            }
-            if (cb.key != CRT_KEY_NONE && cb.t < cl.min_t) {
-              cl.min_t = cb.t;
-              cl.best_t = cb.t;
-              cl.best_tri = cb.tri;
-            }
-          }
-        }
-        if (busy && !in_mesh) {
-          // one step of the itinerary (trav_step's order of events)
-          if (cur < cend) {
-            if (below) {
-              // (the rest of) a mesh tree: from the root of the tree whose node range contains cur (the meshes' ranges
-              // are consecutive and in mesh order); subtrees that end at or before cur are dropped by the walk
-              uint32_t lo_m = 0, hi_m = sc.n_meshes;
-              while (hi_m - lo_m > 1u) {
-                const uint32_t mid = (lo_m + hi_m) >> 1;
-                if (sc.meshes[mid].node_begin <= cur) lo_m = mid; else hi_m = mid;
-              }
-              const DMesh me = sc.meshes[lo_m];
-              if (cur >= me.node_begin && cur < me.node_end) {
-                root_push = me.node_begin;
-                float4 d4 = ww.rd[lane];
-                if (!CULL) d4.w = CRT_INF;
-                ww.rd[lane] = d4;
-                uint4 m4 = ww.meta[lane];
-                m4.y = cur;
-                ww.meta[lane] = m4;
-                coop_best_reset(cb);
-                in_mesh = true;
-              }
-              cur = cend;
-            } else {
-              // one step in the top-level tree (never culled)
-              const float4 lo = __ldg(&sc.nodes[2 * (size_t)cur]), hi = __ldg(&sc.nodes[2 * (size_t)cur + 1]);
-              const uint32_t a = __float_as_uint(lo.w);
-              const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
-              const bool pass = node_test<false>(lo, hi, ray, CRT_INF, CRT_INF, false);
-              cur = (pass || leaf) ? cur + 1u : a;
-              if (pass && leaf) {
-                mref = __float_as_uint(hi.w);
-                mend = mref + (a & ~CRT_LEAF_FLAG);
-                resume = cur;
-                cur = cend;
-                below = 1u;
-              }
-            }
-          } else if (mref != mend) {
-            const uint32_t m = __ldg(&sc.top_refs[mref++]);
-            const DMesh me = sc.meshes[m];
-            bool skip = SHADOW && sc.materials[me.material].type == 3u;  // shadow rays ignore refractive meshes (AccelerationStructure.cpp:67-71)
-            if (sc.dedup_meshes) {
-              const unsigned long long bit = 1ull << (m & 63u);
-              skip = skip || (seen & bit) != 0ull;
-              seen |= bit;
-            }
-            if (!skip) {
-              cur = me.node_begin;
-              cend = me.node_end;
-              float4 d4 = ww.rd[lane];
-              d4.w = CULL ? cull_margin_for(ray, me.cull_margin) : CRT_INF;
-              ww.rd[lane] = d4;
-            }
-          } else if (below) {
-            below = 0u;
-            cur = resume;
-            cend = sc.top_end;
-          } else {
-            if (SHADOW) {
-              lv.vis[id] = 1;
-            } else {
-              lv.hit_tri[id] = cl.best_tri;
-              lv.hit_t[id] = cl.best_t;
-            }
-            busy = false;
-          }
-        }
-      }
-    }
-    if (!__any_sync(CRT_FULL_MASK, mgr && (busy || !drained))) break;
-    __syncwarp();
-
-    // ---- B. pop up to 32 entries of whatever walks, test, push the children ----
-    // (close to capacity: one entry at a time, the LIFO then grows by at most one per step down a single path)
-    const uint32_t n = (CRT_WAVE_CAP - sp < 104u) ? (sp ? 1u : 0u) : (sp < 32u ? sp : 32u);
-    const bool have = lane < n;
-    uint32_t slot = 0, j = 0;
-    if (have) {
-      const uint32_t e = ww.stack[sp - 1u - lane];
-      slot = e >> 29;
-      j = e & CRT_WAVE_NODE_MASK;
-    }
-    sp -= n;
-    __syncwarp();
-    bool leaf_hit = false;
-    uint32_t a = 0, b = CRT_INVALID, cnt = 0;
-    Ray wr;
-    wr.o = wr.d = wr.inv = mk(0.f, 0.f, 0.f);
-    wr.flags = 0;
-    float wdist = 0.0f;
-    if (have) {
-      const uint4 m4 = ww.meta[slot];
-      if (m4.z) {  // entries of a dead walk are dropped
-        const float4 o4 = ww.ro[slot], d4 = ww.rd[slot], i4 = ww.ri[slot];
-        wr.o = mk(o4.x, o4.y, o4.z);
-        wr.d = mk(d4.x, d4.y, d4.z);
-        wr.inv = mk(i4.x, i4.y, i4.z);
-        wr.flags = m4.x;
-        wdist = o4.w;
-        const float4 lo = __ldg(&sc.nodes[2 * (size_t)j]), hi = __ldg(&sc.nodes[2 * (size_t)j + 1]);
-        a = __float_as_uint(lo.w);
-        b = __float_as_uint(hi.w);
-        const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
-        const uint32_t endj = leaf ? j + 1u : a;
-        if (endj > m4.y && node_test<CULL>(lo, hi, wr, d4.w, i4.w, SHADOW || i4.w < CRT_INF)) {
-          leaf_hit = leaf;
-          if (!leaf) cnt = (b != CRT_INVALID) ? 2u : 1u;
-        }
-      }
-      if (cnt != 1u) atomicAdd(&ww.pending[slot], (int)cnt - 1);  // entries of the slot: -1 popped, +cnt pushed
-    }
-    const uint32_t rootc = (mgr && root_push != CRT_INVALID) ? 1u : 0u;
-    if (rootc) atomicAdd(&ww.pending[lane], 1);
-    uint32_t incl = cnt + rootc;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t v = __shfl_up_sync(CRT_FULL_MASK, incl, d);
-      if (lane >= (uint32_t)d) incl += v;
-    }
-    const uint32_t total = __shfl_sync(CRT_FULL_MASK, incl, 31);
-    uint32_t at = sp + incl - cnt - rootc;
-    if (rootc) ww.stack[at++] = (lane << 29) | root_push;
-    if (cnt == 2u) ww.stack[at++] = (slot << 29) | b;  // second child below the first
-    if (cnt) ww.stack[at] = (slot << 29) | (j + 1u);
-    sp += total;
-    __syncwarp();
-
-    // ---- C. triangles of the leaves that passed, packed across the warp (cf. tri_phase) ----
-    if (__any_sync(CRT_FULL_MASK, leaf_hit)) {
-      const uint32_t tcnt = leaf_hit ? (a & ~CRT_LEAF_FLAG) : 0u;
-      uint32_t tincl = tcnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(CRT_FULL_MASK, tincl, d);
-        if (lane >= (uint32_t)d) tincl += v;
-      }
-      const uint32_t ttotal = __shfl_sync(CRT_FULL_MASK, tincl, 31);
-      const uint32_t tstart = tincl - tcnt;
-      if (tcnt) {
-        ww.refbase[lane] = b - tstart;
-        ww.leafidx[lane] = j;
-      }
-      for (uint32_t base = 0; base < ttotal; base += 32u) {
-        const bool in_win = tcnt && tstart < base + 32u && tstart + tcnt > base;
-        const uint32_t hp = (in_win && tstart > base) ? tstart - base : 0u;
-        const uint32_t heads = __reduce_or_sync(CRT_FULL_MASK, in_win ? (1u << hp) : 0u);
-        if (in_win) ww.owner[hp] = lane;
-        __syncwarp();
-        const uint32_t g = base + lane;
-        uint32_t own = 0;
-        if (g < ttotal) own = ww.owner[31 - __clz(heads & (CRT_FULL_MASK >> (31u - lane)))];  // slot 0 of a window is always a head
-        // the owner's ray (every lane holds the ray of the entry it popped)
-        const uint32_t oslot = __shfl_sync(CRT_FULL_MASK, slot, own);
-        Ray tr;
-        tr.o = mk(__shfl_sync(CRT_FULL_MASK, wr.o.x, own), __shfl_sync(CRT_FULL_MASK, wr.o.y, own), __shfl_sync(CRT_FULL_MASK, wr.o.z, own));
-        tr.d = mk(__shfl_sync(CRT_FULL_MASK, wr.d.x, own), __shfl_sync(CRT_FULL_MASK, wr.d.y, own), __shfl_sync(CRT_FULL_MASK, wr.d.z, own));
-        tr.flags = PRIMARY ? 8u : 0u;
-        const float tdist = __shfl_sync(CRT_FULL_MASK, wdist, own);
-        bool hit = false;
-        float t = 0.0f;
-        uint32_t tri = 0;
-        unsigned long long key = 0ull;
-        if (g < ttotal) {
-          const uint32_t ref = ww.refbase[own] + g;
-          tri = __ldg(&sc.leaf_refs[ref]);
-          const float4 t0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
-          const float4 t1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
-          const float4 t2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
-          V3 p;
-          hit = triangle_test(t0, t1, t2, tr, t, p);
-          if (SHADOW) hit = hit && vlen(vsub(p, tr.o)) <= tdist;
-          key = ((unsigned long long)ww.leafidx[own] << 32) | ref;
-        }
-        uint32_t hm = __ballot_sync(CRT_FULL_MASK, hit);
-        if (SHADOW) {
-          if (hit) {  // dead: the slot's remaining entries are dropped, its manager reports "occluded"
-            uint4 m4 = ww.meta[oslot];
-            m4.z = 0u;
-            ww.meta[oslot] = m4;
-          }
-        } else {
-          while (hm) {  // hand every candidate to its slot's manager
-            const int l = __ffs(hm) - 1;
-            hm &= hm - 1u;
-            const uint32_t s_l = __shfl_sync(CRT_FULL_MASK, oslot, l);
-            const float t_l = __shfl_sync(CRT_FULL_MASK, t, l);
-            const unsigned long long k_l = __shfl_sync(CRT_FULL_MASK, key, l);
-            const uint32_t tri_l = __shfl_sync(CRT_FULL_MASK, tri, l);
-            if (lane == s_l) {
-              if (k_l < cb.fkey) {
-                cb.fkey = k_l;
-                cb.ft = t_l;
-                cb.ftri = tri_l;
-              }
-              if (t_l < CRT_INF && (t_l < cb.t || (t_l == cb.t && k_l < cb.key))) {
-                cb.t = t_l;
-                cb.key = k_l;
-                cb.tri = tri_l;
-                if (CULL && t_l < ww.ri[lane].w) {  // tighten the slot's culling limit
-                  float4 i4 = ww.ri[lane];
-                  i4.w = t_l;
-                  ww.ri[lane] = i4;
-                }
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
-    }
-    __syncwarp();
-  }
 }
 
 // K3b: the light loop of RayTracer::calculateDiffusion (RayTracer.cpp:308-330): per diffuse hit, walk the lights IN

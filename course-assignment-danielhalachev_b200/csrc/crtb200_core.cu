@@ -26,9 +26,6 @@ using namespace crtd;
 #ifndef CRT_REFILL
 #define CRT_REFILL 8  // refill a warp when at least this many lanes are idle
 #endif
-#ifndef CRT_COOP_KIND
-#define CRT_COOP_KIND 1  // hand-off pass: 0 = k_coop (a group of lanes per walk), 1 = k_wave (eight walks per warp share a frontier)
-#endif
 #ifndef CRT_LOOP_MODE
 #define CRT_LOOP_MODE 2  // 0 = while-while, 1 = merged loop, 2 = node phase + warp-cooperative triangle phase (crt_kernels.cuh)
 #endif
@@ -267,11 +264,7 @@ int crtb200_create(int device, crtb200_ctx **out) {
   c->blocks_closest = std::max(1, occ) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
-#if CRT_COOP_KIND == 1
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<true, false, true>, 32 * CRT_WAVE_WARPS, 0);
-#else
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_coop<true, false, true, CRT_COOP_GROUP>, 32 * CRT_COOP_WARPS, 0);
-#endif
   c->blocks_coop = std::max(1, occ) * c->sm_count;
   if (const char *env = getenv("CRT_BLOCKS_PER_SM")) {  // tuning only (tools/): resident persistent CTAs per SM
     const int b = atoi(env);
@@ -946,25 +939,14 @@ static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const 
 
 template <bool CULL>
 static void launch_coop_closest(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, cudaStream_t st) {
-#if CRT_COOP_KIND == 1
-  if (primary)
-    k_wave<false, true, CULL><<<c->blocks_coop, 32 * CRT_WAVE_WARPS, 0, st>>>(c->sc, fr, lv, level);
-  else
-    k_wave<false, false, CULL><<<c->blocks_coop, 32 * CRT_WAVE_WARPS, 0, st>>>(c->sc, fr, lv, level);
-#else
   if (primary)
     k_coop<false, true, CULL, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
   else
     k_coop<false, false, CULL, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
-#endif
 }
 template <bool CULL>
 static void launch_coop_shadow(crtb200_ctx *c, const Frame &fr, const Levels &lv, cudaStream_t st) {
-#if CRT_COOP_KIND == 1
-  k_wave<true, false, CULL><<<c->blocks_coop, 32 * CRT_WAVE_WARPS, 0, st>>>(c->sc, fr, lv, 0);
-#else
   k_coop<true, false, CULL, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, 0);
-#endif
 }
 
 // Host destinations of crtb200_render: each chunk's band of rows is copied back on the chunk's own stream right after
