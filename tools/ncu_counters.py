@@ -24,7 +24,8 @@ M = {
     "wr": "dram__bytes_write.sum",
     "l2": "lts__t_sector_hit_rate.pct",
     "l1": "l1tex__t_sector_hit_rate.pct",
-    "issue": "smsp__issue_active.avg.pct",
+    "issue": "sm__inst_issued.avg.pct_of_peak_sustained_active",
+    "ipc": "sm__inst_executed.avg.per_cycle_elapsed",
     "thr": "smsp__thread_inst_executed_per_inst_executed.ratio",
     "occ": "sm__warps_active.avg.pct_of_peak_sustained_active",
     "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -53,7 +54,7 @@ def load(rep):
         name = d.get("Kernel Name", "")
         rec = {"name": name, "ms": to_ms(d[M["t"]], u[M["t"]]),
                "dram": to_bytes(d[M["rd"]], u[M["rd"]]) + to_bytes(d[M["wr"]], u[M["wr"]])}
-        for k in ("l2", "l1", "issue", "thr", "occ", "dram_pct", "lsb"):
+        for k in ("l2", "l1", "issue", "ipc", "thr", "occ", "dram_pct", "lsb"):
             try:
                 rec[k] = float(d[M[k]].replace(",", ""))
             except Exception:
@@ -67,17 +68,17 @@ def group(launches, main, frames):
     sel = []
     take_coop = False
     for l in launches:
-        if l["name"].startswith(main):
+        if (main + "<") in l["name"]:
             sel.append(l)
             take_coop = True
-        elif l["name"].startswith("k_coop") and take_coop:
+        elif "k_coop<" in l["name"] and take_coop:
             sel.append(l)
             take_coop = False
-        elif not l["name"].startswith("k_coop"):
+        elif "k_coop<" not in l["name"]:
             take_coop = False
     if not sel:
         return None
-    mains = [l for l in sel if l["name"].startswith(main)]
+    mains = [l for l in sel if (main + "<") in l["name"]]
     w = sum(l["ms"] for l in mains)
 
     def wmean(k):
@@ -87,7 +88,7 @@ def group(launches, main, frames):
     return {"dram_bytes": sum(l["dram"] for l in sel) / frames, "kernel_ms": sum(l["ms"] for l in sel) / frames,
             "main_kernel_ms": w / frames, "launches_per_frame": len(sel) / frames,
             "l2_hit": wmean("l2"), "l1_hit": wmean("l1"), "issue_slot_util": wmean("issue"), "warp_exec_eff": wmean("thr"),
-            "achieved_occupancy": wmean("occ"), "dram_throughput_pct_of_peak": wmean("dram_pct"), "long_scoreboard": wmean("lsb")}
+            "achieved_occupancy": wmean("occ"), "ipc_per_sm": wmean("ipc"), "dram_throughput_pct_of_peak": wmean("dram_pct"), "long_scoreboard": wmean("lsb")}
 
 
 def main():
