@@ -199,7 +199,7 @@ struct crtb200_ctx {
     }
   };
   std::vector<QueueSet> sets;
-  uint32_t concurrency = 6;  // chunks of a host-bound frame in flight (tools/e2e_time.py: 4.93 ms at 6 vs 5.09 at 4 for the 4K frame)
+  uint32_t concurrency = 4;  // chunk streams of a host-bound frame (tools/e2e_time.py, round 2: 4K frame 3.93 ms with 4 streams x 2 chunks, 4.43 with 6 x 2)
   cudaEvent_t fork_ev = nullptr;
   DevBuf<unsigned long long> stats_dev;
   uint32_t cap_items = 0;
