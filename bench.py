@@ -387,24 +387,33 @@ def ours_arm(args):
         parallelism = "tiles"  # BASELINE.json config 4: "tile-sharded over 1/2/4/8 GPUs" -- one frame, strong scaling
     opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n_rects, traversal=args.traversal)
     sharded = None
+    peer = None
     tiles_check = None
     if world > 1:
         mg = importlib.import_module(PKG + ".multigpu")
-        sharded = mg.ShardedRenderer(crt, ctx, torch, dist, dev)
-        # the assembled N-GPU frame must be bit-equal to the frame one GPU renders alone (rank 0 renders both)
+        sharded = mg.ShardedRenderer(crt, ctx, torch, dist, dev)  # NCCL gather of slabs + assembly on rank 0
+        peer = mg.PeerStoreRenderer(crt, ctx, torch, dist, dev, W, H)  # every rank stores into rank 0's frame (CUDA IPC)
+        if rank == 0:
+            pframe, pframe8 = peer.frame_tensors()
+        # both assembled N-GPU frames must be bit-equal to the frame one GPU renders alone (rank 0 renders all three)
         sharded.render(cam, max_depth=depth, traversal=args.traversal, frame=frame if rank == 0 else None, frame8=frame8 if rank == 0 else None)
+        peer.render(cam, max_depth=depth, traversal=args.traversal)
         torch.cuda.synchronize()
         if rank == 0:
             single = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
             single8 = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
             ctx.render_device(cam, opt, d_rgb=single.data_ptr(), d_rgb8=single8.data_ptr(), stream=stream)
             torch.cuda.synchronize()
-            neq = ((frame.view(torch.int32) != single.view(torch.int32)) & ~(torch.isnan(frame) & torch.isnan(single))).any(dim=2)
-            tiles_check = {"pixels_differing_from_single_gpu_frame": int(neq.sum().item()), "rgb8_equal": bool(torch.equal(frame8, single8)),
-                           "pixels": W * H}
+
+            def differing(a):
+                return int(((a.view(torch.int32) != single.view(torch.int32)) & ~(torch.isnan(a) & torch.isnan(single))).any(dim=2).sum().item())
+            tiles_check = {"pixels": W * H,
+                           "peer_store": {"pixels_differing_from_single_gpu_frame": differing(pframe), "rgb8_equal": bool(torch.equal(pframe8, single8))},
+                           "nccl_gather": {"pixels_differing_from_single_gpu_frame": differing(frame), "rgb8_equal": bool(torch.equal(frame8, single8))}}
             del single, single8
-            if tiles_check["pixels_differing_from_single_gpu_frame"] or not tiles_check["rgb8_equal"]:
-                raise SystemExit(f"[bench] tile-sharded frame differs from the single-GPU frame: {tiles_check}")
+            for k in ("peer_store", "nccl_gather"):
+                if tiles_check[k]["pixels_differing_from_single_gpu_frame"] or not tiles_check[k]["rgb8_equal"]:
+                    raise SystemExit(f"[bench] tile-sharded frame ({k}) differs from the single-GPU frame: {tiles_check}")
         dist.barrier()
 
     # frames partition (weak scaling, kept as an extra key at N > 1): every rank renders one frame of a static-camera
@@ -417,11 +426,20 @@ def ours_arm(args):
         gls = [[gflat[b][i] for i in range(world)] for b in range(2)] if rank == 0 else [None, None]
     host_frame = torch.empty((H, W, 3), dtype=torch.float32).pin_memory() if (world > 1 and rank == 0) else None
 
-    def step_tiles(to_host=False):
+    use_peer = args.tile_transport == "peer"
+
+    def step_tiles_gather(to_host=False):
         sharded.render(cam, max_depth=depth, traversal=args.traversal, frame=frame if rank == 0 else None,
                        frame8=frame8 if rank == 0 else None)
         if to_host and rank == 0:
             host_frame.copy_(frame, non_blocking=True)
+
+    def step_tiles_peer(to_host=False):
+        peer.render(cam, max_depth=depth, traversal=args.traversal)
+        if to_host and rank == 0:
+            host_frame.copy_(pframe, non_blocking=True)
+
+    step_tiles = step_tiles_peer if use_peer else step_tiles_gather
 
     def step_frames(k):
         b = k & 1
@@ -513,6 +531,7 @@ def ours_arm(args):
     # timed region (all ranks take part: the gather is a collective); device events, max over ranks
     e2e_multi_ms = None
     frames_extra = None
+    other_extra = None
     if tiles_mode:
         a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
@@ -524,6 +543,14 @@ def ours_arm(args):
         torch.cuda.synchronize()
         dist.barrier()
         e2e_multi_ms = max_over_ranks(a.elapsed_time(b2)) / args.steps
+        # extra key: the other transport of the same tile split
+        other = step_tiles_gather if use_peer else step_tiles_peer
+        for k in range(3):
+            other()
+        o_ms, _ = timed_per_step(other, args.steps)
+        o_per = max_over_ranks(sum(o_ms)) / args.steps
+        other_extra = {"transport": "nccl_gather" if use_peer else "peer_store", "value": rays_step / (o_per * 1e-3) / 1e6, "unit": "Mrays/s",
+                       "ms_per_step": o_per}
         # extra key: the frames partition on the same ranks (weak scaling: N frames per step)
         for k in range(3):
             step_frames(k)
@@ -557,7 +584,8 @@ def ours_arm(args):
     elif tiles_mode:
         e2e = {"value": rays_step / (e2e_multi_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_multi_ms,
                "h2d_bytes_per_step": (48 + 40 + 16 * n_rects) * world, "d2h_bytes_per_step": W * H * 12,
-               "api": "crtb200_render_device shard per rank -> NCCL gather -> crtb200_assemble_shards -> pinned host float RGB on rank 0"}
+               "api": ("crtb200_render_device shard per rank, stored straight into rank 0's frame (CUDA IPC over NVLink) -> pinned host float RGB on rank 0"
+                       if use_peer else "crtb200_render_device shard per rank -> NCCL gather -> crtb200_assemble_shards -> pinned host float RGB on rank 0")}
     else:
         e2e = None
 
@@ -624,7 +652,7 @@ def ours_arm(args):
             config5 = {"error": str(e)}
 
     per_frame_launches = kstats[-1]["kernel_launches"]
-    launches = (per_frame_launches + (1 if tiles_mode else 0)) * (world if frames_mode else 1)
+    launches = (per_frame_launches + (1 if (tiles_mode and not use_peer) else 0)) * (world if frames_mode else 1)
     line = {
         "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -634,7 +662,10 @@ def ours_arm(args):
                    "traversal": ("default: conservative culling + tail hand-off (results identical to the reference)" if args.traversal == 0
                                  else "literal visit-all itinerary"),
                    "parallelism": (f"frames{world}: one frame per GPU per step, rgb8 gathered to rank 0 (NCCL, overlapped)" if frames_mode
-                                   else f"tiles{world}: one frame, 8x4 tiles round-robin over {world} GPUs, float slabs gathered to rank 0 (NCCL) and assembled" if world > 1 else "single"),
+                                   else (f"tiles{world}: one frame, 8x4 tiles round-robin over {world} GPUs, every GPU's store kernel writes into rank 0's frame "
+                                         f"(peer memory over NVLink, CUDA IPC; one NCCL all-reduce as completion barrier)" if use_peer else
+                                         f"tiles{world}: one frame, 8x4 tiles round-robin over {world} GPUs, float slabs gathered to rank 0 (NCCL) and assembled")
+                                   if world > 1 else "single"),
                    "l2": ("each frame streams ~1 GB of queues through the 126 MB L2 (inputs larger than L2)" if frames_mode
                           else "flushed between steps (256 MiB fill)"),
                    "rays_per_step": rays_step, "chunks_in_flight": args.concurrency},
@@ -650,6 +681,8 @@ def ours_arm(args):
         line["literal_walk"] = literal
     if tiles_check:
         line["tiles_check"] = tiles_check
+    if other_extra:
+        line["tiles_other_transport"] = other_extra
     if frames_extra:
         line["frames_mode"] = frames_extra
     if config5:
@@ -814,6 +847,9 @@ def main():
     ap.add_argument("--parallelism", default="auto", choices=["auto", "frames", "tiles"],
                     help="N > 1: tiles (default) = one frame split by 8x4 tiles (strong scaling, config 4); frames = one frame per GPU per step (weak)")
     ap.add_argument("--no-config5", action="store_true", help="skip the synthetic_10M sub-record (N = 1)")
+    ap.add_argument("--tile-transport", default="peer", choices=["peer", "gather"],
+                    help="tiles, N > 1: peer = every rank's store kernel writes into rank 0's frame (CUDA IPC over NVLink); "
+                         "gather = compact slabs, one NCCL gather, crtb200_assemble_shards.  The other one is timed as an extra key")
     ap.add_argument("--concurrency", type=int, default=4, help="chunks of a frame in flight on separate streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--animation", type=int, default=0, help="F > 0: a step is the F-frame orbit animation (config 5), frames round-robin over GPUs")

@@ -96,7 +96,7 @@ class Options(C.Structure):
     _fields_ = [("max_depth", C.c_uint32), ("shadow_bias", C.c_float), ("reflection_bias", C.c_float),
                 ("refraction_bias", C.c_float), ("n_rects", C.c_uint32), ("rects", C.POINTER(Rect)),
                 ("traversal", C.c_uint32), ("count_work", C.c_uint32), ("shard_index", C.c_uint32),
-                ("shard_count", C.c_uint32)]
+                ("shard_count", C.c_uint32), ("shard_full_frame", C.c_uint32)]
 
 
 class Hit(C.Structure):
@@ -164,6 +164,11 @@ def core() -> C.CDLL:
         lib.crtb200_set_concurrency.argtypes = [C.c_void_p, C.c_uint32]
         lib.crtb200_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         lib.crtb200_shard_items.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        lib.crtb200_ipc_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+        lib.crtb200_ipc_free.argtypes = [C.c_int, C.c_void_p]
+        lib.crtb200_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+        lib.crtb200_ipc_open.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.crtb200_ipc_close.argtypes = [C.c_int, C.c_void_p]
         lib.crtb200_generate_rays.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_void_p]
         lib.crtb200_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.crtb200_device_count.argtypes = [C.POINTER(C.c_int)]
@@ -280,7 +285,7 @@ def write_ppm(path: str, rgb: np.ndarray) -> None:
 
 # ---- CUDA core ---------------------------------------------------------------------------------------------------
 def make_options(max_depth: int = 5, rects=None, n_rects: int = 0, traversal: int = 0, count_work: int = 0,
-                 shard_index: int = 0, shard_count: int = 1, bias: float = 1e-4) -> Options:
+                 shard_index: int = 0, shard_count: int = 1, bias: float = 1e-4, shard_full_frame: bool = False) -> Options:
     o = Options()
     o.max_depth = max_depth
     o.shadow_bias = o.reflection_bias = o.refraction_bias = bias
@@ -290,7 +295,38 @@ def make_options(max_depth: int = 5, rects=None, n_rects: int = 0, traversal: in
     o.count_work = int(count_work)
     o.shard_index = shard_index
     o.shard_count = shard_count
+    o.shard_full_frame = 1 if shard_full_frame else 0
     return o
+
+
+def ipc_alloc(device: int, nbytes: int) -> int:
+    """A whole cudaMalloc allocation on `device` (zeroed), exportable with ipc_export."""
+    p = C.c_void_p()
+    _check_core(core().crtb200_ipc_alloc(device, nbytes, C.byref(p)))
+    return p.value
+
+
+def ipc_free(device: int, d_ptr: int) -> None:
+    _check_core(core().crtb200_ipc_free(device, d_ptr))
+
+
+def ipc_export(d_ptr: int) -> bytes:
+    """64-byte CUDA IPC handle of a cudaMalloc allocation of this process (crtb200_ipc_export)."""
+    buf = (C.c_uint8 * 64)()
+    _check_core(core().crtb200_ipc_export(d_ptr, buf))
+    return bytes(buf)
+
+
+def ipc_open(device: int, handle: bytes) -> int:
+    """Maps another process's allocation on `device`; returns the device pointer (crtb200_ipc_open)."""
+    buf = (C.c_uint8 * 64)(*handle)
+    p = C.c_void_p()
+    _check_core(core().crtb200_ipc_open(device, buf, C.byref(p)))
+    return p.value
+
+
+def ipc_close(device: int, d_ptr: int) -> None:
+    _check_core(core().crtb200_ipc_close(device, d_ptr))
 
 
 class Context:

@@ -1387,6 +1387,8 @@ int crtb200_render_device(crtb200_ctx *c, const crtb200_camera *cam, const crtb2
   const uint32_t shard_count = o->shard_count ? o->shard_count : 1;
   c->last = crtb200_stats{};
   c->last_pending = true;
+  if (shard_count > 1 && o->shard_full_frame)  // the shard's pixels at their place in a full frame (peer-mapped, crtb200_ipc_open)
+    return enqueue_frame(c, cam, o, d_rgb_out, d_rgb8_out, nullptr, nullptr, (cudaStream_t)stream, true);
   if (shard_count > 1) {
     // sharded: d_rgb_out is the shard's compact slab (crtb200_shard_items x 3 floats), see crtb200_assemble_shards
     if (d_rgb8_out) return fail(CRTB200_ERR_ARG, "sharded rendering writes a float slab only");
@@ -1415,6 +1417,42 @@ int crtb200_shard_items(crtb200_ctx *c, uint32_t shard_count, uint32_t *items) {
   if (!c->have_scene) return fail(CRTB200_ERR_STATE, "no scene uploaded");
   const uint32_t tiles = ((c->sc.width + 7) / 8) * ((c->sc.height + 3) / 4);
   *items = ((tiles + shard_count - 1) / shard_count) * 32u;
+  return CRTB200_OK;
+}
+
+int crtb200_ipc_alloc(int device, size_t bytes, void **d_ptr_out) {
+  if (!d_ptr_out || bytes == 0) return fail(CRTB200_ERR_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMalloc(d_ptr_out, bytes));
+  CUDA_TRY(cudaMemset(*d_ptr_out, 0, bytes));
+  return CRTB200_OK;
+}
+int crtb200_ipc_free(int device, void *d_ptr) {
+  if (!d_ptr) return CRTB200_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaFree(d_ptr));
+  return CRTB200_OK;
+}
+int crtb200_ipc_export(void *d_ptr, uint8_t handle_out[CRTB200_IPC_HANDLE_BYTES]) {
+  if (!d_ptr || !handle_out) return fail(CRTB200_ERR_ARG, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == CRTB200_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, d_ptr));
+  std::memcpy(handle_out, &h, sizeof(h));
+  return CRTB200_OK;
+}
+int crtb200_ipc_open(int device, const uint8_t handle[CRTB200_IPC_HANDLE_BYTES], void **d_ptr_out) {
+  if (!handle || !d_ptr_out) return fail(CRTB200_ERR_ARG, "null argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return CRTB200_OK;
+}
+int crtb200_ipc_close(int device, void *d_ptr) {
+  if (!d_ptr) return CRTB200_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
   return CRTB200_OK;
 }
 

@@ -41,6 +41,66 @@ def assemble_host(slabs: np.ndarray, width: int, height: int) -> np.ndarray:
     return frame
 
 
+class PeerStoreRenderer:
+    """Per-rank helper for the tile split WITHOUT a gather: rank 0 owns the frame (float RGB + PPMColor bytes) and exports
+    it with CUDA IPC; every rank renders its shard with `shard_full_frame`, so its store kernel writes the pixels straight
+    into rank 0's frame over NVLink / NVSwitch.  One tiny NCCL all-reduce per frame is the completion barrier between
+    the ranks' streams.  The frame tensors must be whole cudaMalloc allocations (allocated here, before anything else
+    shares their block)."""
+
+    def __init__(self, crt, ctx, torch, dist, device, width: int, height: int):
+        self.crt, self.ctx, self.torch, self.dist, self.device = crt, ctx, torch, dist, device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.frame = self.frame8 = None
+        self._mapped = []
+        handles = torch.zeros((2, 64), dtype=torch.uint8, device=device)
+        if self.rank == 0:
+            # cudaMalloc directly (not torch's caching allocator): an IPC handle names a whole allocation
+            n = width * height * 3
+            self._own = [crt.ipc_alloc(device.index, n * 4), crt.ipc_alloc(device.index, n)]
+            self.d_rgb, self.d_rgb8 = self._own
+            import numpy as np
+            h = np.stack([np.frombuffer(crt.ipc_export(p), dtype=np.uint8) for p in self._own])
+            handles.copy_(torch.from_numpy(h.copy()))
+        dist.broadcast(handles, src=0)
+        if self.rank != 0:
+            hb = handles.cpu().numpy()
+            self.d_rgb = crt.ipc_open(device.index, bytes(hb[0]))
+            self.d_rgb8 = crt.ipc_open(device.index, bytes(hb[1]))
+            self._mapped = [self.d_rgb, self.d_rgb8]
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.width, self.height = width, height
+
+    def frame_tensors(self):
+        """rank 0: (float HxWx3, uint8 HxWx3) views of the frame the ranks store into"""
+        assert self.rank == 0
+        t = self.torch
+
+        class _Arr:  # minimal __cuda_array_interface__ holder
+            def __init__(s, ptr, shape, typestr):
+                s.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+        f = t.as_tensor(_Arr(self.d_rgb, (self.height, self.width, 3), "<f4"), device=self.device)
+        b = t.as_tensor(_Arr(self.d_rgb8, (self.height, self.width, 3), "|u1"), device=self.device)
+        return f, b
+
+    def render(self, camera, max_depth: int = 5, traversal: int = 0) -> None:
+        """Asynchronous on the current torch stream; after it (on rank 0's stream) the frame is complete."""
+        stream = self.torch.cuda.current_stream().cuda_stream
+        opt = self.crt.make_options(max_depth=max_depth, shard_index=self.rank, shard_count=self.world, traversal=traversal,
+                                    shard_full_frame=True)
+        self.ctx.render_device(camera, opt, d_rgb=self.d_rgb, d_rgb8=self.d_rgb8, stream=stream)
+        self.dist.all_reduce(self._flag)  # completion barrier: rank 0's stream continues when every rank has stored
+
+    def close(self):
+        for p in self._mapped:
+            self.crt.ipc_close(self.device.index, p)
+        self._mapped = []
+        if self.rank == 0 and getattr(self, "_own", None):
+            for p in self._own:
+                self.crt.ipc_free(self.device.index, p)
+            self._own = None
+
+
 class ShardedRenderer:
     """Per-rank helper: render this rank's shard, gather on rank 0, assemble.  `ctx` is a crt.Context with the scene
     uploaded on this rank's GPU; `dist` is an initialised torch.distributed NCCL group (world_size = shard count)."""

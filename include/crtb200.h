@@ -165,6 +165,10 @@ typedef struct crtb200_options {
                        /* 2 = count the tests the production kernels really perform                             */
   /* tile sharding (multi-GPU): render only tile blocks b with b % shard_count == shard_index; 0/1 = all */
   uint32_t shard_index, shard_count;
+  /* crtb200_render_device with shard_count > 1: 0 = write the shard's pixels compactly (a slab, for an NCCL gather +    */
+  /* crtb200_assemble_shards); 1 = write them at their place in a FULL frame -- d_rgb_out / d_rgb8_out then usually    */
+  /* point at the gathering rank's frame, mapped with crtb200_ipc_open: the store kernel does the transfer (NVLink)   */
+  uint32_t shard_full_frame;
 } crtb200_options;
 
 /* Primary-ray closest hit, the record the parity gate compares (mesh index, mesh-local triangle index, t). */
@@ -248,6 +252,16 @@ int crtb200_last_stats(crtb200_ctx *ctx, crtb200_stats *stats);
  * slabs can be all-gathered / gathered with NCCL); d_rgb8_out must be NULL.  crtb200_assemble_shards scatters
  * shard_count consecutive slabs back into a full frame (and/or PPMColor bytes) on the gathering rank. */
 int crtb200_shard_items(crtb200_ctx *ctx, uint32_t shard_count, uint32_t *items);
+/* One process per GPU without a gather: the gathering rank exports its frame buffer (cudaIpcGetMemHandle, 64 bytes to
+ * ship to the other ranks by any means), the others map it and render their shard straight into it with
+ * options.shard_full_frame = 1.  Completion still needs a barrier between the ranks' streams (e.g. one tiny NCCL
+ * all-reduce).  d_ptr must be the base of a cudaMalloc allocation of the exporting process. */
+#define CRTB200_IPC_HANDLE_BYTES 64
+int crtb200_ipc_alloc(int device, size_t bytes, void **d_ptr_out); /* a whole cudaMalloc allocation, exportable */
+int crtb200_ipc_free(int device, void *d_ptr);
+int crtb200_ipc_export(void *d_ptr, uint8_t handle_out[CRTB200_IPC_HANDLE_BYTES]);
+int crtb200_ipc_open(int device, const uint8_t handle[CRTB200_IPC_HANDLE_BYTES], void **d_ptr_out);
+int crtb200_ipc_close(int device, void *d_ptr);
 int crtb200_assemble_shards(crtb200_ctx *ctx, const float *d_slabs, uint32_t shard_count, float *d_rgb_out,
                             uint8_t *d_rgb8_out, void *stream);
 

@@ -48,7 +48,7 @@ def test_struct_layouts_match_header(built):
     # sizes the C compiler gives the ABI structs (x86-64): guards the ctypes mirrors in the package
     assert C.sizeof(built.KdNode) == 40 and C.sizeof(built.Mesh) == 36 and C.sizeof(built.Material) == 28
     assert C.sizeof(built.Texture) == 48 and C.sizeof(built.Light) == 16 and C.sizeof(built.Camera) == 48
-    assert C.sizeof(built.Rect) == 16 and C.sizeof(built.Hit) == 12 and C.sizeof(built.Options) == 48
+    assert C.sizeof(built.Rect) == 16 and C.sizeof(built.Hit) == 12 and C.sizeof(built.Options) == 56
     assert C.sizeof(built.Stats) == 136 and C.sizeof(built.Scene) == 224
 
 

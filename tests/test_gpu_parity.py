@@ -431,3 +431,22 @@ def test_reference_binary_with_b200_binding_writes_the_same_ppm(name, built, ob,
             continue  # ... which is the right answer there
         assert r.returncode == 0, r.stderr[-2000:]
         assert open(out, "rb").read() == want, f"{name}: PPM of the reference + B200 binding differs from the reference's own"
+
+
+def test_shards_written_in_place_make_the_same_frame(gpu, loaded, crt):
+    """options.shard_full_frame: each tile shard is stored at its place in ONE full frame (what the ranks of a multi-
+    process run do into rank 0's IPC-mapped frame); three shards == the unsharded frame, f32 and PPMColor bytes."""
+    torch = pytest.importorskip("torch")
+    sf, flat, _, _ = loaded["hw11_room"]
+    gpu.upload(flat, keepalive=sf)
+    full, full8, _, _ = gpu.render(sf.camera(), crt.make_options(), want_rgb8=True)
+    H, W = sf.info.height, sf.info.width
+    out = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+    out8 = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(3):
+        gpu.render_device(sf.camera(), crt.make_options(shard_index=r, shard_count=3, shard_full_frame=True),
+                          d_rgb=out.data_ptr(), d_rgb8=out8.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert same_f32(out.cpu().numpy(), full).all()
+    assert np.array_equal(out8.cpu().numpy(), full8)
