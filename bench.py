@@ -847,9 +847,9 @@ def main():
     ap.add_argument("--parallelism", default="auto", choices=["auto", "frames", "tiles"],
                     help="N > 1: tiles (default) = one frame split by 8x4 tiles (strong scaling, config 4); frames = one frame per GPU per step (weak)")
     ap.add_argument("--no-config5", action="store_true", help="skip the synthetic_10M sub-record (N = 1)")
-    ap.add_argument("--tile-transport", default="peer", choices=["peer", "gather"],
-                    help="tiles, N > 1: peer = every rank's store kernel writes into rank 0's frame (CUDA IPC over NVLink); "
-                         "gather = compact slabs, one NCCL gather, crtb200_assemble_shards.  The other one is timed as an extra key")
+    ap.add_argument("--tile-transport", default="gather", choices=["gather", "peer"],
+                    help="tiles, N > 1: gather (default) = compact slabs, one NCCL gather over NVLink, crtb200_assemble_shards; "
+                         "peer = every rank's store kernel writes into rank 0's frame (CUDA IPC).  The other one is timed as an extra key")
     ap.add_argument("--concurrency", type=int, default=4, help="chunks of a frame in flight on separate streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--animation", type=int, default=0, help="F > 0: a step is the F-frame orbit animation (config 5), frames round-robin over GPUs")
