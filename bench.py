@@ -12,15 +12,24 @@ is quoted on that fits one GPU.
              (crtb200_render_device); per-step CUDA events on the launching stream, L2 flushed between steps
   e2e        the same metric through crtb200_render with HOST buffers: camera + options in, the float colour buffer
              (what RayTracer::render returns) copied back to pinned host memory inside the timed region
-  roofline   dominant traversal kernel: algorithmic bytes (32 B/node test + 52 B/triangle test + 64 B/ray, counted
-             under the reference's visit-all rule) / its CUDA-event duration, vs the measured HBM copy peak
-  cpu_baseline  the UNMODIFIED reference (oracle/_ref/crt_ref) on this box's host cores, bounded sample
+  roofline   dominant traversal launch group (k_shadow + its k_coop, or k_closest): the DRAM bytes it really moves
+             (ncu dram__bytes_read + write of the same sources, profiles/ncu_counters.json) / its CUDA-event time in
+             THIS run, vs the measured HBM copy peak; L2 / L1 hit rates, issue-slot use and warp execution efficiency
+             from the same capture; the SURVEY 8(d) byte model (visit-all and executed) under `byte_model`
+  config5    synthetic_10M (10 M triangles) on the same GPU: a static 1080p frame and the 60-frame orbit
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/crt_ref) on this box's host cores, one full frame, its pixels and
+             ray counts compared with ours; --impl reference: steps + warmup full frames of the same binary
+  literal_walk  the reference's visit-all itinerary (traversal = 1) beside the default, with the pixel difference (0)
 
-N > 1 (torchrun), scene replicated per GPU, two partitions:
-  --parallelism frames (default)  every rank renders one frame of the sequence per step, PPMColor bytes gathered to rank 0
+N > 1 (torchrun), scene replicated per GPU:
+  tiles (default)                 one frame, 8x4-pixel tiles dealt round-robin, float slabs gathered to rank 0 over NCCL
+                                  and scattered into the frame.  Strong scaling: total work fixed.  The assembled frame is
+                                  checked bit-equal to the single-GPU frame before timing (tiles_check).  --tile-transport
+                                  peer stores straight into rank 0's frame (CUDA IPC) instead; the other transport is timed
+                                  as `tiles_other_transport`, the frames partition as `frames_mode`.
+  --parallelism frames            every rank renders one frame of the sequence per step, PPMColor bytes gathered to rank 0
                                   over NCCL overlapped with the next render.  Weak scaling: per-GPU work fixed.
-  --parallelism tiles             one frame, 8x4-pixel tiles dealt round-robin, float slabs gathered to rank 0 and
-                                  scattered into the frame.  Strong scaling: total work fixed.
+  --animation F                   config 5's orbit: frame f on rank f % N, frames gathered to rank 0.
 """
 from __future__ import annotations
 

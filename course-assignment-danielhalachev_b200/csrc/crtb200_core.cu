@@ -1251,6 +1251,8 @@ static int collect_stats_one(crtb200_ctx *c, bool timed) {
       if (c->kev_kind[k] == 1 || c->kev_kind[k] == 3) c->last.shadow_ms += kms;
       if (c->kev_kind[k] == 2) c->last.coop_closest_ms += kms;
       if (c->kev_kind[k] == 3) c->last.coop_shadow_ms += kms;
+      if (getenv("CRT_KERNEL_TIMES"))  // tools: one line per traversal launch of the frame, in launch order
+        fprintf(stderr, "[kernel times] %s %.3f ms\n", c->kev_kind[k] == 0 ? "k_closest" : c->kev_kind[k] == 1 ? "k_shadow" : "k_coop", kms);
     }
   }
   return CRTB200_OK;
