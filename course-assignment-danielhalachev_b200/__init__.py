@@ -113,7 +113,7 @@ class Stats(C.Structure):
                 ("device_ms", C.c_double), ("closest_ms", C.c_double), ("shadow_ms", C.c_double), ("total_ms", C.c_double),
                 ("kernel_launches", C.c_uint32), ("levels", C.c_uint32),
                 ("handoff_closest", C.c_uint64), ("handoff_shadow", C.c_uint64),
-                ("coop_closest_ms", C.c_double), ("coop_shadow_ms", C.c_double)]
+                ("coop_closest_ms", C.c_double), ("coop_shadow_ms", C.c_double), ("shadow_rays_zero_term", C.c_uint64)]
 
     def as_dict(self) -> dict:
         d = {n: getattr(self, n) for n, _ in self._fields_}

@@ -46,7 +46,7 @@ struct Levels {
   float4 *dq;         // diffuse queue, 3 x float4 per item: {P, bits(node)} {N, base.r} {base.g, base.b, -, -}
   uint8_t *vis;       // per (diffuse item, light): 1 = the light is visible from the hit
   uint32_t *counts;   // [CRT_MAX_LEVELS] rays per level; [CRT_MAX_LEVELS] = diffuse queue length
-  unsigned long long *stats;  // [0..3] rays by type, [4],[5] closest node / triangle tests, [6],[7] shadow, [32],[33] walks handed to k_coop
+  unsigned long long *stats;  // [0..3] rays by type, [4],[5] closest node / triangle tests, [6],[7] shadow, [32],[33] walks handed to k_coop, [40] shadow rays answered without a walk
   uint32_t offset[CRT_MAX_LEVELS + 1];
   // tail hand-off (k_coop): once the work queue of a traversal kernel is dry, the walks still running are written to
   // ovf[] (3 x uint4 per record) and finished one WARP per ray; tail_grace = 0 switches this off
@@ -56,6 +56,7 @@ struct Levels {
   uint32_t tail_iters;  // 0 = off; else tail_iters - 1 = the floor of the hand-off threshold (see tail_policy)
   uint32_t tail_start;  // the threshold's value when the queue of a large launch has just run dry (1024)
   uint32_t tail_small;  // launches of at most this many rays hand off at the floor from the start (see tail_policy)
+  uint32_t skip_zero_terms;  // 1 (default traversal): shadow rays whose light term is exactly zero are answered without a walk
 };
 
 enum { COMB_FINAL = 0, COMB_REFLECT = 1, COMB_FRESNEL = 2, COMB_COPY = 3 };
@@ -676,7 +677,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
   const uint32_t lane = lane_id();
   const uint32_t tail_start = COUNT ? CRT_INVALID : tail_policy(lv, total);
   bool active = false, exhausted = false, occluded = false, closed = false;
-  uint32_t slot = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0, dry_rounds = 0;
+  uint32_t slot = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0, dry_rounds = 0, n_moot = 0;
 #if CRT_PHASE_CLOCKS
   uint32_t ray_iters = 0;
 #endif
@@ -703,19 +704,36 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
         const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];
         float contrib;
         shadow_ray_setup(sc, fr, mk(q0.x, q0.y, q0.z), mk(q1.x, q1.y, q1.z), light, ray, dist, contrib);
-        ray_prepare(ray, false);
-        trav_begin(tv, sc);
-        t_limit = shadow_limit(ray, dist);
-        occluded = false;
         slot = hit * sc.n_lights + light;
-        active = true;
-        walk_iters = 0;
+        // A light term that is exactly zero needs no walk.  The reference traces the shadow ray of every (hit, light) pair
+        // (RayTracer.cpp:314-317) and then adds `direct * albedo` with direct = float(I) / area * max(0, L.N)
+        // (:313, :320-327): for a surface turned away from the light direct is +0, the term is (+-0, +-0, +-0) for any
+        // finite albedo / texel, and x + (+-0) == x bit for bit (the sum starts at +0): visible or not, the pixel is the
+        // same.  The pair still counts as a traced ray (ray counts are the reference's).  Not in the visit-all counting
+        // mode, which reproduces the reference's work.
+        bool moot = false;
+        if (COUNT != 1 && lv.skip_zero_terms && contrib == 0.0f) {
+          const float4 q2 = lv.dq[3 * (size_t)hit + 2];
+          const uint32_t nf = 0x7f800000u;
+          moot = (__float_as_uint(q1.w) & nf) != nf && (__float_as_uint(q2.x) & nf) != nf && (__float_as_uint(q2.y) & nf) != nf;
+        }
+        if (moot) {
+          lv.vis[slot] = 0;
+          n_moot++;
+        } else {
+          ray_prepare(ray, false);
+          trav_begin(tv, sc);
+          t_limit = shadow_limit(ray, dist);
+          occluded = false;
+          active = true;
+          walk_iters = 0;
 #if CRT_PHASE_CLOCKS
-        ray_iters = 0;
+          ray_iters = 0;
 #endif
-        if (MODE == 2) {
-          ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, dist);
-          ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
+          if (MODE == 2) {
+            ws->ro[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, dist);
+            ws->rd[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
+          }
         }
       }
     }
@@ -772,6 +790,12 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
     }
   }
   CRT_PC_FLUSH(16)
+  {
+    uint32_t m = n_moot;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m += __shfl_xor_sync(CRT_FULL_MASK, m, d);
+    if (lane == 0 && m) atomicAdd(&lv.stats[40], (unsigned long long)m);
+  }
   if (COUNT) {
     unsigned long long a = n_nodes, b = n_tris;
 #pragma unroll

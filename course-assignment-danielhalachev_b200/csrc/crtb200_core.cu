@@ -764,7 +764,7 @@ static int upload_one(crtb200_ctx *c, const crtb200_scene *s) {
   CUDA_TRY(cudaMemset(c->frame.p, 0, px * 3 * sizeof(float)));  // colorBuffer starts at (0,0,0), RayTracer.cpp:47-50
   CUDA_TRY(c->frame8.ensure(px * 3));
   CUDA_TRY(cudaMemset(c->frame8.p, 0, px * 3));
-  CUDA_TRY(c->stats_dev.ensure(40));
+  CUDA_TRY(c->stats_dev.ensure(48));
   c->mask_valid = false;
   c->cap_items = 0;
   c->have_scene = true;
@@ -874,6 +874,7 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     q.lv.tail_iters = 0;
     q.lv.tail_start = 1024;
     q.lv.tail_small = 0;
+    q.lv.skip_zero_terms = 0;
     q.lv.ray_o = q.ray_o.p;
     q.lv.ray_d = q.ray_d.p;
     q.lv.hit_tri = q.hit_tri.p;
@@ -1004,7 +1005,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   const int grid_simple = c->sm_count * 8;
 
   // frames after the first of a batch (crtb200_render_frames) keep accumulating into the same counters and time span
-  if (!batch_continuation) CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 40 * sizeof(unsigned long long), st));
+  if (!batch_continuation) CUDA_TRY(cudaMemsetAsync(c->stats_dev.p, 0, 48 * sizeof(unsigned long long), st));
 #if CRT_PHASE_CLOCKS
   CUDA_TRY(cudaMemsetAsync(c->stats_dev.p + 27, 0xFF, sizeof(unsigned long long), st));  // atomicMin slots
   CUDA_TRY(cudaMemsetAsync(c->stats_dev.p + 31, 0xFF, sizeof(unsigned long long), st));
@@ -1026,6 +1027,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     fr.n_items0 = std::min(c->cap_items, shard_items - begin);
     CUDA_TRY(cudaMemsetAsync(q.ctl.p, 0, q.ctl.n * sizeof(uint32_t), qs));
     q.lv.tail_iters = handoff ? (uint32_t)(c->tail_iters + 1) : 0u;
+    q.lv.skip_zero_terms = (o->traversal == 0 && o->count_work != 1) ? 1u : 0u;
     q.lv.tail_start = (uint32_t)c->tail_start;
     q.lv.tail_small = (uint32_t)c->tail_small;
     for (uint32_t l = 0; l < levels; l++) {
@@ -1171,6 +1173,7 @@ static int collect_stats(crtb200_ctx *c, bool timed) {
     c->last.triangle_tests_shadow += p->last.triangle_tests_shadow;
     c->last.handoff_closest += p->last.handoff_closest;
     c->last.handoff_shadow += p->last.handoff_shadow;
+    c->last.shadow_rays_zero_term += p->last.shadow_rays_zero_term;
     c->last.kernel_launches += p->last.kernel_launches;
   }
   CUDA_TRY(cudaSetDevice(c->device));
@@ -1178,7 +1181,7 @@ static int collect_stats(crtb200_ctx *c, bool timed) {
 }
 
 static int collect_stats_one(crtb200_ctx *c, bool timed) {
-  unsigned long long st[40];
+  unsigned long long st[48];
   CUDA_TRY(cudaMemcpy(st, c->stats_dev.p, sizeof(st), cudaMemcpyDeviceToHost));
 #if CRT_PHASE_CLOCKS
   for (int k = 0; k < 2; k++) {
@@ -1234,6 +1237,7 @@ static int collect_stats_one(crtb200_ctx *c, bool timed) {
   c->last.triangle_tests_shadow = st[7];
   c->last.handoff_closest = st[32];
   c->last.handoff_shadow = st[33];
+  c->last.shadow_rays_zero_term = st[40];
 #if CRT_COOP_STATS
   fprintf(stderr, "[coop stats] closest: %llu walks, %llu iterations, %llu box tests, %llu triangle tests | shadow: %llu walks, %llu iterations, %llu box tests, %llu triangle tests\n",
           st[32], st[34], st[35], st[36], st[33], st[37], st[38], st[39]);
@@ -1309,6 +1313,7 @@ static void add_stats(crtb200_stats &total, const crtb200_stats &s) {
   total.triangle_tests_shadow += s.triangle_tests_shadow;
   total.handoff_closest += s.handoff_closest;
   total.handoff_shadow += s.handoff_shadow;
+  total.shadow_rays_zero_term += s.shadow_rays_zero_term;
   total.device_ms += s.device_ms;
   total.closest_ms += s.closest_ms;
   total.shadow_ms += s.shadow_ms;

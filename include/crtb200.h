@@ -156,8 +156,9 @@ typedef struct crtb200_options {
   const crtb200_rect *rects;
   uint32_t traversal; /* 0 = DEFAULT: the reference's walk (KDTree.cpp:48-87, 127-166) minus the subtrees that provably  */
                       /*     cannot contribute (conservative culling with a per-mesh margin), long    */
-                      /*     walks finished by a group of lanes (tail hand-off).  Results are          */
-                      /*     identical to the reference's: hit ids, t, float RGB, ray counts.                         */
+                      /*     walks finished by a group of lanes (tail hand-off), shadow rays whose light */
+                      /*     term is exactly zero answered without a walk (3.9).  Results are identical to the        */
+                      /*     reference's: hit ids, t, float RGB, ray counts.                                          */
                       /* 1 = the reference's literal itinerary: every node whose box passes is visited, nothing is    */
                       /*     skipped or reordered (what count_work = 1 counts; the round-1 default).                  */
   uint32_t count_work; /* 0 = off; 1 = count node / triangle tests under the reference's visit-all rule (shadow  */
@@ -193,6 +194,9 @@ typedef struct crtb200_stats {
   /* spent there                                                                                                      */
   uint64_t handoff_closest, handoff_shadow;
   double coop_closest_ms, coop_shadow_ms;
+  /* shadow rays (included in rays_shadow) that were answered without a walk because their light term is exactly zero  */
+  /* whatever the visibility: surface turned away from the light, RayTracer.cpp:313-327                */
+  uint64_t shadow_rays_zero_term;
 } crtb200_stats;
 
 typedef struct crtb200_ctx crtb200_ctx;

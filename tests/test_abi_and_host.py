@@ -49,7 +49,7 @@ def test_struct_layouts_match_header(built):
     assert C.sizeof(built.KdNode) == 40 and C.sizeof(built.Mesh) == 36 and C.sizeof(built.Material) == 28
     assert C.sizeof(built.Texture) == 48 and C.sizeof(built.Light) == 16 and C.sizeof(built.Camera) == 48
     assert C.sizeof(built.Rect) == 16 and C.sizeof(built.Hit) == 12 and C.sizeof(built.Options) == 56
-    assert C.sizeof(built.Stats) == 136 and C.sizeof(built.Scene) == 224
+    assert C.sizeof(built.Stats) == 144 and C.sizeof(built.Scene) == 224
 
 
 def test_rectangle_grid_matches_reference_arithmetic(built):

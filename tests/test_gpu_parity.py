@@ -190,6 +190,9 @@ def test_default_traversal_equals_literal_walk(name, gpu, loaded, crt):
     assert sb["node_tests"] <= sa["node_tests"] and sb["triangle_tests"] <= sa["triangle_tests"]
     if name in ("hw14_small", "hw11_room", "hw07_scene0b"):
         assert sb["node_tests"] < sa["node_tests"]
+        assert sa["shadow_rays_zero_term"] == 0
+        if name != "hw11_room":  # (its diffuse surfaces are the room's walls: none is turned away from a light)
+            assert sb["shadow_rays_zero_term"] > 0
     # count_work = 1 counts the reference's visit-all work whatever `traversal` says
     _, _, _, sc1 = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=0, count_work=1))
     _, _, _, sc2 = gpu.render(sf.camera(), crt.make_options(rects=rects, n_rects=n, traversal=1, count_work=1))

@@ -1,10 +1,5 @@
 #!/usr/bin/env bash
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
-V=$PWD/course-assignment-danielhalachev_b200/csrc/variants
-for w in hw11_room; do
-echo "== $w (phase clocks build, hand-off off, then default)"
-CRT_CORE_LIB=$V/libcrtb200_pc.so CRT_WARP_DUMP=1 CRT_TAIL_ITERS=-1 python tools/profile_frame.py --workload $w --frames 2 --concurrency 1 2>&1 | tail -60
-CRT_CORE_LIB=$V/libcrtb200_pc.so CRT_WARP_DUMP=1 python tools/profile_frame.py --workload $w --frames 2 --concurrency 1 2>&1 | tail -60
-done > $O/r2q_phase.txt 2>&1
-cut -c1-330 $O/r2q_phase.txt
+timeout 1700 python -m pytest tests -m gpu -q --timeout 1500 -x > $O/r2t_pytest.log 2>&1; tail -3 $O/r2t_pytest.log
+timeout 900 python tools/r2_measure.py --workloads hw14_dragon_class,hw11_room,hw11_room_128,synthetic_10M,hw07_scene0b,hw12_textures --tails 16:8,-1 --shards 1,8 --json $O/r2t_matrix.json > $O/r2t_matrix.txt 2>&1; grep -v "^\[bench\]" $O/r2t_matrix.txt | cut -c1-215
