@@ -76,7 +76,9 @@ struct DScene {
   uint32_t top_begin, top_end;
   uint32_t width, height;
   float bg[3];
-  uint32_t dedup_meshes;  // 1 when n_meshes <= 64: per-ray visited-mesh bitmask is usable
+  uint32_t dedup_meshes;  // per-ray visited-mesh set: 1 = a 64-bit register (n_meshes <= 64), 2 = dedup_words words per
+                          // lane in dynamic shared memory (n_meshes <= 512), 0 = none (more meshes: every listing is walked)
+  uint32_t dedup_words;
 };
 
 struct DCamera {
@@ -283,7 +285,11 @@ struct Trav {
   float mu;               // culling margin of the tree being walked, in space units (+inf: top-level tree / culling off)
 };
 #define CRT_INF __int_as_float(0x7f800000)
+// visited-mesh bitset of scenes with more than 64 meshes: word w of thread t at crt_dyn_smem[w * blockDim.x + t]
+extern __shared__ uint32_t crt_dyn_smem[];
 CRT_DI void trav_begin(Trav &s, const DScene &sc) {
+  if (sc.dedup_meshes == 2u)
+    for (uint32_t w = 0; w < sc.dedup_words; w++) crt_dyn_smem[w * blockDim.x + threadIdx.x] = 0u;
   s.cur = sc.top_begin;
   s.cend = sc.top_end;
   s.resume = sc.top_end;
@@ -461,10 +467,15 @@ CRT_DI int trav_slow(Trav &s, const DScene &sc, const Ray &r) {
     const uint32_t m = __ldg(&sc.top_refs[s.mref++]);
     const DMesh me = sc.meshes[m];
     bool skip = SKIP_REFRACTIVE && sc.materials[me.material].type == 3u;
-    if (DEDUP && sc.dedup_meshes) {
+    if (DEDUP && sc.dedup_meshes == 1u) {
       const unsigned long long bit = 1ull << (m & 63u);
       skip = skip || (s.seen & bit) != 0ull;
       s.seen |= bit;
+    } else if (DEDUP && sc.dedup_meshes == 2u) {
+      uint32_t *w = crt_dyn_smem + (m >> 5) * blockDim.x + threadIdx.x;
+      const uint32_t bit = 1u << (m & 31u), old = *w;
+      skip = skip || (old & bit) != 0u;
+      *w = old | bit;
     }
     if (!skip) {
       s.cur = me.node_begin;

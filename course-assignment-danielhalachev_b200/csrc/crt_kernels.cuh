@@ -1031,8 +1031,8 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_co
         const uint32_t m = __ldg(&sc.top_refs[mref++]);
         const DMesh me = sc.meshes[m];
         bool skip = SHADOW && sc.materials[me.material].type == 3u;  // shadow rays ignore refractive meshes (AccelerationStructure.cpp:67-71)
-        if (sc.dedup_meshes) {
-          const unsigned long long bit = 1ull << (m & 63u);
+        if (sc.dedup_meshes == 1u) {  // (scenes with more than 64 meshes: the rest of a handed-off walk re-walks a mesh for
+          const unsigned long long bit = 1ull << (m & 63u);  //  every listing, like the reference; same result)
           skip = skip || (seen & bit) != 0ull;
           seen |= bit;
         }

@@ -757,7 +757,8 @@ static int upload_one(crtb200_ctx *c, const crtb200_scene *s) {
   d.width = s->width;
   d.height = s->height;
   for (int k = 0; k < 3; k++) d.bg[k] = s->background[k];
-  d.dedup_meshes = s->n_meshes <= 64 ? 1u : 0u;
+  d.dedup_meshes = s->n_meshes <= 64 ? 1u : (s->n_meshes <= 512 ? 2u : 0u);
+  d.dedup_words = d.dedup_meshes == 2u ? (s->n_meshes + 31u) / 32u : 0u;
 
   const size_t px = (size_t)s->width * s->height;
   CUDA_TRY(c->frame.ensure(px * 3));
@@ -929,13 +930,16 @@ static cudaEvent_t next_event(crtb200_ctx *c) {
   return c->kev[c->kev_used++];
 }
 
+// dynamic shared memory of the kernels that walk one ray per lane: the visited-mesh bitset of scenes with > 64 meshes
+static size_t dyn_smem(const crtb200_ctx *c, int block) { return (size_t)c->sc.dedup_words * (size_t)block * sizeof(uint32_t); }
+
 template <bool COUNT, bool CULL>
 static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, uint32_t *work,
                            cudaStream_t st) {
   if (primary)
-    k_closest<true, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
+    k_closest<true, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, level, work);
   else
-    k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, level, work);
+    k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, level, work);
 }
 
 template <bool CULL>
@@ -1065,15 +1069,15 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     }
     uint32_t *swork = q.work + CRT_MAX_LEVELS;
     if (o->count_work == 1)
-      k_shadow<1, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow<1, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), qs>>>(c->sc, fr, q.lv, swork);
     else if (o->count_work == 2 && cull)
-      k_shadow<2, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow<2, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), qs>>>(c->sc, fr, q.lv, swork);
     else if (o->count_work == 2)
-      k_shadow<2, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow<2, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), qs>>>(c->sc, fr, q.lv, swork);
     else if (cull)
-      k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), qs>>>(c->sc, fr, q.lv, swork);
     else
-      k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, qs>>>(c->sc, fr, q.lv, swork);
+      k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), qs>>>(c->sc, fr, q.lv, swork);
     if (handoff) {
       if (per_kernel) {
         cudaEventRecord(next_event(c), qs);
@@ -1545,7 +1549,7 @@ int crtb200_trace_rays(crtb200_ctx *c, const float *rays, uint32_t n, uint32_t r
     e = d_hits.ensure(n);
   }
   if (e == cudaSuccess) {
-    k_query<<<c->sm_count * 8, 256, 0, c->stream>>>(c->sc, d_rays.p, n, ray_type, d_dist.p, d_hits.p, d_occ.p);
+    k_query<<<c->sm_count * 8, 256, dyn_smem(c, 256), c->stream>>>(c->sc, d_rays.p, n, ray_type, d_dist.p, d_hits.p, d_occ.p);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) {

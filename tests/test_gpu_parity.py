@@ -208,6 +208,14 @@ def test_dedup_does_less_work_than_visit_all_with_same_pixels(gpu, loaded, crt):
     b, _, _, real = gpu.render(sf.camera(), crt.make_options(count_work=2))
     assert same_f32(a, b).all()
     assert real["node_tests"] < visit_all["node_tests"] and real["triangle_tests"] < visit_all["triangle_tests"]
+    # more than 64 meshes: the visited-mesh set lives in shared memory instead of a 64-bit register, same effect
+    sf, flat, rects, n = loaded["many_meshes"]
+    assert flat.contents.n_meshes > 64
+    gpu.upload(flat, keepalive=sf)
+    a, _, _, visit_all = gpu.render(sf.camera(), crt.make_options(count_work=1))
+    b, _, _, real = gpu.render(sf.camera(), crt.make_options(count_work=2, traversal=1))  # literal walk: only the de-duplication differs
+    assert same_f32(a, b).all()
+    assert real["node_tests"] < visit_all["node_tests"]
 
 
 @pytest.mark.parametrize("name", list(SMALL_SCENES))
