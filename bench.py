@@ -677,7 +677,9 @@ def ours_arm(args):
                                    if world > 1 else "single"),
                    "l2": ("each frame streams ~1 GB of queues through the 126 MB L2 (inputs larger than L2)" if frames_mode
                           else "flushed between steps (256 MiB fill)"),
-                   "rays_per_step": rays_step, "chunks_in_flight": args.concurrency},
+                   "rays_per_step": rays_step, "chunks_in_flight": args.concurrency,
+                   "shadow_rays_zero_term_per_step_rank0": kstats[-1].get("shadow_rays_zero_term", 0),
+                   "walks_handed_to_k_coop_per_step_rank0": kstats[-1].get("handoff_closest", 0) + kstats[-1].get("handoff_shadow", 0)},
         "clocks": clocks, "gpu_launches": launches * args.steps, "step_ms": step_ms,
     }
     if e2e:
