@@ -147,6 +147,40 @@ CRT_DI float stdmin(float a, float b) { return (b < a) ? b : a; }
 #define CRT_LEAF_FLAG 0x80000000u
 
 // ------------------------------------------------------------------------------------------------------------
+// Read-only loads of the scene with an L1 residency policy per data class (A/B knobs for tools/ builds; 0 = ld.global.nc
+// with the default policy, which is what ships -- see profiles/r2_tuning.md section 5 for the measurements):
+//   1 = L1::evict_last   2 = L1::no_allocate   3 = L1::evict_first
+// CRT_NODE_LD applies to KD nodes, CRT_TRI_LD to leaf references and triangle records.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef CRT_NODE_LD
+#define CRT_NODE_LD 0
+#endif
+#ifndef CRT_TRI_LD
+#define CRT_TRI_LD 0
+#endif
+template <int POLICY>
+CRT_DI float4 ld_policy(const float4 *p) {
+  if (POLICY == 0) return __ldg(p);
+  float4 v;
+  if (POLICY == 1) asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  if (POLICY == 2) asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  if (POLICY == 3) asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+template <int POLICY>
+CRT_DI uint32_t ld_policy(const uint32_t *p) {
+  if (POLICY == 0) return __ldg(p);
+  uint32_t v = 0;
+  if (POLICY == 1) asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  if (POLICY == 2) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  if (POLICY == 3) asm volatile("ld.global.nc.L1::evict_first.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+CRT_DI float4 ld_node(const float4 *p) { return ld_policy<CRT_NODE_LD>(p); }
+CRT_DI float4 ld_tri(const float4 *p) { return ld_policy<CRT_TRI_LD>(p); }
+CRT_DI uint32_t ld_ref(const uint32_t *p) { return ld_policy<CRT_TRI_LD>(p); }
+
+// ------------------------------------------------------------------------------------------------------------
 // rays
 // ------------------------------------------------------------------------------------------------------------
 struct Ray {
@@ -285,11 +319,24 @@ struct Trav {
   float mu;               // culling margin of the tree being walked, in space units (+inf: top-level tree / culling off)
 };
 #define CRT_INF __int_as_float(0x7f800000)
-// visited-mesh bitset of scenes with more than 64 meshes: word w of thread t at crt_dyn_smem[w * blockDim.x + t]
+// visited-mesh bitset of scenes with more than 64 meshes: word w of thread t at crt_dyn_smem[w * blockDim.x + t].
+// Kept out of line: the common case (<= 64 meshes, a 64-bit register) must not pay registers for it.
 extern __shared__ uint32_t crt_dyn_smem[];
+static __device__ __noinline__ void dedup_smem_clear(const uint32_t words) {
+  for (uint32_t w = 0; w < words; w++) crt_dyn_smem[w * blockDim.x + threadIdx.x] = 0u;
+}
+static __device__ __noinline__ bool dedup_smem_test_and_set(const uint32_t m) {
+  uint32_t *w = crt_dyn_smem + (m >> 5) * blockDim.x + threadIdx.x;
+  const uint32_t bit = 1u << (m & 31u), old = *w;
+  *w = old | bit;
+  return (old & bit) != 0u;
+}
+// WIDE: the kernel was instantiated for scenes whose visited-mesh set lives in shared memory (65..512 meshes).  The
+// one-ray-per-lane traversal kernels exist in both flavours so that the common one carries no code for the other
+// (measured: with a run-time switch inside one kernel hw11_room_128 lost 10 %, profiles/r2_tuning.md section 5).
+template <bool WIDE>
 CRT_DI void trav_begin(Trav &s, const DScene &sc) {
-  if (sc.dedup_meshes == 2u)
-    for (uint32_t w = 0; w < sc.dedup_words; w++) crt_dyn_smem[w * blockDim.x + threadIdx.x] = 0u;
+  if (WIDE && sc.dedup_meshes == 2u) dedup_smem_clear(sc.dedup_words);
   s.cur = sc.top_begin;
   s.cend = sc.top_end;
   s.resume = sc.top_end;
@@ -349,15 +396,15 @@ CRT_DI bool node_test(const float4 lo, const float4 hi, const Ray &r, const floa
 //   CULL             conservative culling inside mesh trees (node_test): `limit` = the best finite hit so far / the
 //                    light distance, `allow_behind` = a finite candidate exists (closest hit) / always (shadow).
 enum { TRAV_STEP = 0, TRAV_LEAF = 1, TRAV_DONE = 2 };
-template <bool SKIP_REFRACTIVE, bool DEDUP, bool CULL>
+template <bool SKIP_REFRACTIVE, int DEDUP, bool CULL>
 CRT_DI int trav_slow(Trav &s, const DScene &sc, const Ray &r);
 
-template <bool SKIP_REFRACTIVE, bool COUNT, bool DEDUP, bool CULL>
+template <bool SKIP_REFRACTIVE, bool COUNT, int DEDUP, bool CULL>
 CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float limit, const bool allow_behind) {
   if (s.cur != s.cend) {
     const uint32_t idx = s.cur;
-    const float4 lo = __ldg(&sc.nodes[2 * (size_t)idx]);
-    const float4 hi = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
+    const float4 lo = ld_node(&sc.nodes[2 * (size_t)idx]);
+    const float4 hi = ld_node(&sc.nodes[2 * (size_t)idx + 1]);
     const uint32_t a = __float_as_uint(lo.w);
     const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
     if (COUNT) node_tests++;
@@ -390,8 +437,8 @@ CRT_DI int trav_step(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tes
 template <bool COUNT, bool CULL>
 CRT_DI bool trav_fast(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_tests, const float limit, const bool allow_behind) {
   const uint32_t idx = s.cur;
-  const float4 lo = __ldg(&sc.nodes[2 * (size_t)idx]);
-  const float4 hi = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
+  const float4 lo = ld_node(&sc.nodes[2 * (size_t)idx]);
+  const float4 hi = ld_node(&sc.nodes[2 * (size_t)idx + 1]);
   const uint32_t a = __float_as_uint(lo.w);
   const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
 #if CRT_PREFETCH_SKIP
@@ -429,8 +476,8 @@ CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_t
   const uint32_t idx = s.cur;
   const bool has2 = idx + 1u < s.cend;
   const uint32_t jdx = has2 ? idx + 1u : idx;
-  const float4 lo0 = __ldg(&sc.nodes[2 * (size_t)idx]), hi0 = __ldg(&sc.nodes[2 * (size_t)idx + 1]);
-  const float4 lo1 = __ldg(&sc.nodes[2 * (size_t)jdx]), hi1 = __ldg(&sc.nodes[2 * (size_t)jdx + 1]);
+  const float4 lo0 = ld_node(&sc.nodes[2 * (size_t)idx]), hi0 = ld_node(&sc.nodes[2 * (size_t)idx + 1]);
+  const float4 lo1 = ld_node(&sc.nodes[2 * (size_t)jdx]), hi1 = ld_node(&sc.nodes[2 * (size_t)jdx + 1]);
   const bool pass0 = node_test<CULL>(lo0, hi0, r, s.mu, limit, allow_behind);
   const bool pass1 = node_test<CULL>(lo1, hi1, r, s.mu, limit, allow_behind);
   const uint32_t a0 = __float_as_uint(lo0.w), a1 = __float_as_uint(lo1.w);
@@ -461,21 +508,22 @@ CRT_DI bool trav_fast2(Trav &s, const DScene &sc, const Ray &r, uint32_t &node_t
   return s.cur < s.cend;
 }
 
-template <bool SKIP_REFRACTIVE, bool DEDUP, bool CULL>
+// DEDUP: 0 = every listing of a mesh is walked (the reference's work; counting mode), 1 = visited-mesh set in the 64-bit
+// register Trav::seen (scenes with <= 64 meshes), 2 = in shared memory (65..512 meshes; kernels instantiated WIDE),
+// 3 = whichever of the two the scene asks for (k_query: not a hot kernel).  Scenes with more meshes than that walk
+// every listing -- correct (the candidates repeat and a repeat never wins a strict <), only slower.
+template <bool SKIP_REFRACTIVE, int DEDUP, bool CULL>
 CRT_DI int trav_slow(Trav &s, const DScene &sc, const Ray &r) {
   if (s.mref != s.mend) {
     const uint32_t m = __ldg(&sc.top_refs[s.mref++]);
     const DMesh me = sc.meshes[m];
     bool skip = SKIP_REFRACTIVE && sc.materials[me.material].type == 3u;
-    if (DEDUP && sc.dedup_meshes == 1u) {
+    if ((DEDUP & 1) && sc.dedup_meshes == 1u) {
       const unsigned long long bit = 1ull << (m & 63u);
       skip = skip || (s.seen & bit) != 0ull;
       s.seen |= bit;
-    } else if (DEDUP && sc.dedup_meshes == 2u) {
-      uint32_t *w = crt_dyn_smem + (m >> 5) * blockDim.x + threadIdx.x;
-      const uint32_t bit = 1u << (m & 31u), old = *w;
-      skip = skip || (old & bit) != 0u;
-      *w = old | bit;
+    } else if ((DEDUP & 2) && sc.dedup_meshes == 2u) {
+      if (dedup_smem_test_and_set(m)) skip = true;
     }
     if (!skip) {
       s.cur = me.node_begin;

@@ -197,10 +197,10 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, const
     uint32_t tri = 0, own = 0;
     if (g < total) {
       own = ws.owner[31 - __clz(heads & (CRT_FULL_MASK >> (31u - lane)))];  // slot 0 of a window is always a head
-      tri = __ldg(&sc.leaf_refs[ws.refbase[own] + g]);
-      const float4 g0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
-      const float4 g1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
-      const float4 g2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+      tri = ld_ref(&sc.leaf_refs[ws.refbase[own] + g]);
+      const float4 g0 = ld_tri(&sc.tri_geom[3 * (size_t)tri]);
+      const float4 g1 = ld_tri(&sc.tri_geom[3 * (size_t)tri + 1]);
+      const float4 g2 = ld_tri(&sc.tri_geom[3 * (size_t)tri + 2]);
       const float4 o4 = ws.ro[own], d4 = ws.rd[own];
       Ray r;
       r.o = mk(o4.x, o4.y, o4.z);
@@ -307,7 +307,7 @@ CRT_DI bool tail_handoff(const Levels &lv, const uint32_t launch, const bool wan
 // MODE: 2 = this loop.  (0 = while-while and 1 = merged single loop were the round-1 predecessors; their measurements are
 // in profiles/r1_tuning.md, their code is gone.)
 // ------------------------------------------------------------------------------------------------------------
-template <bool PRIMARY, bool COUNT, int REFILL, int MODE, bool CULL>
+template <bool PRIMARY, bool COUNT, int REFILL, int MODE, bool CULL, bool WIDE>
 __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest(const DScene sc, const Frame fr, const Levels lv, const uint32_t level,
                                                 uint32_t *__restrict__ work_counter) {
   static_assert(MODE == 2, "only loop mode 2 is implemented");
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
   tv.tref = tv.tend = 0;
   ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
   ray.flags = 0;
-  trav_begin(tv, sc);
+  trav_begin<WIDE>(tv, sc);
   closest_begin(cl);
   CRT_PC_DECL
   for (;;) {
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
         }
         if (valid) {
           ray_prepare(ray, PRIMARY);
-          trav_begin(tv, sc);
+          trav_begin<WIDE>(tv, sc);
           closest_begin(cl);
           node = node_base + i;
           active = true;
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest
       for (;;) {
         const bool slow = active && tv.tref == tv.tend && tv.cur == tv.cend;
         if (!__any_sync(CRT_FULL_MASK, slow)) break;
-        if (slow && trav_slow<false, !COUNT, CULL>(tv, sc, ray) == TRAV_DONE) {
+        if (slow && trav_slow<false, (COUNT ? 0 : (WIDE ? 2 : 1)), CULL>(tv, sc, ray) == TRAV_DONE) {
           lv.hit_tri[node] = cl.best_tri;
           lv.hit_t[node] = cl.best_t;
           active = false;
@@ -666,7 +666,7 @@ CRT_DI float shadow_limit(const Ray &ray, const float dist) {
   return dist * 1.0001f + 1e-4f + 1e-6f * (fabsf(ray.o.x) + fabsf(ray.o.y) + fabsf(ray.o.z));
 }
 
-template <int COUNT, int REFILL, int MODE, bool CULL>
+template <int COUNT, int REFILL, int MODE, bool CULL, bool WIDE>
 __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(const DScene sc, const Frame fr, const Levels lv,
                                                                              uint32_t *__restrict__ work_counter) {
   static_assert(MODE == 2, "only loop mode 2 is implemented");
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
   Trav tv;
   ray.o = ray.d = ray.inv = mk(0.f, 0.f, 0.f);
   ray.flags = 0;
-  trav_begin(tv, sc);
+  trav_begin<WIDE>(tv, sc);
   CRT_PC_DECL
   for (;;) {
     CRT_PC_MARK(4)
@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
           n_moot++;
         } else {
           ray_prepare(ray, false);
-          trav_begin(tv, sc);
+          trav_begin<WIDE>(tv, sc);
           t_limit = shadow_limit(ray, dist);
           occluded = false;
           active = true;
@@ -754,7 +754,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
       for (;;) {
         const bool slow = active && tv.tref == tv.tend && tv.cur == tv.cend;
         if (!__any_sync(CRT_FULL_MASK, slow)) break;
-        if (slow && trav_slow<true, (COUNT != 1), CULL>(tv, sc, ray) == TRAV_DONE) {
+        if (slow && trav_slow<true, (COUNT == 1 ? 0 : (WIDE ? 2 : 1)), CULL>(tv, sc, ray) == TRAV_DONE) {
           lv.vis[slot] = occluded ? 0 : 1;
           active = false;
           CRT_PC_RAY_DONE(1, ray_iters)
@@ -1014,7 +1014,7 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_co
           }
         } else {
           // one step in the top-level tree (a handful of nodes: every lane does the same step; never culled)
-          const float4 lo = __ldg(&sc.nodes[2 * (size_t)cur]), hi = __ldg(&sc.nodes[2 * (size_t)cur + 1]);
+          const float4 lo = ld_node(&sc.nodes[2 * (size_t)cur]), hi = ld_node(&sc.nodes[2 * (size_t)cur + 1]);
           const uint32_t a = __float_as_uint(lo.w);
           const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
           const bool pass = node_test<false>(lo, hi, ray, CRT_INF, CRT_INF, false);
@@ -1075,7 +1075,7 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_co
       bool leaf_hit = false;
       uint32_t a = 0, b = CRT_INVALID, cnt = 0;
       if (have) {
-        const float4 lo = __ldg(&sc.nodes[2 * (size_t)j]), hi = __ldg(&sc.nodes[2 * (size_t)j + 1]);
+        const float4 lo = ld_node(&sc.nodes[2 * (size_t)j]), hi = ld_node(&sc.nodes[2 * (size_t)j + 1]);
         a = __float_as_uint(lo.w);
         b = __float_as_uint(hi.w);
         const bool leaf = (a & CRT_LEAF_FLAG) != 0u;
@@ -1127,10 +1127,10 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_co
 #endif
             const uint32_t own = owner[31 - __clz(heads & (CRT_FULL_MASK >> (31u - gl)))];  // slot 0 of a window is always a head
             const uint32_t ref = refbase[own] + slot;
-            const uint32_t tri = __ldg(&sc.leaf_refs[ref]);
-            const float4 t0 = __ldg(&sc.tri_geom[3 * (size_t)tri]);
-            const float4 t1 = __ldg(&sc.tri_geom[3 * (size_t)tri + 1]);
-            const float4 t2 = __ldg(&sc.tri_geom[3 * (size_t)tri + 2]);
+            const uint32_t tri = ld_ref(&sc.leaf_refs[ref]);
+            const float4 t0 = ld_tri(&sc.tri_geom[3 * (size_t)tri]);
+            const float4 t1 = ld_tri(&sc.tri_geom[3 * (size_t)tri + 1]);
+            const float4 t2 = ld_tri(&sc.tri_geom[3 * (size_t)tri + 2]);
             V3 p;
             hit = triangle_test(t0, t1, t2, ray, t, p);
             if (SHADOW) {
@@ -1252,30 +1252,70 @@ struct HitRec {
   int mesh, tri;
   float t;
 };
+// A warp holds one 8x4 tile (items are tile-major and chunks start on tile boundaries).  When the whole tile is inside
+// the frame its four 96-byte rows leave as 16-byte stores (24 lanes x float4; PPMColor: 12 lanes x 8 bytes), staged
+// through shared memory: a third of the store instructions, and -- what matters when `rgb` is the frame of another GPU
+// (crtb200_create_multi, shard_full_frame) -- NVLink packets of 16 bytes instead of 4.  Partial tiles, odd widths and
+// unaligned frames take the scalar path.
 __global__ void __launch_bounds__(256) k_store(const DScene sc, const Frame fr, const Levels lv, float *__restrict__ rgb,
                                               uint8_t *__restrict__ rgb8, HitRec *__restrict__ hits,
                                               float *__restrict__ slab) {
+  __shared__ __align__(16) float s_f[8][96];
+  __shared__ __align__(8) uint8_t s_b[8][96];
   // shadow rays traced for this chunk = diffuse hits x lights (one per pair even when cos = 0, RayTracer.cpp:314-317)
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&lv.stats[1], (unsigned long long)lv.counts[CRT_MAX_LEVELS] * sc.n_lights);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fr.n_items0; i += gridDim.x * blockDim.x) {
-    uint32_t row, col;
-    const bool valid = item_pixel(fr, sc, fr.item_begin + i, row, col);
+  const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+  const bool aligned = (sc.width & 7u) == 0u && (fr.item_begin & 31u) == 0u && (reinterpret_cast<uintptr_t>(rgb) & 15u) == 0u &&
+                       (reinterpret_cast<uintptr_t>(rgb8) & 7u) == 0u && (reinterpret_cast<uintptr_t>(slab) & 15u) == 0u;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < fr.n_items0; base += gridDim.x * blockDim.x) {
+    const uint32_t i = base + lane;
+    uint32_t row = 0, col = 0;
+    const bool valid = i < fr.n_items0 && item_pixel(fr, sc, fr.item_begin + i, row, col);
     const float4 c = valid ? lv.color[lv.offset[0] + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (slab) {
+    const bool whole = aligned && base + 32u <= fr.n_items0;                 // all 32 items exist (slab path)
+    const bool full = whole && __all_sync(CRT_FULL_MASK, valid);             // ... and are pixels of the frame
+    const size_t pix = (size_t)row * sc.width + col;
+    if (whole && (slab || (full && rgb))) {
+      s_f[w][3 * lane + 0] = c.x;
+      s_f[w][3 * lane + 1] = c.y;
+      s_f[w][3 * lane + 2] = c.z;
+      __syncwarp();
+      if (lane < 24u) {
+        const float4 v = *reinterpret_cast<const float4 *>(&s_f[w][4 * lane]);
+        if (slab) *reinterpret_cast<float4 *>(slab + 3 * (size_t)(fr.item_begin + base) + 4 * lane) = v;
+        if (full && rgb) {
+          const size_t p0 = (size_t)__shfl_sync(0x00FFFFFFu, (unsigned long long)pix, 0);  // tile origin
+          *reinterpret_cast<float4 *>(rgb + 3 * (p0 + (size_t)(lane / 6u) * sc.width) + 4 * (lane % 6u)) = v;
+        }
+      }
+      __syncwarp();
+    }
+    if (full && rgb8) {
+      s_b[w][3 * lane + 0] = quantize(c.x);
+      s_b[w][3 * lane + 1] = quantize(c.y);
+      s_b[w][3 * lane + 2] = quantize(c.z);
+      __syncwarp();
+      if (lane < 12u) {
+        const size_t p0 = (size_t)__shfl_sync(0x00000FFFu, (unsigned long long)pix, 0);
+        *reinterpret_cast<uint2 *>(rgb8 + 3 * (p0 + (size_t)(lane / 3u) * sc.width) + 8 * (lane % 3u)) =
+            *reinterpret_cast<const uint2 *>(&s_b[w][8 * lane]);
+      }
+      __syncwarp();
+    }
+    if (slab && !whole && i < fr.n_items0) {
       float *s = slab + 3 * (size_t)(fr.item_begin + i);
       s[0] = c.x;
       s[1] = c.y;
       s[2] = c.z;
     }
     if (!valid) continue;
-    const size_t pix = (size_t)row * sc.width + col;
-    if (rgb) {
+    if (rgb && !full) {
       rgb[3 * pix + 0] = c.x;
       rgb[3 * pix + 1] = c.y;
       rgb[3 * pix + 2] = c.z;
     }
-    if (rgb8) {
+    if (rgb8 && !full) {
       rgb8[3 * pix + 0] = quantize(c.x);
       rgb8[3 * pix + 1] = quantize(c.y);
       rgb8[3 * pix + 2] = quantize(c.z);
@@ -1299,19 +1339,47 @@ __global__ void __launch_bounds__(256) k_store(const DScene sc, const Frame fr, 
 }
 
 // Scatter gathered shard slabs (shard-major, item order) into a full frame: the rank-0 side of the NCCL gather.
+// A warp moves one 8x4 tile: 384 contiguous slab bytes in, four 96-byte frame rows out (16-byte accesses both ways when
+// the tile is whole and everything is aligned, like k_store).
 __global__ void __launch_bounds__(256) k_assemble(const DScene sc, Frame fr, const float *__restrict__ slabs,
                                                  uint32_t items_per_shard, uint32_t shard_count,
                                                  float *__restrict__ rgb, uint8_t *__restrict__ rgb8) {
+  __shared__ __align__(16) float s_f[8][96];
+  __shared__ __align__(8) uint8_t s_b[8][96];
+  const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+  const bool aligned = (sc.width & 7u) == 0u && (items_per_shard & 31u) == 0u && (reinterpret_cast<uintptr_t>(rgb) & 15u) == 0u &&
+                       (reinterpret_cast<uintptr_t>(rgb8) & 7u) == 0u && (reinterpret_cast<uintptr_t>(slabs) & 15u) == 0u;
   const unsigned long long total = (unsigned long long)items_per_shard * shard_count;
-  for (unsigned long long g = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; g < total;
-       g += (unsigned long long)gridDim.x * blockDim.x) {
+  for (unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x + (threadIdx.x & ~31u); base < total;
+       base += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long g = base + lane;
     const uint32_t shard = (uint32_t)(g / items_per_shard), i = (uint32_t)(g % items_per_shard);
     fr.shard_index = shard;
     fr.shard_count = shard_count;
-    uint32_t row, col;
-    if (!item_pixel(fr, sc, i, row, col)) continue;
-    const float *s = slabs + 3 * g;
+    uint32_t row = 0, col = 0;
+    const bool valid = g < total && item_pixel(fr, sc, i, row, col);
     const size_t pix = (size_t)row * sc.width + col;
+    if (aligned && __all_sync(CRT_FULL_MASK, valid)) {  // (aligned => a warp's 32 items are one tile of one shard)
+      const size_t p0 = (size_t)__shfl_sync(CRT_FULL_MASK, (unsigned long long)pix, 0);
+      if (lane < 24u) *reinterpret_cast<float4 *>(&s_f[w][4 * lane]) = *reinterpret_cast<const float4 *>(slabs + 3 * base + 4 * lane);
+      __syncwarp();
+      if (rgb && lane < 24u)
+        *reinterpret_cast<float4 *>(rgb + 3 * (p0 + (size_t)(lane / 6u) * sc.width) + 4 * (lane % 6u)) =
+            *reinterpret_cast<const float4 *>(&s_f[w][4 * lane]);
+      if (rgb8) {
+        s_b[w][3 * lane + 0] = quantize(s_f[w][3 * lane + 0]);
+        s_b[w][3 * lane + 1] = quantize(s_f[w][3 * lane + 1]);
+        s_b[w][3 * lane + 2] = quantize(s_f[w][3 * lane + 2]);
+        __syncwarp();
+        if (lane < 12u)
+          *reinterpret_cast<uint2 *>(rgb8 + 3 * (p0 + (size_t)(lane / 3u) * sc.width) + 8 * (lane % 3u)) =
+              *reinterpret_cast<const uint2 *>(&s_b[w][8 * lane]);
+      }
+      __syncwarp();
+      continue;
+    }
+    if (!valid) continue;
+    const float *s = slabs + 3 * g;
     if (rgb) {
       rgb[3 * pix + 0] = s[0];
       rgb[3 * pix + 1] = s[1];
@@ -1356,14 +1424,14 @@ __global__ void __launch_bounds__(256) k_query(const DScene sc, const float *__r
     ray.d = mk(rays[6 * (size_t)i + 3], rays[6 * (size_t)i + 4], rays[6 * (size_t)i + 5]);
     ray_prepare(ray, ray_type == 0u);
     Trav tv;
-    trav_begin(tv, sc);
+    trav_begin<true>(tv, sc);
     uint32_t dummy = 0;
     if (ray_type == 1u) {
       const float dist = max_distance[i];
       bool occ = false;
       for (;;) {
         int st = TRAV_STEP;
-        while (st == TRAV_STEP) st = trav_step<true, false, true, false>(tv, sc, ray, dummy, 0.0f, false);
+        while (st == TRAV_STEP) st = trav_step<true, false, 3, false>(tv, sc, ray, dummy, 0.0f, false);
         if (st == TRAV_DONE || occ) break;
         while (tv.tref != tv.tend) {
           const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);
@@ -1381,7 +1449,7 @@ __global__ void __launch_bounds__(256) k_query(const DScene sc, const float *__r
       closest_begin(cl);
       for (;;) {
         int st = TRAV_STEP;
-        while (st == TRAV_STEP) st = trav_step<false, false, true, false>(tv, sc, ray, dummy, 0.0f, false);
+        while (st == TRAV_STEP) st = trav_step<false, false, 3, false>(tv, sc, ray, dummy, 0.0f, false);
         if (st == TRAV_DONE) break;
         while (tv.tref != tv.tend) {
           const uint32_t tri = __ldg(&sc.leaf_refs[tv.tref++]);

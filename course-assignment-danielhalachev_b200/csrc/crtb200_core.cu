@@ -205,6 +205,15 @@ struct crtb200_ctx {
   uint32_t cap_items = 0;
   uint32_t cap_depth = 0xFFFFFFFFu;
   uint32_t cap_sets = 0;
+  // chunk schedule of the current plan: item counts in launch order (chunk k runs on set k % cap_sets).  Equal chunks,
+  // except that the FIRST chunk of every set of a host-bound frame is shortened / lengthened by `stagger` so that the sets
+  // finish their chunks one after the other instead of all at once: the band copies then ride behind the traversal of
+  // the other sets instead of queueing up on the copy engine at half time and at the end (tools/e2e_time.py)
+  std::vector<uint32_t> chunk_items;
+  float stagger = 0.15f;
+  cudaStream_t band_stream = nullptr;  // device -> host band copies of a chunked host-bound frame
+  cudaEvent_t band_done = nullptr;
+  std::vector<cudaEvent_t> chunk_done;
 
   int blocks_closest = 0, blocks_shadow = 0, blocks_coop = 0;
   crtb200_stats last{};
@@ -260,9 +269,9 @@ int crtb200_create(int device, crtb200_ctx **out) {
   }
   for (auto &e : c->ev) cudaEventCreate(&e);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL, CRT_LOOP_MODE, false, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_closest = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false>, CRT_TRAV_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_coop<true, false, true, CRT_COOP_GROUP>, 32 * CRT_COOP_WARPS, 0);
   c->blocks_coop = std::max(1, occ) * c->sm_count;
@@ -275,6 +284,7 @@ int crtb200_create(int device, crtb200_ctx **out) {
   if (const char *env = getenv("CRT_TAIL_CAP")) c->tail_cap = std::max(1, atoi(env));
   if (const char *env = getenv("CRT_TAIL_START")) c->tail_start = std::max(0, atoi(env));
   if (const char *env = getenv("CRT_TAIL_SMALL")) c->tail_small = std::max(0, atoi(env));
+  if (const char *env = getenv("CRT_CHUNK_STAGGER")) c->stagger = std::min(0.3f, std::max(0.0f, (float)atof(env)));  // tools: e2e tuning
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
   c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
   if (c->l2_persist && c->l2_persist_max)
@@ -366,6 +376,9 @@ int crtb200_destroy(crtb200_ctx *c) {
     if (q.done) cudaEventDestroy(q.done);
   }
   if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+  if (c->band_stream) cudaStreamDestroy(c->band_stream);
+  if (c->band_done) cudaEventDestroy(c->band_done);
+  for (cudaEvent_t e : c->chunk_done) cudaEventDestroy(e);
   c->stats_dev.release();
   for (auto &e : c->ev)
     if (e) cudaEventDestroy(e);
@@ -835,11 +848,40 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
   const uint32_t parts = n_sets * per_set;
   uint64_t even = ((uint64_t)shard_items + parts - 1) / parts;
   even = ((even + row_items - 1) / row_items) * row_items;
+  // staggered first round (see crtb200_ctx::chunk_items): set k's first chunk is (1 + (k - (n_sets - 1) / 2) * stagger)
+  // times the mean; the queues are sized for the largest chunk
+  std::vector<uint32_t> sched;
+  if (pipelined && n_sets > 1 && per_set > 1 && c->stagger > 0.0f && shard_items >= parts * row_items) {
+    const double mean = (double)shard_items / parts;
+    uint64_t placed = 0;
+    for (uint32_t k = 0; k < parts; k++) {
+      double w = k < n_sets ? 1.0 + ((double)k - 0.5 * (n_sets - 1)) * c->stagger : 1.0;
+      uint64_t n = (uint64_t)(mean * w / row_items + 0.5) * row_items;
+      n = std::max<uint64_t>(n, row_items);
+      if (k + 1 == parts || placed + n > shard_items) n = shard_items - placed;
+      sched.push_back((uint32_t)n);
+      placed += n;
+      if (placed == shard_items) break;
+    }
+    uint64_t largest = 0;
+    for (uint32_t n : sched) largest = std::max<uint64_t>(largest, n);
+    largest = ((largest + row_items - 1) / row_items) * row_items;
+    if (largest <= items) even = largest; else sched.clear();  // (budget too small: equal chunks of what fits)
+  }
   items = std::min<uint64_t>(items, even);
   // node ids and (diffuse item, light) slots are 32-bit on the device
   if (items * sum * n_lights >= 0x7FFFFFFFull) items = ((0x7FFFFFFFull / (sum * n_lights)) - 32) & ~31ull;
   if (items < 32) return fail(CRTB200_ERR_MEMORY, "too many lights x ray-tree nodes for 32-bit queue slots");
   if (items >= row_items) items = (items / row_items) * row_items;  // whole tile rows (band copies need it)
+  for (uint32_t n : sched)
+    if (n > items) {  // (a later clamp shrank the queues)
+      sched.clear();
+      break;
+    }
+  if (sched.empty()) {
+    for (uint64_t b = 0; b < shard_items; b += items) sched.push_back((uint32_t)std::min<uint64_t>(items, shard_items - b));
+  }
+  c->chunk_items = sched;
   if (c->cap_items == items && c->cap_depth == max_depth && c->cap_sets == n_sets) return CRTB200_OK;
   if (c->sets.size() < n_sets) c->sets.resize(n_sets);
   if (!c->fork_ev) CUDA_TRY(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
@@ -933,13 +975,30 @@ static cudaEvent_t next_event(crtb200_ctx *c) {
 // dynamic shared memory of the kernels that walk one ray per lane: the visited-mesh bitset of scenes with > 64 meshes
 static size_t dyn_smem(const crtb200_ctx *c, int block) { return (size_t)c->sc.dedup_words * (size_t)block * sizeof(uint32_t); }
 
+template <bool COUNT, bool CULL, bool WIDE>
+static void launch_closest_w(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, uint32_t *work,
+                             cudaStream_t st) {
+  if (primary)
+    k_closest<true, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL, WIDE><<<c->blocks_closest, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, level, work);
+  else
+    k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL, WIDE><<<c->blocks_closest, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, level, work);
+}
+// the WIDE flavour (visited-mesh set in shared memory) only for scenes that need it, and never when counting the
+// reference's visit-all work (no de-duplication there)
 template <bool COUNT, bool CULL>
 static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, uint32_t *work,
                            cudaStream_t st) {
-  if (primary)
-    k_closest<true, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, level, work);
+  if (!COUNT && c->sc.dedup_meshes == 2u)
+    launch_closest_w<COUNT, CULL, !COUNT>(c, primary, fr, lv, level, work, st);
   else
-    k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL><<<c->blocks_closest, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, level, work);
+    launch_closest_w<COUNT, CULL, false>(c, primary, fr, lv, level, work, st);
+}
+template <int COUNT, bool CULL>
+static void launch_shadow(crtb200_ctx *c, const Frame &fr, const Levels &lv, uint32_t *work, cudaStream_t st) {
+  if (COUNT != 1 && c->sc.dedup_meshes == 2u)
+    k_shadow<COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL, (COUNT != 1)><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, work);
+  else
+    k_shadow<COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, work);
 }
 
 template <bool CULL>
@@ -1024,11 +1083,22 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   CUDA_TRY(cudaEventRecord(c->fork_ev, st));
   for (uint32_t k = 0; k < n_sets; k++) CUDA_TRY(cudaStreamWaitEvent(c->sets[k].stream, c->fork_ev, 0));
   uint32_t launches = 0, chunk = 0;
-  for (uint32_t begin = 0; begin < shard_items; begin += c->cap_items, chunk++) {
+  // band copies leave on their own stream, so a set starts its next chunk while its last band is still in flight
+  const bool band_stream = band_copies && n_sets > 1;
+  if (band_stream) {
+    if (!c->band_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->band_stream, cudaStreamNonBlocking));
+    if (!c->band_done) CUDA_TRY(cudaEventCreateWithFlags(&c->band_done, cudaEventDisableTiming));
+    while (c->chunk_done.size() < c->chunk_items.size()) {
+      cudaEvent_t e = nullptr;
+      CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->chunk_done.push_back(e);
+    }
+  }
+  for (uint32_t begin = 0; chunk < c->chunk_items.size() && begin < shard_items; begin += c->chunk_items[chunk], chunk++) {
     crtb200_ctx::QueueSet &q = c->sets[chunk % n_sets];
     cudaStream_t qs = q.stream;
     fr.item_begin = begin;
-    fr.n_items0 = std::min(c->cap_items, shard_items - begin);
+    fr.n_items0 = std::min(c->chunk_items[chunk], shard_items - begin);
     CUDA_TRY(cudaMemsetAsync(q.ctl.p, 0, q.ctl.n * sizeof(uint32_t), qs));
     q.lv.tail_iters = handoff ? (uint32_t)(c->tail_iters + 1) : 0u;
     q.lv.skip_zero_terms = (o->traversal == 0 && o->count_work != 1) ? 1u : 0u;
@@ -1069,15 +1139,15 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     }
     uint32_t *swork = q.work + CRT_MAX_LEVELS;
     if (o->count_work == 1)
-      k_shadow<1, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), qs>>>(c->sc, fr, q.lv, swork);
+      launch_shadow<1, false>(c, fr, q.lv, swork, qs);
     else if (o->count_work == 2 && cull)
-      k_shadow<2, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), qs>>>(c->sc, fr, q.lv, swork);
+      launch_shadow<2, true>(c, fr, q.lv, swork, qs);
     else if (o->count_work == 2)
-      k_shadow<2, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), qs>>>(c->sc, fr, q.lv, swork);
+      launch_shadow<2, false>(c, fr, q.lv, swork, qs);
     else if (cull)
-      k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, true><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), qs>>>(c->sc, fr, q.lv, swork);
+      launch_shadow<0, true>(c, fr, q.lv, swork, qs);
     else
-      k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), qs>>>(c->sc, fr, q.lv, swork);
+      launch_shadow<0, false>(c, fr, q.lv, swork, qs);
     if (handoff) {
       if (per_kernel) {
         cudaEventRecord(next_event(c), qs);
@@ -1103,10 +1173,20 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       const uint32_t row0 = (begin / row_items) * 4u;
       const uint32_t row1 = std::min<uint32_t>(H, ((begin + fr.n_items0 + row_items - 1) / row_items) * 4u);
       const size_t off = (size_t)row0 * W, cnt = (size_t)(row1 - row0) * W;
-      if (host->rgb) CUDA_TRY(cudaMemcpyAsync(host->rgb + off * 3, d_rgb + off * 3, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, qs));
-      if (host->rgb8) CUDA_TRY(cudaMemcpyAsync(host->rgb8 + off * 3, d_rgb8 + off * 3, cnt * 3, cudaMemcpyDeviceToHost, qs));
-      if (host->hits) CUDA_TRY(cudaMemcpyAsync(host->hits + off, d_hits + off, cnt * sizeof(HitRec), cudaMemcpyDeviceToHost, qs));
+      cudaStream_t cs = qs;
+      if (band_stream) {
+        CUDA_TRY(cudaEventRecord(c->chunk_done[chunk], qs));
+        CUDA_TRY(cudaStreamWaitEvent(c->band_stream, c->chunk_done[chunk], 0));
+        cs = c->band_stream;
+      }
+      if (host->rgb) CUDA_TRY(cudaMemcpyAsync(host->rgb + off * 3, d_rgb + off * 3, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+      if (host->rgb8) CUDA_TRY(cudaMemcpyAsync(host->rgb8 + off * 3, d_rgb8 + off * 3, cnt * 3, cudaMemcpyDeviceToHost, cs));
+      if (host->hits) CUDA_TRY(cudaMemcpyAsync(host->hits + off, d_hits + off, cnt * sizeof(HitRec), cudaMemcpyDeviceToHost, cs));
     }
+  }
+  if (band_stream) {
+    CUDA_TRY(cudaEventRecord(c->band_done, c->band_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, c->band_done, 0));
   }
   for (uint32_t k = 0; k < n_sets; k++) {
     CUDA_TRY(cudaEventRecord(c->sets[k].done, c->sets[k].stream));

@@ -335,7 +335,13 @@ def test_trees_that_do_not_nest_take_the_literal_walk(gpu, built, scene_dir, ob,
     assert st["rays_total"] == o_st["rays_total"]
     _, _, _, a = gpu.render(sf.camera(), crt.make_options(count_work=2, traversal=0))
     _, _, _, b = gpu.render(sf.camera(), crt.make_options(count_work=2, traversal=1))
-    assert a["node_tests"] == b["node_tests"]  # nothing was culled
+    # nothing was culled: the closest-hit walks execute the literal walk's box tests one for one; the shadow kernel
+    # differs only by the rays whose light term is exactly zero (answered without a walk whatever the tree looks like)
+    assert a["node_tests_closest"] == b["node_tests_closest"]
+    assert a["triangle_tests_closest"] == b["triangle_tests_closest"]
+    assert a["handoff_closest"] == a["handoff_shadow"] == 0
+    assert a["shadow_rays_zero_term"] > 0 and b["shadow_rays_zero_term"] == 0
+    assert a["node_tests_shadow"] < b["node_tests_shadow"]
 
 
 def test_multi_gpu_context_matches_single(gpu, built, loaded, crt):

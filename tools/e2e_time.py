@@ -21,22 +21,27 @@ def main():
     rects, n = sf.rects()
     host = torch.empty((sf.info.height, sf.info.width, 3), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for per_set in (1, 2, 3):
-        os.environ["CRT_HOST_CHUNKS_PER_SET"] = str(per_set)
-        for conc in (1, 2, 3, 4, 6, 8):
-            ctx = crt.Context(0)
-            ctx.upload(flat, keepalive=sf)
-            ctx.set_concurrency(conc)
-            opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n)
-            ts = []
-            for k in range(8):
-                flush.fill_(k)
-                torch.cuda.synchronize()
-                t = time.perf_counter()
-                ctx.render(sf.camera(), opt, rgb_out=host.numpy())
-                ts.append((time.perf_counter() - t) * 1e3)
-            print(f"{wl} chunks/set {per_set} sets {conc}: e2e {statistics.mean(ts[2:]):.3f} ms (min {min(ts[2:]):.3f})", flush=True)
-            ctx.close()
+    staggers = os.environ.get("E2E_STAGGERS", "0,0.1,0.15,0.2,0.3").split(",")
+    per_sets = [int(x) for x in os.environ.get("E2E_PER_SET", "2,3").split(",")]
+    concs = [int(x) for x in os.environ.get("E2E_SETS", "3,4,6").split(",")]
+    for stagger in staggers:
+        os.environ["CRT_CHUNK_STAGGER"] = stagger
+        for per_set in per_sets:
+            os.environ["CRT_HOST_CHUNKS_PER_SET"] = str(per_set)
+            for conc in concs:
+                ctx = crt.Context(0)
+                ctx.upload(flat, keepalive=sf)
+                ctx.set_concurrency(conc)
+                opt = crt.make_options(max_depth=depth, rects=rects, n_rects=n)
+                ts = []
+                for k in range(9):
+                    flush.fill_(k)
+                    torch.cuda.synchronize()
+                    t = time.perf_counter()
+                    ctx.render(sf.camera(), opt, rgb_out=host.numpy())
+                    ts.append((time.perf_counter() - t) * 1e3)
+                print(f"{wl} stagger {stagger} chunks/set {per_set} sets {conc}: e2e {statistics.median(ts[2:]):.3f} ms (min {min(ts[2:]):.3f})", flush=True)
+                ctx.close()
 
 
 if __name__ == "__main__":
