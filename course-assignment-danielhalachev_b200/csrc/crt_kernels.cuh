@@ -51,7 +51,8 @@ struct Levels {
   // tail hand-off (k_coop): once the work queue of a traversal kernel is dry, the walks still running are written to
   // ovf[] (3 x uint4 per record) and finished one WARP per ray; tail_grace = 0 switches this off
   uint4 *ovf;
-  uint32_t *ovf_ctl;  // per traversal launch L (level, or CRT_MAX_LEVELS for the shadow pass): [2L] written, [2L+1] taken
+  uint32_t *ovf_ctl;  // per traversal launch L (level, or CRT_MAX_LEVELS for the shadow pass): [4L] written, [4L+1] / [4L+2] next
+                      // record index of the early / the final k_coop pass, [4L+3] != 0 once the traversal kernel has ended
   uint32_t ovf_cap;     // walks k_coop can take per launch (about two per resident k_coop warp): hand-off stops there
   uint32_t tail_iters;  // 0 = off; else tail_iters - 1 = the floor of the hand-off threshold (see tail_policy)
   uint32_t tail_start;  // the threshold's value when the queue of a large launch has just run dry (1024)
@@ -280,15 +281,18 @@ CRT_DI bool tail_handoff(const Levels &lv, const uint32_t launch, const bool wan
   const uint32_t wm = __ballot_sync(CRT_FULL_MASK, want);
   if (!wm) return false;
   uint32_t base = 0;
-  if (lane_id() == 0) base = atomicAdd(&lv.ovf_ctl[2u * launch], (uint32_t)__popc(wm));
+  if (lane_id() == 0) base = atomicAdd(&lv.ovf_ctl[4u * launch], (uint32_t)__popc(wm));
   base = __shfl_sync(CRT_FULL_MASK, base, 0);
   const uint32_t r = base + __popc(wm & lanemask_lt());
   if (base + (uint32_t)__popc(wm) >= lv.ovf_cap) closed = true;
   if (!want || r >= lv.ovf_cap) return false;  // k_coop's capacity is used up: the lane keeps walking here
+  // r0.x (the ray id, never CRT_INVALID) is also the record's "published" flag: k_coop's early pass runs concurrently
+  // with this kernel and takes a record by exchanging r0.x back to CRT_INVALID, so r0 goes out last, behind a fence
   uint4 *rec = lv.ovf + 3 * (size_t)r;
-  rec[0] = make_uint4(id, tv.cur, tv.cend, tv.resume);
   rec[1] = make_uint4(tv.mref, tv.mend, (uint32_t)tv.seen, (uint32_t)(tv.seen >> 32));
   rec[2] = make_uint4(tv.below, __float_as_uint(tv.mu), __float_as_uint(best_t), best_tri);
+  __threadfence();
+  rec[0] = make_uint4(id, tv.cur, tv.cend, tv.resume);
   return true;
 }
 
@@ -841,6 +845,9 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
 // Every group runs the same loop; group-uniform branches use the group's own lane mask for their shuffles and votes.
 // ------------------------------------------------------------------------------------------------------------
 #define CRT_COOP_CAP 512    // LIFO entries per warp (2 KB), shared out between its groups
+#ifndef CRT_COOP_SPINS
+#define CRT_COOP_SPINS 4000  // early pass: polls (0.5 us apart) for a record to be published before the group gives up
+#endif
 #define CRT_COOP_WARPS 4    // warps per CTA
 #ifndef CRT_COOP_MIN_BLOCKS
 #define CRT_COOP_MIN_BLOCKS 6  // resident CTAs per SM the register allocation is bounded for (24 warps = 96 walks per SM)
@@ -909,8 +916,13 @@ CRT_DI void coop_fold(const uint32_t gm, CoopBest &cb, Closest &cl) {
   }
 }
 
+// Runs behind a traversal kernel on its stream: tells k_coop's early pass that nothing more will be published.
+__global__ void k_mark(uint32_t *flag) {
+  if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t *>(flag) = 1u;
+}
+
 template <bool SHADOW, bool PRIMARY, bool CULL, int GW>
-__global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_coop(const DScene sc, const Frame fr, const Levels lv, const uint32_t level) {
+__global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_coop(const DScene sc, const Frame fr, const Levels lv, const uint32_t level, const uint32_t early) {
   constexpr uint32_t NG = 32u / GW;            // walks per warp
   constexpr uint32_t CAP = CRT_COOP_CAP / NG;  // LIFO entries per walk
   static_assert(GW == 8 || GW == 16 || GW == 32, "group width");
@@ -921,8 +933,14 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_co
   uint32_t *const stack = wc.stack + (g0 / GW) * CAP;
   uint32_t *const refbase = wc.refbase + g0, *const owner = wc.owner + g0, *const leafidx = wc.leafidx + g0;
   const uint32_t launch = SHADOW ? (uint32_t)CRT_MAX_LEVELS : level;
-  const uint32_t n_rec = min(lv.ovf_ctl[2u * launch], lv.ovf_cap);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && n_rec) atomicAdd(&lv.stats[SHADOW ? 33 : 32], (unsigned long long)n_rec);
+  // Two passes per traversal launch.  early = 1: launched next to the traversal kernel on a second
+  // stream; its blocks become resident as the traversal kernel's blocks exit and take records while the last lanes
+  // there are still walking.  Record r is waited for until it is published, the traversal kernel has ended (ovf_ctl
+  // [4L+3], set by k_mark behind it) or CRT_COOP_SPINS polls have passed -- a bounded wait, so this pass can never hold
+  // the GPU against the kernel it waits for.  early = 0: launched behind both; takes whatever is still published.
+  volatile uint32_t *const ctl = lv.ovf_ctl + 4u * launch;
+  const uint32_t n_rec = early ? lv.ovf_cap : min(ctl[0], lv.ovf_cap);
+  if (!early && blockIdx.x == 0 && threadIdx.x == 0 && n_rec) atomicAdd(&lv.stats[SHADOW ? 33 : 32], (unsigned long long)n_rec);
 
   // group state: identical in all lanes of a group, except cb (per-lane partial results)
   bool busy = false, drained = false, in_mesh = false, occluded = false;
@@ -943,15 +961,30 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_co
 #endif
   for (;;) {
     // ---- 1. an idle group takes the next record ----
-    if (!busy && !drained) {
-      uint32_t r = 0;
-      if (gl == 0) r = atomicAdd(&lv.ovf_ctl[2u * launch + 1u], 1u);
+    while (!busy && !drained) {
+      uint32_t r = 0, got = CRT_INVALID;
+      if (gl == 0) {
+        r = atomicAdd(const_cast<uint32_t *>(&ctl[early ? 1 : 2]), 1u);
+        if (r < n_rec) {
+          uint32_t *flag = reinterpret_cast<uint32_t *>(lv.ovf + 3 * (size_t)r);
+          if (early) {
+            for (uint32_t spins = 0; spins < (uint32_t)CRT_COOP_SPINS; spins++) {
+              if (*reinterpret_cast<volatile uint32_t *>(flag) != CRT_INVALID) break;
+              if (ctl[3]) break;  // the traversal kernel has ended: what is not published now never will be
+              __nanosleep(500);
+            }
+          }
+          got = atomicExch(flag, CRT_INVALID);  // take the record (the other pass may have been here first)
+          __threadfence();
+        }
+      }
       r = __shfl_sync(gm, r, 0, GW);
-      if (r >= n_rec) {
-        drained = true;
-      } else {
-        const uint4 r0 = lv.ovf[3 * (size_t)r], r1 = lv.ovf[3 * (size_t)r + 1], r2 = lv.ovf[3 * (size_t)r + 2];
-        id = r0.x;
+      got = __shfl_sync(gm, got, 0, GW);
+      if (r >= n_rec || (early && got == CRT_INVALID)) {
+        drained = true;  // (early pass: an unpublished record ends the group; the final pass looks at every record)
+      } else if (got != CRT_INVALID) {
+        const uint4 r0 = __ldcg(&lv.ovf[3 * (size_t)r]), r1 = __ldcg(&lv.ovf[3 * (size_t)r + 1]), r2 = __ldcg(&lv.ovf[3 * (size_t)r + 2]);
+        id = got;
         if (SHADOW) {
           const uint32_t hit = id / sc.n_lights, light = id - hit * sc.n_lights;
           const float4 q0 = lv.dq[3 * (size_t)hit], q1 = lv.dq[3 * (size_t)hit + 1];

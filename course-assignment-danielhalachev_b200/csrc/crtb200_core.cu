@@ -193,6 +193,9 @@ struct crtb200_ctx {
     uint32_t *work = nullptr;   // into ctl
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    // early k_coop pass: low-priority side stream, forked before and joined behind every traversal launch
+    cudaStream_t coop_stream = nullptr;
+    cudaEvent_t coop_fork = nullptr, coop_join = nullptr;
     void release() {
       ray_o.release(); ray_d.release(); color.release(); dq.release(); hit_tri.release(); ctl.release();
       hit_t.release(); comb.release(); vis.release(); ovf.release();
@@ -209,11 +212,14 @@ struct crtb200_ctx {
   // except that the FIRST chunk of every set of a host-bound frame is shortened / lengthened by `stagger` so that the sets
   // finish their chunks one after the other instead of all at once: the band copies then ride behind the traversal of
   // the other sets instead of queueing up on the copy engine at half time and at the end (tools/e2e_time.py)
+  int coop_early = 3;  // blocks per SM of k_coop's early pass (0 = final pass only); env CRT_COOP_EARLY
   std::vector<uint32_t> chunk_items;
   float stagger = 0.15f;
   cudaStream_t band_stream = nullptr;  // device -> host band copies of a chunked host-bound frame
   cudaEvent_t band_done = nullptr;
   std::vector<cudaEvent_t> chunk_done;
+  std::vector<cudaEvent_t> dbg_ev;  // CRT_CHUNK_TIMES (tools): per chunk, end of k_store and end of its band copy
+  uint32_t dbg_chunks = 0;
 
   int blocks_closest = 0, blocks_shadow = 0, blocks_coop = 0;
   crtb200_stats last{};
@@ -284,6 +290,7 @@ int crtb200_create(int device, crtb200_ctx **out) {
   if (const char *env = getenv("CRT_TAIL_CAP")) c->tail_cap = std::max(1, atoi(env));
   if (const char *env = getenv("CRT_TAIL_START")) c->tail_start = std::max(0, atoi(env));
   if (const char *env = getenv("CRT_TAIL_SMALL")) c->tail_small = std::max(0, atoi(env));
+  if (const char *env = getenv("CRT_COOP_EARLY")) c->coop_early = std::max(0, std::min(CRT_COOP_MIN_BLOCKS, atoi(env)));
   if (const char *env = getenv("CRT_CHUNK_STAGGER")) c->stagger = std::min(0.3f, std::max(0.0f, (float)atof(env)));  // tools: e2e tuning
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
   c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
@@ -376,9 +383,15 @@ int crtb200_destroy(crtb200_ctx *c) {
     if (q.done) cudaEventDestroy(q.done);
   }
   if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+  for (auto &q : c->sets) {
+    if (q.coop_stream) cudaStreamDestroy(q.coop_stream);
+    if (q.coop_fork) cudaEventDestroy(q.coop_fork);
+    if (q.coop_join) cudaEventDestroy(q.coop_join);
+  }
   if (c->band_stream) cudaStreamDestroy(c->band_stream);
   if (c->band_done) cudaEventDestroy(c->band_done);
   for (cudaEvent_t e : c->chunk_done) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->dbg_ev) cudaEventDestroy(e);
   c->stats_dev.release();
   for (auto &e : c->ev)
     if (e) cudaEventDestroy(e);
@@ -908,7 +921,16 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     // hand-off records: every lane of a traversal grid hands off at most once per launch
     const uint64_t ovf_cap = (uint64_t)std::max(c->blocks_closest, c->blocks_shadow) * CRT_TRAV_BLOCK;
     CUDA_TRY(q.ovf.ensure(3 * ovf_cap));
-    const size_t n_counts = CRT_MAX_LEVELS + 1, n_work = CRT_MAX_LEVELS + 2, n_ovf = 2 * (CRT_MAX_LEVELS + 1);
+    // every record starts out "not published" (r0.x = CRT_INVALID); k_coop leaves a taken record in that state again
+    CUDA_TRY(cudaMemsetAsync(q.ovf.p, 0xFF, 3 * ovf_cap * sizeof(uint4), q.stream));
+    if (!q.coop_stream) {
+      int lo = 0, hi = 0;
+      CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least priority: the traversal kernel's blocks go first
+      CUDA_TRY(cudaStreamCreateWithPriority(&q.coop_stream, cudaStreamNonBlocking, lo));
+      CUDA_TRY(cudaEventCreateWithFlags(&q.coop_fork, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&q.coop_join, cudaEventDisableTiming));
+    }
+    const size_t n_counts = CRT_MAX_LEVELS + 1, n_work = CRT_MAX_LEVELS + 2, n_ovf = 4 * (CRT_MAX_LEVELS + 1);
     CUDA_TRY(q.ctl.ensure(n_counts + n_work + n_ovf));
     q.work = q.ctl.p + n_counts;
     q.lv.ovf = q.ovf.p;
@@ -1001,16 +1023,36 @@ static void launch_shadow(crtb200_ctx *c, const Frame &fr, const Levels &lv, uin
     k_shadow<COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, work);
 }
 
-template <bool CULL>
-static void launch_coop_closest(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, cudaStream_t st) {
-  if (primary)
-    k_coop<false, true, CULL, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
-  else
-    k_coop<false, false, CULL, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, level);
+// k_coop around one traversal launch.  coop_begin forks the side stream BEFORE the traversal kernel is
+// launched; coop_end marks the traversal kernel's end behind it, starts the early pass on the side stream (its blocks
+// get SM resources as the traversal kernel's blocks exit), joins, and runs the final pass over what is left.
+static int coop_begin(crtb200_ctx *c, crtb200_ctx::QueueSet &q) {
+  if (!c->coop_early) return CRTB200_OK;
+  CUDA_TRY(cudaEventRecord(q.coop_fork, q.stream));
+  CUDA_TRY(cudaStreamWaitEvent(q.coop_stream, q.coop_fork, 0));
+  return CRTB200_OK;
 }
-template <bool CULL>
-static void launch_coop_shadow(crtb200_ctx *c, const Frame &fr, const Levels &lv, cudaStream_t st) {
-  k_coop<true, false, CULL, CRT_COOP_GROUP><<<c->blocks_coop, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, lv, 0);
+template <bool SHADOW, bool CULL>
+static int coop_end(crtb200_ctx *c, crtb200_ctx::QueueSet &q, bool primary, const Frame &fr, uint32_t level, uint32_t &launches) {
+  const uint32_t launch = SHADOW ? (uint32_t)CRT_MAX_LEVELS : level;
+  auto run = [&](int blocks, cudaStream_t st, uint32_t early) {
+    if (SHADOW)
+      k_coop<true, false, CULL, CRT_COOP_GROUP><<<blocks, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, q.lv, 0, early);
+    else if (primary)
+      k_coop<false, true, CULL, CRT_COOP_GROUP><<<blocks, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, q.lv, level, early);
+    else
+      k_coop<false, false, CULL, CRT_COOP_GROUP><<<blocks, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, q.lv, level, early);
+    launches++;
+  };
+  if (c->coop_early) {
+    k_mark<<<1, 32, 0, q.stream>>>(q.lv.ovf_ctl + 4u * launch + 3u);
+    run(c->sm_count * c->coop_early, q.coop_stream, 1u);
+    CUDA_TRY(cudaEventRecord(q.coop_join, q.coop_stream));
+    CUDA_TRY(cudaStreamWaitEvent(q.stream, q.coop_join, 0));
+    launches++;
+  }
+  run(c->blocks_coop, q.stream, 0u);
+  return CRTB200_OK;
 }
 
 // Host destinations of crtb200_render: each chunk's band of rows is copied back on the chunk's own stream right after
@@ -1109,6 +1151,10 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
         cudaEventRecord(next_event(c), qs);
         c->kev_kind.push_back(0);
       }
+      if (handoff) {
+        rc = coop_begin(c, q);
+        if (rc) return rc;
+      }
       if (o->count_work && cull)
         launch_closest<true, true>(c, l == 0, fr, q.lv, l, q.work + l, qs);
       else if (o->count_work)
@@ -1123,11 +1169,8 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
           cudaEventRecord(next_event(c), qs);
           c->kev_kind.push_back(2);
         }
-        if (cull)
-          launch_coop_closest<true>(c, l == 0, fr, q.lv, l, qs);
-        else
-          launch_coop_closest<false>(c, l == 0, fr, q.lv, l, qs);
-        launches++;
+        rc = cull ? coop_end<false, true>(c, q, l == 0, fr, l, launches) : coop_end<false, false>(c, q, l == 0, fr, l, launches);
+        if (rc) return rc;
       }
       if (per_kernel) cudaEventRecord(next_event(c), qs);
       k_shade<<<grid_simple, 256, 0, qs>>>(c->sc, fr, q.lv, l);
@@ -1138,6 +1181,10 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       c->kev_kind.push_back(1);
     }
     uint32_t *swork = q.work + CRT_MAX_LEVELS;
+    if (handoff) {
+      rc = coop_begin(c, q);
+      if (rc) return rc;
+    }
     if (o->count_work == 1)
       launch_shadow<1, false>(c, fr, q.lv, swork, qs);
     else if (o->count_work == 2 && cull)
@@ -1154,11 +1201,8 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
         cudaEventRecord(next_event(c), qs);
         c->kev_kind.push_back(3);
       }
-      if (cull)
-        launch_coop_shadow<true>(c, fr, q.lv, qs);
-      else
-        launch_coop_shadow<false>(c, fr, q.lv, qs);
-      launches++;
+      rc = cull ? coop_end<true, true>(c, q, false, fr, 0, launches) : coop_end<true, false>(c, q, false, fr, 0, launches);
+      if (rc) return rc;
     }
     if (per_kernel) cudaEventRecord(next_event(c), qs);
     k_accumulate<<<grid_simple, 256, 0, qs>>>(c->sc, fr, q.lv);
@@ -1182,6 +1226,16 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       if (host->rgb) CUDA_TRY(cudaMemcpyAsync(host->rgb + off * 3, d_rgb + off * 3, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, cs));
       if (host->rgb8) CUDA_TRY(cudaMemcpyAsync(host->rgb8 + off * 3, d_rgb8 + off * 3, cnt * 3, cudaMemcpyDeviceToHost, cs));
       if (host->hits) CUDA_TRY(cudaMemcpyAsync(host->hits + off, d_hits + off, cnt * sizeof(HitRec), cudaMemcpyDeviceToHost, cs));
+      if (getenv("CRT_CHUNK_TIMES")) {
+        while (c->dbg_ev.size() < 2 * (size_t)(chunk + 1)) {
+          cudaEvent_t e = nullptr;
+          CUDA_TRY(cudaEventCreate(&e));
+          c->dbg_ev.push_back(e);
+        }
+        CUDA_TRY(cudaEventRecord(c->dbg_ev[2 * chunk], qs));
+        CUDA_TRY(cudaEventRecord(c->dbg_ev[2 * chunk + 1], cs));
+        c->dbg_chunks = chunk + 1;
+      }
     }
   }
   if (band_stream) {
@@ -1378,10 +1432,23 @@ int crtb200_render(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_opti
     if (rgb8_out) CUDA_TRY(cudaMemcpyAsync(rgb8_out, c->frame8.p, px * 3, cudaMemcpyDeviceToHost, c->stream));
     if (hits_out) CUDA_TRY(cudaMemcpyAsync(hits_out, c->hits.p, px * sizeof(HitRec), cudaMemcpyDeviceToHost, c->stream));
   }
+  const double enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const double sync_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   rc = collect_stats(c, true);
   if (rc) return rc;
   c->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (banded && c->dbg_chunks && getenv("CRT_CHUNK_TIMES")) {
+    fprintf(stderr, "[chunk times] host: enqueue %.3f ms, synchronised %.3f ms, stats read %.3f ms; device frame %.3f ms\n", enqueue_ms, sync_ms,
+            c->last.total_ms, c->last.device_ms);
+    for (uint32_t k = 0; k < c->dbg_chunks; k++) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, c->ev[0], c->dbg_ev[2 * k]);
+      cudaEventElapsedTime(&b, c->ev[0], c->dbg_ev[2 * k + 1]);
+      fprintf(stderr, "[chunk times]   chunk %u (%u items, set %u): stored at %.3f ms, band on the host at %.3f ms\n", k, c->chunk_items[k], k % c->cap_sets, a, b);
+    }
+    c->dbg_chunks = 0;
+  }
   if (stats) *stats = c->last;
   return CRTB200_OK;
 }
