@@ -208,13 +208,12 @@ struct crtb200_ctx {
   uint32_t cap_items = 0;
   uint32_t cap_depth = 0xFFFFFFFFu;
   uint32_t cap_sets = 0;
-  // chunk schedule of the current plan: item counts in launch order (chunk k runs on set k % cap_sets).  Equal chunks,
-  // except that the FIRST chunk of every set of a host-bound frame is shortened / lengthened by `stagger` so that the sets
-  // finish their chunks one after the other instead of all at once: the band copies then ride behind the traversal of
-  // the other sets instead of queueing up on the copy engine at half time and at the end (tools/e2e_time.py)
-  int coop_early = 3;  // blocks per SM of k_coop's early pass (0 = final pass only); env CRT_COOP_EARLY
-  std::vector<uint32_t> chunk_items;
-  float stagger = 0.15f;
+  // blocks per SM of k_coop's early pass (0 = final pass only); env CRT_COOP_EARLY.  Used for the primary level and the
+  // shadow pass of frames that run on ONE stream (device frames, tile shards): with several chunk streams the tails
+  // already overlap other chunks' work and waiting blocks would only take SM resources from them (run r2ad: 4.1 -> 8 ms);
+  // the small secondary levels pay more for the extra launches and joins than they gain (hw11_room +2 %)
+  int coop_early = CRT_COOP_MIN_BLOCKS;
+  uint32_t n_chunks = 0;  // chunks of the current plan (chunk k runs on set k % cap_sets)
   cudaStream_t band_stream = nullptr;  // device -> host band copies of a chunked host-bound frame
   cudaEvent_t band_done = nullptr;
   std::vector<cudaEvent_t> chunk_done;
@@ -291,7 +290,6 @@ int crtb200_create(int device, crtb200_ctx **out) {
   if (const char *env = getenv("CRT_TAIL_START")) c->tail_start = std::max(0, atoi(env));
   if (const char *env = getenv("CRT_TAIL_SMALL")) c->tail_small = std::max(0, atoi(env));
   if (const char *env = getenv("CRT_COOP_EARLY")) c->coop_early = std::max(0, std::min(CRT_COOP_MIN_BLOCKS, atoi(env)));
-  if (const char *env = getenv("CRT_CHUNK_STAGGER")) c->stagger = std::min(0.3f, std::max(0.0f, (float)atof(env)));  // tools: e2e tuning
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
   c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
   if (c->l2_persist && c->l2_persist_max)
@@ -861,40 +859,12 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
   const uint32_t parts = n_sets * per_set;
   uint64_t even = ((uint64_t)shard_items + parts - 1) / parts;
   even = ((even + row_items - 1) / row_items) * row_items;
-  // staggered first round (see crtb200_ctx::chunk_items): set k's first chunk is (1 + (k - (n_sets - 1) / 2) * stagger)
-  // times the mean; the queues are sized for the largest chunk
-  std::vector<uint32_t> sched;
-  if (pipelined && n_sets > 1 && per_set > 1 && c->stagger > 0.0f && shard_items >= parts * row_items) {
-    const double mean = (double)shard_items / parts;
-    uint64_t placed = 0;
-    for (uint32_t k = 0; k < parts; k++) {
-      double w = k < n_sets ? 1.0 + ((double)k - 0.5 * (n_sets - 1)) * c->stagger : 1.0;
-      uint64_t n = (uint64_t)(mean * w / row_items + 0.5) * row_items;
-      n = std::max<uint64_t>(n, row_items);
-      if (k + 1 == parts || placed + n > shard_items) n = shard_items - placed;
-      sched.push_back((uint32_t)n);
-      placed += n;
-      if (placed == shard_items) break;
-    }
-    uint64_t largest = 0;
-    for (uint32_t n : sched) largest = std::max<uint64_t>(largest, n);
-    largest = ((largest + row_items - 1) / row_items) * row_items;
-    if (largest <= items) even = largest; else sched.clear();  // (budget too small: equal chunks of what fits)
-  }
   items = std::min<uint64_t>(items, even);
   // node ids and (diffuse item, light) slots are 32-bit on the device
   if (items * sum * n_lights >= 0x7FFFFFFFull) items = ((0x7FFFFFFFull / (sum * n_lights)) - 32) & ~31ull;
   if (items < 32) return fail(CRTB200_ERR_MEMORY, "too many lights x ray-tree nodes for 32-bit queue slots");
   if (items >= row_items) items = (items / row_items) * row_items;  // whole tile rows (band copies need it)
-  for (uint32_t n : sched)
-    if (n > items) {  // (a later clamp shrank the queues)
-      sched.clear();
-      break;
-    }
-  if (sched.empty()) {
-    for (uint64_t b = 0; b < shard_items; b += items) sched.push_back((uint32_t)std::min<uint64_t>(items, shard_items - b));
-  }
-  c->chunk_items = sched;
+  c->n_chunks = (uint32_t)((shard_items + items - 1) / items);
   if (c->cap_items == items && c->cap_depth == max_depth && c->cap_sets == n_sets) return CRTB200_OK;
   if (c->sets.size() < n_sets) c->sets.resize(n_sets);
   if (!c->fork_ev) CUDA_TRY(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
@@ -1026,8 +996,11 @@ static void launch_shadow(crtb200_ctx *c, const Frame &fr, const Levels &lv, uin
 // k_coop around one traversal launch.  coop_begin forks the side stream BEFORE the traversal kernel is
 // launched; coop_end marks the traversal kernel's end behind it, starts the early pass on the side stream (its blocks
 // get SM resources as the traversal kernel's blocks exit), joins, and runs the final pass over what is left.
-static int coop_begin(crtb200_ctx *c, crtb200_ctx::QueueSet &q) {
-  if (!c->coop_early) return CRTB200_OK;
+static bool coop_early_on(const crtb200_ctx *c, bool secondary_level) {
+  return c->coop_early > 0 && c->cap_sets == 1 && !secondary_level;
+}
+static int coop_begin(crtb200_ctx *c, crtb200_ctx::QueueSet &q, bool secondary_level) {
+  if (!coop_early_on(c, secondary_level)) return CRTB200_OK;
   CUDA_TRY(cudaEventRecord(q.coop_fork, q.stream));
   CUDA_TRY(cudaStreamWaitEvent(q.coop_stream, q.coop_fork, 0));
   return CRTB200_OK;
@@ -1044,7 +1017,7 @@ static int coop_end(crtb200_ctx *c, crtb200_ctx::QueueSet &q, bool primary, cons
       k_coop<false, false, CULL, CRT_COOP_GROUP><<<blocks, 32 * CRT_COOP_WARPS, 0, st>>>(c->sc, fr, q.lv, level, early);
     launches++;
   };
-  if (c->coop_early) {
+  if (coop_early_on(c, !SHADOW && !primary)) {
     k_mark<<<1, 32, 0, q.stream>>>(q.lv.ovf_ctl + 4u * launch + 3u);
     run(c->sm_count * c->coop_early, q.coop_stream, 1u);
     CUDA_TRY(cudaEventRecord(q.coop_join, q.coop_stream));
@@ -1130,17 +1103,17 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   if (band_stream) {
     if (!c->band_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->band_stream, cudaStreamNonBlocking));
     if (!c->band_done) CUDA_TRY(cudaEventCreateWithFlags(&c->band_done, cudaEventDisableTiming));
-    while (c->chunk_done.size() < c->chunk_items.size()) {
+    while (c->chunk_done.size() < c->n_chunks) {
       cudaEvent_t e = nullptr;
       CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       c->chunk_done.push_back(e);
     }
   }
-  for (uint32_t begin = 0; chunk < c->chunk_items.size() && begin < shard_items; begin += c->chunk_items[chunk], chunk++) {
+  for (uint32_t begin = 0; begin < shard_items; begin += c->cap_items, chunk++) {
     crtb200_ctx::QueueSet &q = c->sets[chunk % n_sets];
     cudaStream_t qs = q.stream;
     fr.item_begin = begin;
-    fr.n_items0 = std::min(c->chunk_items[chunk], shard_items - begin);
+    fr.n_items0 = std::min(c->cap_items, shard_items - begin);
     CUDA_TRY(cudaMemsetAsync(q.ctl.p, 0, q.ctl.n * sizeof(uint32_t), qs));
     q.lv.tail_iters = handoff ? (uint32_t)(c->tail_iters + 1) : 0u;
     q.lv.skip_zero_terms = (o->traversal == 0 && o->count_work != 1) ? 1u : 0u;
@@ -1152,7 +1125,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
         c->kev_kind.push_back(0);
       }
       if (handoff) {
-        rc = coop_begin(c, q);
+        rc = coop_begin(c, q, l != 0);
         if (rc) return rc;
       }
       if (o->count_work && cull)
@@ -1182,7 +1155,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     }
     uint32_t *swork = q.work + CRT_MAX_LEVELS;
     if (handoff) {
-      rc = coop_begin(c, q);
+      rc = coop_begin(c, q, false);
       if (rc) return rc;
     }
     if (o->count_work == 1)
@@ -1445,7 +1418,7 @@ int crtb200_render(crtb200_ctx *c, const crtb200_camera *cam, const crtb200_opti
       float a = 0.f, b = 0.f;
       cudaEventElapsedTime(&a, c->ev[0], c->dbg_ev[2 * k]);
       cudaEventElapsedTime(&b, c->ev[0], c->dbg_ev[2 * k + 1]);
-      fprintf(stderr, "[chunk times]   chunk %u (%u items, set %u): stored at %.3f ms, band on the host at %.3f ms\n", k, c->chunk_items[k], k % c->cap_sets, a, b);
+      fprintf(stderr, "[chunk times]   chunk %u (up to %u items, set %u): stored at %.3f ms, band on the host at %.3f ms\n", k, c->cap_items, k % c->cap_sets, a, b);
     }
     c->dbg_chunks = 0;
   }
