@@ -55,7 +55,7 @@ struct Levels {
                       // record index of the early / the final k_coop pass, [4L+3] != 0 once the traversal kernel has ended
   uint32_t ovf_cap;     // walks k_coop can take per launch (about two per resident k_coop warp): hand-off stops there
   uint32_t tail_iters;  // 0 = off; else tail_iters - 1 = the floor of the hand-off threshold (see tail_policy)
-  uint32_t tail_start;  // the threshold's value when the queue of a large launch has just run dry (1024)
+  uint32_t tail_start;  // the threshold's value when the queue of a large launch has just run dry (512)
   uint32_t tail_small;  // launches of at most this many rays hand off at the floor from the start (see tail_policy)
   uint32_t skip_zero_terms;  // 1 (default traversal): shadow rays whose light term is exactly zero are answered without a walk
 };
@@ -251,7 +251,7 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, const
 // A walk costs k_coop about five times the instructions it costs a lane here (profiles/r2_tuning.md), so k_coop pays
 // only for walks whose serial latency would otherwise set the kernel's end, and only while it is not itself the
 // bottleneck:
-//   large launch (total > lanes)   the queue runs dry late, with walks of every age in flight.  Threshold = 1024
+//   large launch (total > lanes)   the queue runs dry late, with walks of every age in flight.  Threshold = 512
 //                                  node-phase iterations when the queue has just run dry, halved every 4 rounds
 //                                  (~20 us) down to the floor: the longest walks go first, and k_coop's capacity
 //                                  (Levels::ovf_cap) closes the hand-off.

@@ -147,10 +147,10 @@ struct crtb200_ctx {
   bool nested_ok = false;    // every child box of the uploaded mesh trees lies inside its parent's and no tree is deeper
                              // than the k_coop LIFO allows: the order-free walk of k_coop and the subtree culling are exact
   int tail_iters = 16;       // tail hand-off (crt_kernels.cuh): once a traversal kernel's queue is dry, walks longer than a
-                             // falling threshold (1024 node-phase iterations, halved every 4 rounds, never below this
+                             // falling threshold (512 node-phase iterations, halved every 4 rounds, never below this
                              // floor) go to k_coop.  CRT_TAIL_ITERS overrides (tools / tests): 0 = every walk still
-                             // running (the threshold still falls from 1024), -1 = off
-  int tail_start = 1024;     // CRT_TAIL_START (tests): the threshold's starting value
+                             // running (the threshold still falls from 512), -1 = off
+  int tail_start = 512;      // CRT_TAIL_START (tests): the threshold's starting value
   int tail_small = 32768;    // CRT_TAIL_SMALL: launches of at most this many rays hand off at the floor from the start
   int tail_cap = 8;          // hand-off capacity per launch, in walks per resident k_coop warp (CRT_TAIL_CAP; tests use
                              // a huge value so that every walk goes through k_coop)
@@ -907,7 +907,7 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     q.lv.ovf_ctl = q.ctl.p + n_counts + n_work;
     q.lv.ovf_cap = (uint32_t)std::min<uint64_t>(ovf_cap, (uint64_t)c->tail_cap * c->blocks_coop * CRT_COOP_WARPS);
     q.lv.tail_iters = 0;
-    q.lv.tail_start = 1024;
+    q.lv.tail_start = 512;
     q.lv.tail_small = 0;
     q.lv.skip_zero_terms = 0;
     q.lv.ray_o = q.ray_o.p;
