@@ -22,11 +22,12 @@ is quoted on that fits one GPU.
   literal_walk  the reference's visit-all itinerary (traversal = 1) beside the default, with the pixel difference (0)
 
 N > 1 (torchrun), scene replicated per GPU:
-  tiles (default)                 one frame, 8x4-pixel tiles dealt round-robin, float slabs gathered to rank 0 over NCCL
-                                  and scattered into the frame.  Strong scaling: total work fixed.  The assembled frame is
-                                  checked bit-equal to the single-GPU frame before timing (tiles_check).  --tile-transport
-                                  peer stores straight into rank 0's frame (CUDA IPC) instead; the other transport is timed
-                                  as `tiles_other_transport`, the frames partition as `frames_mode`.
+  tiles (default)                 one frame, 8x4-pixel tiles dealt round-robin; every rank's store kernel writes its tiles
+                                  straight into rank 0's frame (peer memory over NVLink, CUDA IPC; one tiny NCCL all-reduce as
+                                  completion barrier).  Strong scaling: total work fixed.  The frame is checked bit-equal to
+                                  the single-GPU frame before timing (tiles_check).  --tile-transport gather: compact float
+                                  slabs gathered to rank 0 over NCCL and scattered into the frame instead; the other transport
+                                  is timed as `tiles_other_transport`, the frames partition as `frames_mode`.
   --parallelism frames            every rank renders one frame of the sequence per step, PPMColor bytes gathered to rank 0
                                   over NCCL overlapped with the next render.  Weak scaling: per-GPU work fixed.
   --animation F                   config 5's orbit: frame f on rank f % N, frames gathered to rank 0.
@@ -858,9 +859,10 @@ def main():
     ap.add_argument("--parallelism", default="auto", choices=["auto", "frames", "tiles"],
                     help="N > 1: tiles (default) = one frame split by 8x4 tiles (strong scaling, config 4); frames = one frame per GPU per step (weak)")
     ap.add_argument("--no-config5", action="store_true", help="skip the synthetic_10M sub-record (N = 1)")
-    ap.add_argument("--tile-transport", default="gather", choices=["gather", "peer"],
-                    help="tiles, N > 1: gather (default) = compact slabs, one NCCL gather over NVLink, crtb200_assemble_shards; "
-                         "peer = every rank's store kernel writes into rank 0's frame (CUDA IPC).  The other one is timed as an extra key")
+    ap.add_argument("--tile-transport", default="peer", choices=["gather", "peer"],
+                    help="tiles, N > 1: peer (default) = every rank's store kernel writes its tiles into rank 0's frame with 16-byte stores "
+                         "(CUDA IPC over NVLink; one NCCL all-reduce as completion barrier); gather = compact slabs, one NCCL gather, "
+                         "crtb200_assemble_shards.  The other one is timed as an extra key")
     ap.add_argument("--concurrency", type=int, default=4, help="chunks of a frame in flight on separate streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--animation", type=int, default=0, help="F > 0: a step is the F-frame orbit animation (config 5), frames round-robin over GPUs")

@@ -266,20 +266,30 @@ def gpu_coop_mid(built):
 
 
 @pytest.fixture(scope="module")
+def gpu_coop_final_only(built):
+    """Every walk handed off, and k_coop's early pass (next to the traversal kernel) switched off: the final pass alone."""
+    ctx = _ctx_with_env(built, CRT_TAIL_ITERS=0, CRT_TAIL_START=0, CRT_TAIL_SMALL=100000000, CRT_TAIL_CAP=1000000, CRT_COOP_EARLY=0)
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
 def gpu_no_handoff(built):
     ctx = _ctx_with_env(built, CRT_TAIL_ITERS=-1)
     yield ctx
     ctx.close()
 
 
-@pytest.mark.parametrize("which", ["all", "mid", "off"])
+@pytest.mark.parametrize("which", ["all", "mid", "final_only", "off"])
 @pytest.mark.parametrize("name", list(SMALL_SCENES))
-def test_tail_handoff_matches_golden(name, which, gpu_coop_all, gpu_coop_mid, gpu_no_handoff, loaded, crt):
+def test_tail_handoff_matches_golden(name, which, gpu_coop_all, gpu_coop_mid, gpu_coop_final_only, gpu_no_handoff, loaded, crt):
     """k_coop explores a handed-off walk in a different order (a LIFO of subtrees, 32 boxes per iteration); by the nesting
     property the set of tested leaves is the same, and closest-hit candidates are put back into the reference's
     encounter order by their (leaf, reference) key -- so hit ids, t and every pixel stay bit-identical to the
-    reference fixtures, with culling (traversal 0) and without (traversal 1 has no hand-off: literal walk)."""
-    ctx = {"all": gpu_coop_all, "mid": gpu_coop_mid, "off": gpu_no_handoff}[which]
+    reference fixtures, with culling (traversal 0) and without (traversal 1 has no hand-off: literal walk).  "all" and "mid"
+    run k_coop's early pass next to the traversal kernel plus the final pass behind it (small frames run on one stream),
+    "final_only" the final pass alone."""
+    ctx = {"all": gpu_coop_all, "mid": gpu_coop_mid, "final_only": gpu_coop_final_only, "off": gpu_no_handoff}[which]
     sf, flat, rects, n = loaded[name]
     ctx.upload(flat, keepalive=sf)
     rgb, rgb8, hits, st = ctx.render(sf.camera(), crt.make_options(rects=rects, n_rects=n), want_rgb8=True, want_hits=True)
@@ -290,7 +300,7 @@ def test_tail_handoff_matches_golden(name, which, gpu_coop_all, gpu_coop_mid, gp
     assert same_f32(hits["t"][h], g["hits"]["t"][h]).all()
     _assert_pixels(name, rgb, g["rgb"], rgb8, g["ppm"])
     assert [st["rays_primary"], st["rays_shadow"], st["rays_reflection"], st["rays_refraction"]] == list(g["rays"])
-    if which == "all" and name not in ("empty_scene",):
+    if which in ("all", "final_only") and name not in ("empty_scene",):
         assert st["handoff_closest"] > 0  # (warps that fetched their rays before the queue ran dry poll it every 4th round)
     if which == "off":
         assert st["handoff_closest"] == 0 and st["handoff_shadow"] == 0
