@@ -22,6 +22,12 @@ namespace crtd {
 #ifndef CRT_TRAV_MIN_BLOCKS
 #define CRT_TRAV_MIN_BLOCKS 4   // resident CTAs per SM the register allocation is bounded for
 #endif
+#ifndef CRT_TRAV_MIN_BLOCKS_SEC
+// ... of k_closest's secondary-level instantiation.  A secondary level has ~18 warps' worth of rays per SM and is bound
+// by the latency of each warp's instruction chain, not by occupancy: 3 blocks = 76-85 registers, no spills
+// (run r2aj: hw11_room 2.79 -> 2.61 ms; the primary and shadow kernels lose 4-5 % with 3).
+#define CRT_TRAV_MIN_BLOCKS_SEC 3
+#endif
 #define CRT_MAX_LEVELS 34
 
 struct Frame {
@@ -312,7 +318,7 @@ CRT_DI bool tail_handoff(const Levels &lv, const uint32_t launch, const bool wan
 // in profiles/r1_tuning.md, their code is gone.)
 // ------------------------------------------------------------------------------------------------------------
 template <bool PRIMARY, bool COUNT, int REFILL, int MODE, bool CULL, bool WIDE>
-__global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_closest(const DScene sc, const Frame fr, const Levels lv, const uint32_t level,
+__global__ void __launch_bounds__(CRT_TRAV_BLOCK, PRIMARY ? CRT_TRAV_MIN_BLOCKS : CRT_TRAV_MIN_BLOCKS_SEC) k_closest(const DScene sc, const Frame fr, const Levels lv, const uint32_t level,
                                                 uint32_t *__restrict__ work_counter) {
   static_assert(MODE == 2, "only loop mode 2 is implemented");
   __shared__ WarpShare s_ws[CRT_TRAV_BLOCK / 32];

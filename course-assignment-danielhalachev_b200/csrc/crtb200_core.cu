@@ -24,7 +24,13 @@
 using namespace crtd;
 
 #ifndef CRT_REFILL
-#define CRT_REFILL 8  // refill a warp when at least this many lanes are idle
+#define CRT_REFILL 16  // refill a warp when at least this many lanes are idle (8 until run r2aj: hw14 2.92 -> 2.77 ms)
+#endif
+#ifndef CRT_REFILL_CLOSEST
+#define CRT_REFILL_CLOSEST CRT_REFILL
+#endif
+#ifndef CRT_REFILL_SHADOW
+#define CRT_REFILL_SHADOW CRT_REFILL
 #endif
 #ifndef CRT_LOOP_MODE
 #define CRT_LOOP_MODE 2  // 0 = while-while, 1 = merged loop, 2 = node phase + warp-cooperative triangle phase (crt_kernels.cuh)
@@ -220,7 +226,7 @@ struct crtb200_ctx {
   std::vector<cudaEvent_t> dbg_ev;  // CRT_CHUNK_TIMES (tools): per chunk, end of k_store and end of its band copy
   uint32_t dbg_chunks = 0;
 
-  int blocks_closest = 0, blocks_shadow = 0, blocks_coop = 0;
+  int blocks_closest = 0, blocks_closest_sec = 0, blocks_shadow = 0, blocks_coop = 0;
   crtb200_stats last{};
   bool last_pending = false;
 
@@ -274,15 +280,17 @@ int crtb200_create(int device, crtb200_ctx **out) {
   }
   for (auto &e : c->ev) cudaEventCreate(&e);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL, CRT_LOOP_MODE, false, false>, CRT_TRAV_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<true, false, CRT_REFILL_CLOSEST, CRT_LOOP_MODE, false, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_closest = std::max(1, occ) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<0, CRT_REFILL, CRT_LOOP_MODE, false, false>, CRT_TRAV_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_closest<false, false, CRT_REFILL_CLOSEST, CRT_LOOP_MODE, false, false>, CRT_TRAV_BLOCK, 0);
+  c->blocks_closest_sec = std::max(1, occ) * c->sm_count;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<0, CRT_REFILL_SHADOW, CRT_LOOP_MODE, false, false>, CRT_TRAV_BLOCK, 0);
   c->blocks_shadow = std::max(1, occ) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_coop<true, false, true, CRT_COOP_GROUP>, 32 * CRT_COOP_WARPS, 0);
   c->blocks_coop = std::max(1, occ) * c->sm_count;
   if (const char *env = getenv("CRT_BLOCKS_PER_SM")) {  // tuning only (tools/): resident persistent CTAs per SM
     const int b = atoi(env);
-    if (b > 0) c->blocks_closest = c->blocks_shadow = b * c->sm_count;
+    if (b > 0) c->blocks_closest = c->blocks_closest_sec = c->blocks_shadow = b * c->sm_count;
   }
   if (const char *env = getenv("CRT_L2_PERSIST")) c->l2_persist = atoi(env);
   if (const char *env = getenv("CRT_TAIL_ITERS")) c->tail_iters = std::max(-1, atoi(env));
@@ -971,9 +979,9 @@ template <bool COUNT, bool CULL, bool WIDE>
 static void launch_closest_w(crtb200_ctx *c, bool primary, const Frame &fr, const Levels &lv, uint32_t level, uint32_t *work,
                              cudaStream_t st) {
   if (primary)
-    k_closest<true, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL, WIDE><<<c->blocks_closest, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, level, work);
+    k_closest<true, COUNT, CRT_REFILL_CLOSEST, CRT_LOOP_MODE, CULL, WIDE><<<c->blocks_closest, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, level, work);
   else
-    k_closest<false, COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL, WIDE><<<c->blocks_closest, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, level, work);
+    k_closest<false, COUNT, CRT_REFILL_CLOSEST, CRT_LOOP_MODE, CULL, WIDE><<<c->blocks_closest_sec, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, level, work);
 }
 // the WIDE flavour (visited-mesh set in shared memory) only for scenes that need it, and never when counting the
 // reference's visit-all work (no de-duplication there)
@@ -988,9 +996,9 @@ static void launch_closest(crtb200_ctx *c, bool primary, const Frame &fr, const 
 template <int COUNT, bool CULL>
 static void launch_shadow(crtb200_ctx *c, const Frame &fr, const Levels &lv, uint32_t *work, cudaStream_t st) {
   if (COUNT != 1 && c->sc.dedup_meshes == 2u)
-    k_shadow<COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL, (COUNT != 1)><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, work);
+    k_shadow<COUNT, CRT_REFILL_SHADOW, CRT_LOOP_MODE, CULL, (COUNT != 1)><<<c->blocks_shadow, CRT_TRAV_BLOCK, dyn_smem(c, CRT_TRAV_BLOCK), st>>>(c->sc, fr, lv, work);
   else
-    k_shadow<COUNT, CRT_REFILL, CRT_LOOP_MODE, CULL, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, work);
+    k_shadow<COUNT, CRT_REFILL_SHADOW, CRT_LOOP_MODE, CULL, false><<<c->blocks_shadow, CRT_TRAV_BLOCK, 0, st>>>(c->sc, fr, lv, work);
 }
 
 // k_coop around one traversal launch.  coop_begin forks the side stream BEFORE the traversal kernel is
