@@ -57,8 +57,9 @@ struct Levels {
   // tail hand-off (k_coop): once the work queue of a traversal kernel is dry, the walks still running are written to
   // ovf[] (3 x uint4 per record) and finished one WARP per ray; tail_grace = 0 switches this off
   uint4 *ovf;
-  uint32_t *ovf_ctl;  // per traversal launch L (level, or CRT_MAX_LEVELS for the shadow pass): [4L] written, [4L+1] / [4L+2] next
-                      // record index of the early / the final k_coop pass, [4L+3] != 0 once the traversal kernel has ended
+  uint32_t *ovf_ctl;  // per traversal launch L (level, or CRT_MAX_LEVELS for the shadow pass) one 128-byte line at
+                      // ovf_ctl + 32 L: [0] written, [8] / [16] next record index of the early / the final k_coop pass,
+                      // [24] != 0 once the traversal kernel has ended
   uint32_t ovf_cap;     // walks k_coop can take per launch (about two per resident k_coop warp): hand-off stops there
   uint32_t tail_iters;  // 0 = off; else tail_iters - 1 = the floor of the hand-off threshold (see tail_policy)
   uint32_t tail_start;  // the threshold's value when the queue of a large launch has just run dry (512)
@@ -266,6 +267,12 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, const
 //                                  from the start.  With more (the secondary levels of a whole reflective frame:
 //                                  ~90 k rays, half of them long) k_coop would be the bottleneck: no hand-off.
 // Returns the threshold start value, or CRT_INVALID for "no hand-off in this launch".
+#ifndef CRT_TAIL_DECAY_SHIFT
+#define CRT_TAIL_DECAY_SHIFT 2  // the threshold halves every 2^this rounds once the queue is dry
+#endif
+#ifndef CRT_TAIL_POLL_MASK
+#define CRT_TAIL_POLL_MASK 3    // the global work cursor is polled every (this + 1)-th round
+#endif
 CRT_DI uint32_t tail_policy(const Levels &lv, const uint32_t total) {
   if (!lv.tail_iters) return CRT_INVALID;
   const uint32_t lanes = gridDim.x * blockDim.x;
@@ -273,13 +280,21 @@ CRT_DI uint32_t tail_policy(const Levels &lv, const uint32_t total) {
   return total <= lv.tail_small ? lv.tail_iters - 1u : CRT_INVALID;
 }
 CRT_DI uint32_t tail_threshold(const Levels &lv, const uint32_t start, const uint32_t dry_rounds) {
-  const uint32_t sh = dry_rounds >> 2, t = sh < 31u ? (start >> sh) : 0u;
+  const uint32_t sh = dry_rounds >> CRT_TAIL_DECAY_SHIFT, t = sh < 31u ? (start >> sh) : 0u;
   return t > lv.tail_iters - 1u ? t : lv.tail_iters - 1u;
 }
-CRT_DI bool queue_dry(const uint32_t *work_counter, const uint32_t total) {
+// Every hot counter of a launch has a 128-byte line of its own (CRT_CTL_STRIDE words): the work cursor (one atomicAdd per
+// refill of every warp), its "dry" flag, and the hand-off counters.  The warps poll the FLAG, which the warp that takes
+// the last rays sets, so the 4 700 readers stay off the line the refills' atomics go to.
+#define CRT_CTL_STRIDE 32u
+#define CRT_DRY_FLAG 16u  // word offset of the dry flag behind a work cursor
+CRT_DI bool queue_dry(const uint32_t *work_counter) {
   uint32_t v = 0;
-  if (lane_id() == 0) v = *reinterpret_cast<const volatile uint32_t *>(work_counter);
-  return __shfl_sync(CRT_FULL_MASK, v, 0) >= total;
+  if (lane_id() == 0) v = *reinterpret_cast<const volatile uint32_t *>(work_counter + CRT_DRY_FLAG);
+  return __shfl_sync(CRT_FULL_MASK, v, 0) != 0u;
+}
+CRT_DI void queue_mark_dry(uint32_t *work_counter) {
+  if (lane_id() == 0) *reinterpret_cast<volatile uint32_t *>(work_counter + CRT_DRY_FLAG) = 1u;
 }
 // `closed` (warp-uniform) is set once the record buffer is full: the warp stops asking
 CRT_DI bool tail_handoff(const Levels &lv, const uint32_t launch, const bool want, const uint32_t id, const Trav &tv,
@@ -287,7 +302,7 @@ CRT_DI bool tail_handoff(const Levels &lv, const uint32_t launch, const bool wan
   const uint32_t wm = __ballot_sync(CRT_FULL_MASK, want);
   if (!wm) return false;
   uint32_t base = 0;
-  if (lane_id() == 0) base = atomicAdd(&lv.ovf_ctl[4u * launch], (uint32_t)__popc(wm));
+  if (lane_id() == 0) base = atomicAdd(&lv.ovf_ctl[CRT_CTL_STRIDE * launch], (uint32_t)__popc(wm));
   base = __shfl_sync(CRT_FULL_MASK, base, 0);
   const uint32_t r = base + __popc(wm & lanemask_lt());
   if (base + (uint32_t)__popc(wm) >= lv.ovf_cap) closed = true;
@@ -350,7 +365,10 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, PRIMARY ? CRT_TRAV_MIN_BLOCKS 
       uint32_t start = 0;
       if (lane == 0) start = atomicAdd(work_counter, want);
       start = __shfl_sync(CRT_FULL_MASK, start, 0);
-      if (start + want >= total) exhausted = true;
+      if (start + want >= total) {
+        if (!exhausted && start < total) queue_mark_dry(work_counter);  // (the warp that takes the last rays)
+        exhausted = true;
+      }
       const uint32_t i = start + __popc(idle & lanemask_lt());
       if (!active && i < total) {
         bool valid = true;
@@ -382,7 +400,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, PRIMARY ? CRT_TRAV_MIN_BLOCKS 
       }
     }
     if (!COUNT && tail_start != CRT_INVALID) {
-      if (!exhausted && (++round & 3u) == 0u) exhausted = queue_dry(work_counter, total);
+      if (!exhausted && (++round & (uint32_t)CRT_TAIL_POLL_MASK) == 0u) exhausted = queue_dry(work_counter);
       if (exhausted && !closed) {
         const uint32_t thr = tail_threshold(lv, tail_start, dry_rounds++);
         if (tail_handoff(lv, level, active && walk_iters >= thr, node, tv, cl.best_t, cl.best_tri, closed)) active = false;
@@ -707,7 +725,10 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
       uint32_t start = 0;
       if (lane == 0) start = atomicAdd(work_counter, want);
       start = __shfl_sync(CRT_FULL_MASK, start, 0);
-      if (start + want >= total) exhausted = true;
+      if (start + want >= total) {
+        if (!exhausted && start < total) queue_mark_dry(work_counter);  // (the warp that takes the last rays)
+        exhausted = true;
+      }
       const uint32_t i = start + __popc(idle & lanemask_lt());
       if (!active && i < total) {
         const uint32_t light = i / n_hits, hit = i - light * n_hits;
@@ -748,7 +769,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
       }
     }
     if (COUNT == 0 && tail_start != CRT_INVALID) {
-      if (!exhausted && (++round & 3u) == 0u) exhausted = queue_dry(work_counter, total);
+      if (!exhausted && (++round & (uint32_t)CRT_TAIL_POLL_MASK) == 0u) exhausted = queue_dry(work_counter);
       if (exhausted && !closed) {
         const uint32_t thr = tail_threshold(lv, tail_start, dry_rounds++);
         if (tail_handoff(lv, CRT_MAX_LEVELS, active && walk_iters >= thr, slot, tv, 0.0f, CRT_INVALID, closed)) active = false;
@@ -942,9 +963,9 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_co
   // Two passes per traversal launch.  early = 1: launched next to the traversal kernel on a second
   // stream; its blocks become resident as the traversal kernel's blocks exit and take records while the last lanes
   // there are still walking.  Record r is waited for until it is published, the traversal kernel has ended (ovf_ctl
-  // [4L+3], set by k_mark behind it) or CRT_COOP_SPINS polls have passed -- a bounded wait, so this pass can never hold
+  // word 24 of its line, set by k_mark behind it) or CRT_COOP_SPINS polls have passed -- a bounded wait, so this pass can never hold
   // the GPU against the kernel it waits for.  early = 0: launched behind both; takes whatever is still published.
-  volatile uint32_t *const ctl = lv.ovf_ctl + 4u * launch;
+  volatile uint32_t *const ctl = lv.ovf_ctl + CRT_CTL_STRIDE * launch;
   const uint32_t n_rec = early ? lv.ovf_cap : min(ctl[0], lv.ovf_cap);
   if (!early && blockIdx.x == 0 && threadIdx.x == 0 && n_rec) atomicAdd(&lv.stats[SHADOW ? 33 : 32], (unsigned long long)n_rec);
 
@@ -970,13 +991,13 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_co
     while (!busy && !drained) {
       uint32_t r = 0, got = CRT_INVALID;
       if (gl == 0) {
-        r = atomicAdd(const_cast<uint32_t *>(&ctl[early ? 1 : 2]), 1u);
+        r = atomicAdd(const_cast<uint32_t *>(&ctl[early ? 8 : 16]), 1u);
         if (r < n_rec) {
           uint32_t *flag = reinterpret_cast<uint32_t *>(lv.ovf + 3 * (size_t)r);
           if (early) {
             for (uint32_t spins = 0; spins < (uint32_t)CRT_COOP_SPINS; spins++) {
               if (*reinterpret_cast<volatile uint32_t *>(flag) != CRT_INVALID) break;
-              if (ctl[3]) break;  // the traversal kernel has ended: what is not published now never will be
+              if (ctl[24]) break;  // the traversal kernel has ended: what is not published now never will be
               __nanosleep(500);
             }
           }

@@ -908,7 +908,8 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
       CUDA_TRY(cudaEventCreateWithFlags(&q.coop_fork, cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&q.coop_join, cudaEventDisableTiming));
     }
-    const size_t n_counts = CRT_MAX_LEVELS + 1, n_work = CRT_MAX_LEVELS + 2, n_ovf = 4 * (CRT_MAX_LEVELS + 1);
+    // counts | work cursors | hand-off counters; every cursor / counter group on a 128-byte line of its own
+    const size_t n_counts = 64, n_work = CRT_CTL_STRIDE * (CRT_MAX_LEVELS + 2), n_ovf = CRT_CTL_STRIDE * (CRT_MAX_LEVELS + 1);
     CUDA_TRY(q.ctl.ensure(n_counts + n_work + n_ovf));
     q.work = q.ctl.p + n_counts;
     q.lv.ovf = q.ovf.p;
@@ -1026,7 +1027,7 @@ static int coop_end(crtb200_ctx *c, crtb200_ctx::QueueSet &q, bool primary, cons
     launches++;
   };
   if (coop_early_on(c, !SHADOW && !primary)) {
-    k_mark<<<1, 32, 0, q.stream>>>(q.lv.ovf_ctl + 4u * launch + 3u);
+    k_mark<<<1, 32, 0, q.stream>>>(q.lv.ovf_ctl + CRT_CTL_STRIDE * launch + 24u);
     run(c->sm_count * c->coop_early, q.coop_stream, 1u);
     CUDA_TRY(cudaEventRecord(q.coop_join, q.coop_stream));
     CUDA_TRY(cudaStreamWaitEvent(q.stream, q.coop_join, 0));
@@ -1137,13 +1138,13 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
         if (rc) return rc;
       }
       if (o->count_work && cull)
-        launch_closest<true, true>(c, l == 0, fr, q.lv, l, q.work + l, qs);
+        launch_closest<true, true>(c, l == 0, fr, q.lv, l, q.work + CRT_CTL_STRIDE * l, qs);
       else if (o->count_work)
-        launch_closest<true, false>(c, l == 0, fr, q.lv, l, q.work + l, qs);
+        launch_closest<true, false>(c, l == 0, fr, q.lv, l, q.work + CRT_CTL_STRIDE * l, qs);
       else if (cull)
-        launch_closest<false, true>(c, l == 0, fr, q.lv, l, q.work + l, qs);
+        launch_closest<false, true>(c, l == 0, fr, q.lv, l, q.work + CRT_CTL_STRIDE * l, qs);
       else
-        launch_closest<false, false>(c, l == 0, fr, q.lv, l, q.work + l, qs);
+        launch_closest<false, false>(c, l == 0, fr, q.lv, l, q.work + CRT_CTL_STRIDE * l, qs);
       if (handoff) {
         if (per_kernel) {
           cudaEventRecord(next_event(c), qs);
@@ -1161,7 +1162,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
       cudaEventRecord(next_event(c), qs);
       c->kev_kind.push_back(1);
     }
-    uint32_t *swork = q.work + CRT_MAX_LEVELS;
+    uint32_t *swork = q.work + CRT_CTL_STRIDE * CRT_MAX_LEVELS;
     if (handoff) {
       rc = coop_begin(c, q, false);
       if (rc) return rc;
