@@ -863,7 +863,7 @@ def main():
                     help="tiles, N > 1: peer (default) = every rank's store kernel writes its tiles into rank 0's frame with 16-byte stores "
                          "(CUDA IPC over NVLink; one NCCL all-reduce as completion barrier); gather = compact slabs, one NCCL gather, "
                          "crtb200_assemble_shards.  The other one is timed as an extra key")
-    ap.add_argument("--concurrency", type=int, default=4, help="chunks of a frame in flight on separate streams")
+    ap.add_argument("--concurrency", type=int, default=2, help="chunk streams of a host-bound frame (e2e); the library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--animation", type=int, default=0, help="F > 0: a step is the F-frame orbit animation (config 5), frames round-robin over GPUs")
     args = ap.parse_args()

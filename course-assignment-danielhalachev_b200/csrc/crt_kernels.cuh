@@ -62,7 +62,8 @@ struct Levels {
                       // [24] != 0 once the traversal kernel has ended
   uint32_t ovf_cap;     // walks k_coop can take per launch (about two per resident k_coop warp): hand-off stops there
   uint32_t tail_iters;  // 0 = off; else tail_iters - 1 = the floor of the hand-off threshold (see tail_policy)
-  uint32_t tail_start;  // the threshold's value when the queue of a large launch has just run dry (512)
+  uint32_t tail_start;  // the threshold's value when the queue of a large launch has just run dry: shadow pass (512)
+  uint32_t tail_start_closest;  // ... closest-hit launches
   uint32_t tail_small;  // launches of at most this many rays hand off at the floor from the start (see tail_policy)
   uint32_t skip_zero_terms;  // 1 (default traversal): shadow rays whose light term is exactly zero are answered without a walk
 };
@@ -273,10 +274,10 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, const
 #ifndef CRT_TAIL_POLL_MASK
 #define CRT_TAIL_POLL_MASK 3    // the global work cursor is polled every (this + 1)-th round
 #endif
-CRT_DI uint32_t tail_policy(const Levels &lv, const uint32_t total) {
+CRT_DI uint32_t tail_policy(const Levels &lv, const uint32_t total, const bool shadow) {
   if (!lv.tail_iters) return CRT_INVALID;
   const uint32_t lanes = gridDim.x * blockDim.x;
-  if (total > lanes) return lv.tail_start;
+  if (total > lanes) return shadow ? lv.tail_start : lv.tail_start_closest;
   return total <= lv.tail_small ? lv.tail_iters - 1u : CRT_INVALID;
 }
 CRT_DI uint32_t tail_threshold(const Levels &lv, const uint32_t start, const uint32_t dry_rounds) {
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, PRIMARY ? CRT_TRAV_MIN_BLOCKS 
   const uint32_t total = PRIMARY ? fr.n_items0 : lv.counts[level];
   const uint32_t node_base = lv.offset[level];
   const uint32_t lane = lane_id();
-  const uint32_t tail_start = COUNT ? CRT_INVALID : tail_policy(lv, total);
+  const uint32_t tail_start = COUNT ? CRT_INVALID : tail_policy(lv, total, false);
   bool active = false, exhausted = false, closed = false;
   uint32_t node = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0, dry_rounds = 0;
 #if CRT_PHASE_CLOCKS
@@ -703,7 +704,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
   const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];
   const uint32_t total = n_hits * sc.n_lights;
   const uint32_t lane = lane_id();
-  const uint32_t tail_start = COUNT ? CRT_INVALID : tail_policy(lv, total);
+  const uint32_t tail_start = COUNT ? CRT_INVALID : tail_policy(lv, total, true);
   bool active = false, exhausted = false, occluded = false, closed = false;
   uint32_t slot = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0, dry_rounds = 0, n_moot = 0;
 #if CRT_PHASE_CLOCKS

@@ -156,7 +156,8 @@ struct crtb200_ctx {
                              // falling threshold (512 node-phase iterations, halved every 4 rounds, never below this
                              // floor) go to k_coop.  CRT_TAIL_ITERS overrides (tools / tests): 0 = every walk still
                              // running (the threshold still falls from 512), -1 = off
-  int tail_start = 512;      // CRT_TAIL_START (tests): the threshold's starting value
+  int tail_start = 512;      // CRT_TAIL_START (tests): the threshold's starting value, shadow pass
+  int tail_start_closest = 128;  // CRT_TAIL_START_CLOSEST: ... closest-hit launches (run r2aq: 10M 2.04 -> 1.91 ms against 512)
   int tail_small = 32768;    // CRT_TAIL_SMALL: launches of at most this many rays hand off at the floor from the start
   int tail_cap = 8;          // hand-off capacity per launch, in walks per resident k_coop warp (CRT_TAIL_CAP; tests use
                              // a huge value so that every walk goes through k_coop)
@@ -208,7 +209,8 @@ struct crtb200_ctx {
     }
   };
   std::vector<QueueSet> sets;
-  uint32_t concurrency = 4;  // chunk streams of a host-bound frame (tools/e2e_time.py, round 2: 4K frame 3.93 ms with 4 streams x 2 chunks, 4.43 with 6 x 2)
+  uint32_t concurrency = 2;  // chunk streams of a host-bound frame (tools/e2e_time.py, run r2aq: 2 streams with one chunk each
+                             // at 1080p, two each at 4K; 4 streams x 2 chunks cost 1080p frames 15-17 %)
   cudaEvent_t fork_ev = nullptr;
   DevBuf<unsigned long long> stats_dev;
   uint32_t cap_items = 0;
@@ -295,7 +297,8 @@ int crtb200_create(int device, crtb200_ctx **out) {
   if (const char *env = getenv("CRT_L2_PERSIST")) c->l2_persist = atoi(env);
   if (const char *env = getenv("CRT_TAIL_ITERS")) c->tail_iters = std::max(-1, atoi(env));
   if (const char *env = getenv("CRT_TAIL_CAP")) c->tail_cap = std::max(1, atoi(env));
-  if (const char *env = getenv("CRT_TAIL_START")) c->tail_start = std::max(0, atoi(env));
+  if (const char *env = getenv("CRT_TAIL_START")) c->tail_start = c->tail_start_closest = std::max(0, atoi(env));
+  if (const char *env = getenv("CRT_TAIL_START_CLOSEST")) c->tail_start_closest = std::max(0, atoi(env));
   if (const char *env = getenv("CRT_TAIL_SMALL")) c->tail_small = std::max(0, atoi(env));
   if (const char *env = getenv("CRT_COOP_EARLY")) c->coop_early = std::max(0, std::min(CRT_COOP_MIN_BLOCKS, atoi(env)));
   c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
@@ -860,9 +863,9 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
   uint64_t items = c->queue_budget / (bytes_per_node * sum * n_sets);
   items &= ~31ull;
   if (items < 32 * 64) return fail(CRTB200_ERR_MEMORY, "queue budget too small for one chunk at this ray depth");
-  // one chunk per set when it fits; two per set when the bands are copied back to the host as they finish, so the
-  // copy of one band overlaps the traversal of the next
-  uint32_t per_set = (pipelined && n_sets > 1) ? 2u : 1u;
+  // host-bound frames: one chunk per stream at 1080p, two at 4K (a band's copy overlaps the traversal of the next band;
+  // every chunk pays its own kernel tails and, in reflective scenes, the latency of every level again)
+  uint32_t per_set = (pipelined && n_sets > 1 && shard_items >= (1u << 22)) ? 2u : 1u;
   if (const char *env = getenv("CRT_HOST_CHUNKS_PER_SET")) per_set = (uint32_t)std::max(1, std::min(8, atoi(env)));  // tools: e2e tuning
   const uint32_t parts = n_sets * per_set;
   uint64_t even = ((uint64_t)shard_items + parts - 1) / parts;
@@ -917,6 +920,7 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     q.lv.ovf_cap = (uint32_t)std::min<uint64_t>(ovf_cap, (uint64_t)c->tail_cap * c->blocks_coop * CRT_COOP_WARPS);
     q.lv.tail_iters = 0;
     q.lv.tail_start = 512;
+    q.lv.tail_start_closest = 128;
     q.lv.tail_small = 0;
     q.lv.skip_zero_terms = 0;
     q.lv.ray_o = q.ray_o.p;
@@ -1108,7 +1112,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
   for (uint32_t k = 0; k < n_sets; k++) CUDA_TRY(cudaStreamWaitEvent(c->sets[k].stream, c->fork_ev, 0));
   uint32_t launches = 0, chunk = 0;
   // band copies leave on their own stream, so a set starts its next chunk while its last band is still in flight
-  const bool band_stream = band_copies && n_sets > 1;
+  const bool band_stream = band_copies && n_sets > 1 && !getenv("CRT_NO_BAND_STREAM");
   if (band_stream) {
     if (!c->band_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->band_stream, cudaStreamNonBlocking));
     if (!c->band_done) CUDA_TRY(cudaEventCreateWithFlags(&c->band_done, cudaEventDisableTiming));
@@ -1127,6 +1131,7 @@ static int enqueue_frame(crtb200_ctx *c, const crtb200_camera *cam, const crtb20
     q.lv.tail_iters = handoff ? (uint32_t)(c->tail_iters + 1) : 0u;
     q.lv.skip_zero_terms = (o->traversal == 0 && o->count_work != 1) ? 1u : 0u;
     q.lv.tail_start = (uint32_t)c->tail_start;
+    q.lv.tail_start_closest = (uint32_t)c->tail_start_closest;
     q.lv.tail_small = (uint32_t)c->tail_small;
     for (uint32_t l = 0; l < levels; l++) {
       if (per_kernel) {

@@ -221,7 +221,7 @@ int crtb200_device_list(const crtb200_ctx *ctx, int *device_ids, int capacity, i
 int crtb200_destroy(crtb200_ctx *ctx);
 /* device budget in bytes for the per-frame ray queues (default 16 GiB); frames that need more are chunked */
 int crtb200_set_queue_budget(crtb200_ctx *ctx, uint64_t bytes);
-/* chunks of a frame rendered concurrently on separate streams (default 4; 1 = strictly sequential kernels, which is
+/* chunks of a frame rendered concurrently on separate streams (default 2; 1 = strictly sequential kernels, which is
  * what the per-kernel timers closest_ms / shadow_ms of crtb200_stats require -- they read 0 otherwise) */
 int crtb200_set_concurrency(crtb200_ctx *ctx, uint32_t chunks_in_flight);
 

@@ -65,8 +65,10 @@ def main():
                     env["CRT_TAIL_CAP"] = parts[1]
                 if len(parts) > 2:
                     env["CRT_TAIL_START"] = parts[2]
-                if len(parts) > 3:
+                if len(parts) > 3 and parts[3]:
                     env["CRT_TAIL_SMALL"] = parts[3]
+                if len(parts) > 4:
+                    env["CRT_TAIL_START_CLOSEST"] = parts[4]
             ctx = ctx_with_env(crt, env)
             ctx.upload(flat, keepalive=sf)
             ctx.set_concurrency(1)
