@@ -2,7 +2,7 @@
 # multi-GPU measurements on one box (run under `gpurun --gpus 8`): the driver's own launch line for N = 1, 2, 4, 8
 # (tiles = default), the C-ABI multi-GPU context (tests + timing), and the config-5 animation at N = 8.
 cd "$(dirname "$0")/.."
-O=gpurun_out; mkdir -p $O; TAG=${1:-r2s}
+O=gpurun_out; mkdir -p $O; export TAG=${1:-r2s}
 nvidia-smi --query-gpu=index,name --format=csv,noheader > $O/${TAG}_gpus.txt
 python bench.py --steps 10 --warmup 3 --no-config5 > $O/${TAG}_n1.json 2> $O/${TAG}_n1.err; tail -c 400 $O/${TAG}_n1.err
 for N in 2 4 8; do
@@ -14,7 +14,8 @@ timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "multi or bin
 timeout 600 python tools/multi_ctx_time.py > $O/${TAG}_multi_ctx.txt 2>&1; cat $O/${TAG}_multi_ctx.txt
 python - <<'PY'
 import json, glob
-for f in sorted(glob.glob("gpurun_out/r2s_n*.json")):
+import os
+for f in sorted(glob.glob("gpurun_out/" + os.environ.get("TAG", "r2s") + "_n*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, d.get("n_gpus"), "value %.1f" % d["value"], "ms %.3f" % d["ms_per_step"], "e2e %.1f" % d.get("e2e", {}).get("value", 0), d.get("tiles_check"), (d.get("frames_mode") or {}).get("value"))
