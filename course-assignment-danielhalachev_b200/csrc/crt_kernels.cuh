@@ -272,8 +272,21 @@ CRT_DI void tri_phase(const DScene &sc, WarpShare &ws, const bool pending, const
 #define CRT_TAIL_DECAY_SHIFT 2  // the threshold halves every 2^this rounds once the queue is dry
 #endif
 #ifndef CRT_TAIL_POLL_MASK
-#define CRT_TAIL_POLL_MASK 3    // the global work cursor is polled every (this + 1)-th round
+#define CRT_TAIL_POLL_MASK 3    // the queue's dry flag is polled every (this + 1)-th round ...
 #endif
+#ifndef CRT_TAIL_POLL_MASK_BIG
+#define CRT_TAIL_POLL_MASK_BIG 7  // ... in launches with more than CRT_TAIL_BIG rays per grid lane
+#endif
+#ifndef CRT_TAIL_BIG
+#define CRT_TAIL_BIG 32
+#endif
+// When a warp learns that the queue is dry decides when it starts handing off.  A launch with many rays per lane (a whole
+// 4K frame: 55) still has the SMs full of work at that moment, and k_coop's instructions compete with it: polling every
+// 8th round instead of every 4th is worth 4 % there; tile shards and small launches (2-14 rays per lane) lose 3-8 %
+// with it (profiles/r2_tuning.md 5.8).
+CRT_DI uint32_t tail_poll_mask(const uint32_t total) {
+  return total / (gridDim.x * blockDim.x) >= (uint32_t)CRT_TAIL_BIG ? (uint32_t)CRT_TAIL_POLL_MASK_BIG : (uint32_t)CRT_TAIL_POLL_MASK;
+}
 CRT_DI uint32_t tail_policy(const Levels &lv, const uint32_t total, const bool shadow) {
   if (!lv.tail_iters) return CRT_INVALID;
   const uint32_t lanes = gridDim.x * blockDim.x;
@@ -343,6 +356,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, PRIMARY ? CRT_TRAV_MIN_BLOCKS 
   const uint32_t node_base = lv.offset[level];
   const uint32_t lane = lane_id();
   const uint32_t tail_start = COUNT ? CRT_INVALID : tail_policy(lv, total, false);
+  const uint32_t poll_mask = tail_poll_mask(total);
   bool active = false, exhausted = false, closed = false;
   uint32_t node = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0, dry_rounds = 0;
 #if CRT_PHASE_CLOCKS
@@ -401,7 +415,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, PRIMARY ? CRT_TRAV_MIN_BLOCKS 
       }
     }
     if (!COUNT && tail_start != CRT_INVALID) {
-      if (!exhausted && (++round & (uint32_t)CRT_TAIL_POLL_MASK) == 0u) exhausted = queue_dry(work_counter);
+      if (!exhausted && (++round & poll_mask) == 0u) exhausted = queue_dry(work_counter);
       if (exhausted && !closed) {
         const uint32_t thr = tail_threshold(lv, tail_start, dry_rounds++);
         if (tail_handoff(lv, level, active && walk_iters >= thr, node, tv, cl.best_t, cl.best_tri, closed)) active = false;
@@ -705,6 +719,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
   const uint32_t total = n_hits * sc.n_lights;
   const uint32_t lane = lane_id();
   const uint32_t tail_start = COUNT ? CRT_INVALID : tail_policy(lv, total, true);
+  const uint32_t poll_mask = tail_poll_mask(total);
   bool active = false, exhausted = false, occluded = false, closed = false;
   uint32_t slot = 0, n_nodes = 0, n_tris = 0, round = 0, walk_iters = 0, dry_rounds = 0, n_moot = 0;
 #if CRT_PHASE_CLOCKS
@@ -770,7 +785,7 @@ __global__ void __launch_bounds__(CRT_TRAV_BLOCK, CRT_TRAV_MIN_BLOCKS) k_shadow(
       }
     }
     if (COUNT == 0 && tail_start != CRT_INVALID) {
-      if (!exhausted && (++round & (uint32_t)CRT_TAIL_POLL_MASK) == 0u) exhausted = queue_dry(work_counter);
+      if (!exhausted && (++round & poll_mask) == 0u) exhausted = queue_dry(work_counter);
       if (exhausted && !closed) {
         const uint32_t thr = tail_threshold(lv, tail_start, dry_rounds++);
         if (tail_handoff(lv, CRT_MAX_LEVELS, active && walk_iters >= thr, slot, tv, 0.0f, CRT_INVALID, closed)) active = false;

@@ -157,7 +157,7 @@ struct crtb200_ctx {
                              // floor) go to k_coop.  CRT_TAIL_ITERS overrides (tools / tests): 0 = every walk still
                              // running (the threshold still falls from 512), -1 = off
   int tail_start = 512;      // CRT_TAIL_START (tests): the threshold's starting value, shadow pass
-  int tail_start_closest = 128;  // CRT_TAIL_START_CLOSEST: ... closest-hit launches (run r2aq: 10M 2.04 -> 1.91 ms against 512)
+  int tail_start_closest = 256;  // CRT_TAIL_START_CLOSEST: ... closest-hit launches (runs r2aq, r2at: 10M 2.02 -> 1.95 ms against 512, hw07 0.96 -> 1.00; 128: 1.93 / 1.08)
   int tail_small = 32768;    // CRT_TAIL_SMALL: launches of at most this many rays hand off at the floor from the start
   int tail_cap = 8;          // hand-off capacity per launch, in walks per resident k_coop warp (CRT_TAIL_CAP; tests use
                              // a huge value so that every walk goes through k_coop)
@@ -920,7 +920,7 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
     q.lv.ovf_cap = (uint32_t)std::min<uint64_t>(ovf_cap, (uint64_t)c->tail_cap * c->blocks_coop * CRT_COOP_WARPS);
     q.lv.tail_iters = 0;
     q.lv.tail_start = 512;
-    q.lv.tail_start_closest = 128;
+    q.lv.tail_start_closest = 256;
     q.lv.tail_small = 0;
     q.lv.skip_zero_terms = 0;
     q.lv.ray_o = q.ray_o.p;

@@ -8,5 +8,5 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > $O/$
 for v in tree "$@"; do
   if [ "$v" = tree ]; then unset CRT_CORE_LIB; else export CRT_CORE_LIB=$PWD/build/variants/$v.so; fi
   echo "== $v" | tee -a $O/${TAG}_variants.txt
-  python tools/r2_measure.py --workloads $WL --tails ${TAILS:-16,-1} --shards 1,8 --frames 7 2>&1 | grep -v "^\[bench\]\|${SKIP:-zzzz}" | tee -a $O/${TAG}_variants.txt
+  python tools/r2_measure.py --workloads $WL --tails ${TAILS:-16,-1} --shards ${SHARDS:-1,8} --frames 7 2>&1 | grep -v "^\[bench\]\|${SKIP:-zzzz}" | tee -a $O/${TAG}_variants.txt
 done
