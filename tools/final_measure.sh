@@ -13,13 +13,14 @@ for w in hw07_scene0b hw11_room hw11_room_128 hw12_textures; do
   python bench.py --workload $w --steps 10 --warmup 3 --no-config5 > $O/${TAG}_bench_$w.json 2> $O/${TAG}_bench_$w.err
 done
 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_reference_arm.json 2> $O/${TAG}_bench_reference_arm.err
-# ncu: launch list of the bench command, then the full captures (each after its plain run exited 0)
+# ncu: launch list of the bench command, then the full captures (each after its plain run exited 0); a frame has six
+# traversal launches: k_closest + two k_coop passes, k_shadow + two k_coop passes
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-config5 > $O/${TAG}_plain_bench.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-config5 > $O/${TAG}_ncu_bench.log 2>&1
 for w in hw14_dragon_class synthetic_10M; do
   python tools/profile_frame.py --workload $w --frames 2 --concurrency 1 > $O/${TAG}_plain_$w.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:"k_closest|k_shadow|k_coop" -s 4 -c 4 -f -o $O/${TAG}_prof_$w \
+  ncu --set full --clock-control none --import-source on -k regex:"k_closest|k_shadow|k_coop" -s 6 -c 6 -f -o $O/${TAG}_prof_$w \
       python tools/profile_frame.py --workload $w --frames 2 --concurrency 1 > $O/${TAG}_ncu_$w.log 2>&1
 done
 python - <<PY

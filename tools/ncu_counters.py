@@ -72,8 +72,7 @@ def group(launches, main, frames):
             sel.append(l)
             take_coop = True
         elif "k_coop<" in l["name"] and take_coop:
-            sel.append(l)
-            take_coop = False
+            sel.append(l)  # (both passes of k_coop behind the main kernel)
         elif "k_coop<" not in l["name"]:
             take_coop = False
     if not sel:
