@@ -5,7 +5,10 @@
 //   K4/K5 k_shade                   per-hit: barycentrics, smooth normal, texture sample, material switch,
 //                                   reflect / refract + Fresnel, compaction of children into the next level's queue
 //   K3  k_shadow                    persistent any-hit traversal, one (diffuse hit, light) pair per lane -> visibility
-//   K3b k_accumulate                in-order light sum per diffuse hit
+//   K2b/K3b k_coop                  the walks K2 / K3 hand off once their queue is dry: one warp per walk, a LIFO of
+//                                   subtrees in shared memory; an early pass runs next to the traversal kernel
+//                                   (k_mark tells it that the kernel has ended), a final pass behind both
+//   K3c k_accumulate                in-order light sum per diffuse hit
 //   K6  k_resolve                   bottom-up combine of the ray tree in the reference's expression order
 //   K7  k_store                     level-0 colours -> framebuffer (f32 + PPMColor u8)
 //
@@ -55,12 +58,12 @@ struct Levels {
   unsigned long long *stats;  // [0..3] rays by type, [4],[5] closest node / triangle tests, [6],[7] shadow, [32],[33] walks handed to k_coop, [40] shadow rays answered without a walk
   uint32_t offset[CRT_MAX_LEVELS + 1];
   // tail hand-off (k_coop): once the work queue of a traversal kernel is dry, the walks still running are written to
-  // ovf[] (3 x uint4 per record) and finished one WARP per ray; tail_grace = 0 switches this off
+  // ovf[] (3 x uint4 per record) and finished one WARP per ray; tail_iters = 0 switches this off
   uint4 *ovf;
   uint32_t *ovf_ctl;  // per traversal launch L (level, or CRT_MAX_LEVELS for the shadow pass) one 128-byte line at
                       // ovf_ctl + 32 L: [0] written, [8] / [16] next record index of the early / the final k_coop pass,
                       // [24] != 0 once the traversal kernel has ended
-  uint32_t ovf_cap;     // walks k_coop can take per launch (about two per resident k_coop warp): hand-off stops there
+  uint32_t ovf_cap;     // walks k_coop can take per launch (CRT_TAIL_CAP = 8 per resident k_coop warp): hand-off stops there
   uint32_t tail_iters;  // 0 = off; else tail_iters - 1 = the floor of the hand-off threshold (see tail_policy)
   uint32_t tail_start;  // the threshold's value when the queue of a large launch has just run dry: shadow pass (512)
   uint32_t tail_start_closest;  // ... closest-hit launches
@@ -1261,7 +1264,7 @@ __global__ void __launch_bounds__(32 * CRT_COOP_WARPS, CRT_COOP_MIN_BLOCKS) k_co
 #endif
 }
 
-// K3b: the light loop of RayTracer::calculateDiffusion (RayTracer.cpp:308-330): per diffuse hit, walk the lights IN
+// K3c: the light loop of RayTracer::calculateDiffusion (RayTracer.cpp:308-330): per diffuse hit, walk the lights IN
 // ORDER and add `direct * albedo` for the unshadowed ones, so the float sum is formed exactly like the reference's.
 __global__ void __launch_bounds__(256) k_accumulate(const DScene sc, const Frame fr, const Levels lv) {
   const uint32_t n_hits = lv.counts[CRT_MAX_LEVELS];

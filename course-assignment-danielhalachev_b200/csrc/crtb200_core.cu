@@ -851,8 +851,7 @@ static int plan_queues(crtb200_ctx *c, uint32_t shard_items, uint32_t max_depth,
   const uint64_t bytes_per_node = 32 + 8 + 16 + 16 + 48 + n_lights;  // ray + hit + colour + comb + diffuse item + visibility bytes
   // sets used: up to `concurrency`, but never chunks smaller than 64 Ki items (launch overhead would dominate)
   uint32_t n_sets = std::max<uint32_t>(1, std::min<uint32_t>(c->concurrency, (shard_items + 65535u) / 65536u));
-  // host-bound frames: two chunks per set of at least ~256 Ki items each (tools/e2e_time.py: the 4K frame is best with 6
-  // sets, 1080p frames with 4; smaller chunks only add launches and tails)
+  // host-bound frames: chunks of at least ~512 Ki items (smaller ones only add launches and tails)
   if (pipelined) n_sets = std::max<uint32_t>(1, std::min<uint32_t>(n_sets, (shard_items + (1u << 19) - 1u) >> 19));
   // measured (profiles/r1_tuning.md): overlapping chunks only pays when band copies to the host ride along; the
   // persistent kernels already fill the GPU, extra chunks just add launches and tails
