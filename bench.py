@@ -471,19 +471,23 @@ def ours_arm(args):
     frames_mode = world > 1 and parallelism == "frames"
 
     def timed_per_step(step_fn, steps):
-        """flush L2, barrier, event pair per step; returns per-step ms of this rank"""
+        """K steps bracketed by a barrier + synchronize on both sides; per step: L2 flush (outside the events), event pair
+        around the step.  Everything is queued asynchronously: with N > 1 the ranks re-align on the device at the end of
+        every step (the step's own collective), so a step's events contain no host-side barrier.  Returns per-step ms of
+        this rank and the last step's stats."""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        st = []
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         for k in range(steps):
             flush.fill_(k & 0xFF)  # L2 flush (256 MiB > 126 MB L2), outside the timed events
-            if world > 1:
-                dist.barrier()
             ev[k][0].record()
             step_fn()
             ev[k][1].record()
-            torch.cuda.synchronize()
-            st.append(ctx.last_stats())
-        return [a.elapsed_time(b) for a, b in ev], st
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return [a.elapsed_time(b) for a, b in ev], [ctx.last_stats()]
 
     def timed_frames(steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
