@@ -399,6 +399,8 @@ def ours_arm(args):
     sharded = None
     peer = None
     tiles_check = None
+    single_frame_host = None
+    mg = None
     if world > 1:
         mg = importlib.import_module(PKG + ".multigpu")
         sharded = mg.ShardedRenderer(crt, ctx, torch, dist, dev)  # NCCL gather of slabs + assembly on rank 0
@@ -420,6 +422,7 @@ def ours_arm(args):
             tiles_check = {"pixels": W * H,
                            "peer_store": {"pixels_differing_from_single_gpu_frame": differing(pframe), "rgb8_equal": bool(torch.equal(pframe8, single8))},
                            "nccl_gather": {"pixels_differing_from_single_gpu_frame": differing(frame), "rgb8_equal": bool(torch.equal(frame8, single8))}}
+            single_frame_host = single.cpu().numpy()  # (kept for the check of the zero-copy host frame of the e2e leg)
             del single, single8
             for k in ("peer_store", "nccl_gather"):
                 if tiles_check[k]["pixels_differing_from_single_gpu_frame"] or not tiles_check[k]["rgb8_equal"]:
@@ -546,17 +549,50 @@ def ours_arm(args):
     e2e_multi_ms = None
     frames_extra = None
     other_extra = None
+    e2e_zero_copy = False
     if tiles_mode:
+        # the ranks' store kernels write straight into one pinned host frame shared by the ranks (each GPU over its own
+        # PCIe link); falls back to "assemble on rank 0's GPU, then one device-to-host copy" when the registration fails
+        shared = None
+        if use_peer:
+            shared = mg.SharedHostFrame(torch, dist, W, H)  # (collective; never raises on one rank alone)
+            if not shared.usable:
+                log("[bench] shared pinned host frame unavailable; e2e copies the assembled frame from rank 0")
+                shared.close()
+                shared = None
+        if shared is not None:
+            peer.render_to_host(cam, shared, max_depth=depth, traversal=args.traversal)
+            torch.cuda.synchronize()
+            dist.barrier()
+            if rank == 0:
+                import numpy as np
+                a32, b32 = shared.array.view(np.uint32), single_frame_host.view(np.uint32)
+                diff = int(((a32 != b32) & ~(np.isnan(shared.array) & np.isnan(single_frame_host))).any(axis=2).sum())
+                tiles_check["host_zero_copy"] = {"pixels_differing_from_single_gpu_frame": diff}
+                if diff:
+                    raise SystemExit(f"zero-copy host frame differs from the single-GPU frame on {diff} pixels")
+            e2e_zero_copy = True
+
+        def step_e2e():
+            if shared is not None:
+                peer.render_to_host(cam, shared, max_depth=depth, traversal=args.traversal)
+            else:
+                step_tiles(to_host=True)
+
         a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for k in range(2):
+            step_e2e()
         dist.barrier()
         torch.cuda.synchronize()
         a.record()
         for k in range(args.steps):
-            step_tiles(to_host=True)
+            step_e2e()
         b2.record()
         torch.cuda.synchronize()
         dist.barrier()
         e2e_multi_ms = max_over_ranks(a.elapsed_time(b2)) / args.steps
+        if shared is not None:
+            shared.close()
         # extra key: the other transport of the same tile split
         other = step_tiles_gather if use_peer else step_tiles_peer
         for k in range(3):
@@ -598,7 +634,10 @@ def ours_arm(args):
     elif tiles_mode:
         e2e = {"value": rays_step / (e2e_multi_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_multi_ms,
                "h2d_bytes_per_step": (48 + 40 + 16 * n_rects) * world, "d2h_bytes_per_step": W * H * 12,
-               "api": ("crtb200_render_device shard per rank, stored straight into rank 0's frame (CUDA IPC over NVLink) -> pinned host float RGB on rank 0"
+               "api": ("crtb200_render_device shard per rank; every rank's store kernel writes its tiles straight into ONE pinned host float frame "
+                       "shared by the ranks (POSIX shm + cudaHostRegister: zero-copy over each GPU's own PCIe link), NCCL all-reduce as barrier"
+                       if e2e_zero_copy else
+                       "crtb200_render_device shard per rank, stored straight into rank 0's frame (CUDA IPC over NVLink) -> pinned host float RGB on rank 0"
                        if use_peer else "crtb200_render_device shard per rank -> NCCL gather -> crtb200_assemble_shards -> pinned host float RGB on rank 0")}
     else:
         e2e = None

@@ -91,6 +91,16 @@ class PeerStoreRenderer:
         self.ctx.render_device(camera, opt, d_rgb=self.d_rgb, d_rgb8=self.d_rgb8, stream=stream)
         self.dist.all_reduce(self._flag)  # completion barrier: rank 0's stream continues when every rank has stored
 
+    def render_to_host(self, camera, host_frame: "SharedHostFrame", max_depth: int = 5, traversal: int = 0) -> None:
+        """The same split, but every rank's store kernel writes its tiles into `host_frame` (pinned host memory shared by
+        the ranks) over its own PCIe link.  After the call (on every rank's stream, behind the all-reduce) the host frame
+        is complete."""
+        stream = self.torch.cuda.current_stream().cuda_stream
+        opt = self.crt.make_options(max_depth=max_depth, shard_index=self.rank, shard_count=self.world, traversal=traversal,
+                                    shard_full_frame=True)
+        self.ctx.render_device(camera, opt, d_rgb=host_frame.device_ptr, stream=stream)
+        self.dist.all_reduce(self._flag)
+
     def close(self):
         for p in self._mapped:
             self.crt.ipc_close(self.device.index, p)
@@ -99,6 +109,74 @@ class PeerStoreRenderer:
             for p in self._own:
                 self.crt.ipc_free(self.device.index, p)
             self._own = None
+
+
+class SharedHostFrame:
+    """A float RGB frame in pinned host memory that every rank of one node can write from its GPU: rank 0 creates a POSIX
+    shared-memory segment, every rank maps it and registers it with CUDA (cudaHostRegister, portable + mapped).  With
+    `PeerStoreRenderer.render_to_host` each rank's store kernel then writes its tiles straight into this frame over its
+    own GPU's PCIe link (zero-copy), so an N-GPU frame reaches the host without a pass through rank 0's GPU and its
+    single link.  `array` is the numpy view (H, W, 3); `device_ptr` the address the kernels use."""
+
+    def __init__(self, torch, dist, width: int, height: int):
+        from multiprocessing import shared_memory
+        self.torch, self.dist = torch, dist
+        self.rank = dist.get_rank()
+        self.nbytes = width * height * 3 * 4
+        self.shm = None
+        self.array = None
+        self.registered = False
+        self.host_ptr = self.device_ptr = 0
+        # no rank may leave this constructor early: every step below is followed by a collective
+        name = [None]
+        if self.rank == 0:
+            try:
+                self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+                name[0] = self.shm.name
+            except Exception:
+                self.shm = None
+        dist.broadcast_object_list(name, src=0)
+        if name[0] is not None:
+            try:
+                if self.rank != 0:
+                    self.shm = shared_memory.SharedMemory(name=name[0])
+                    try:  # Python < 3.13 registers attached segments with the resource tracker as if this process owned
+                        from multiprocessing import resource_tracker  # them and warns about a "leak" at exit
+                        resource_tracker.unregister(self.shm._name, "shared_memory")
+                    except Exception:
+                        pass
+                self.array = np.ndarray((height, width, 3), dtype=np.float32, buffer=self.shm.buf)
+                self.host_ptr = self.array.ctypes.data
+                rc = int(torch.cuda.cudart().cudaHostRegister(self.host_ptr, self.nbytes, 1 | 2))  # portable | mapped
+                self.registered = rc == 0
+                self.device_ptr = self.host_ptr  # unified addressing: registered host memory keeps its address on x86-64 ...
+                if self.registered:
+                    try:  # ... but ask when the runtime binding is there
+                        from cuda.bindings import runtime as cudart
+                        err, dptr = cudart.cudaHostGetDevicePointer(self.host_ptr, 0)
+                        if int(err) == 0:
+                            self.device_ptr = int(dptr)
+                    except Exception:
+                        pass
+            except Exception:
+                self.registered = False
+        ok = torch.tensor([1 if self.registered else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        self.usable = bool(ok.item())
+
+    def close(self):
+        if getattr(self, "registered", False):
+            self.torch.cuda.cudart().cudaHostUnregister(self.host_ptr)
+            self.registered = False
+        if getattr(self, "shm", None) is not None:
+            self.array = None
+            try:
+                self.shm.close()
+                if self.rank == 0:
+                    self.shm.unlink()
+            except Exception:
+                pass
+            self.shm = None
 
 
 class ShardedRenderer:
