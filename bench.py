@@ -22,12 +22,14 @@ is quoted on that fits one GPU.
   literal_walk  the reference's visit-all itinerary (traversal = 1) beside the default, with the pixel difference (0)
 
 N > 1 (torchrun), scene replicated per GPU:
-  tiles (default)                 one frame, 8x4-pixel tiles dealt round-robin; every rank's store kernel writes its tiles
-                                  straight into rank 0's frame (peer memory over NVLink, CUDA IPC; one tiny NCCL all-reduce as
-                                  completion barrier).  Strong scaling: total work fixed.  The frame is checked bit-equal to
-                                  the single-GPU frame before timing (tiles_check).  --tile-transport gather: compact float
-                                  slabs gathered to rank 0 over NCCL and scattered into the frame instead; the other transport
-                                  is timed as `tiles_other_transport`, the frames partition as `frames_mode`.
+  tiles (default)                 one frame, 8x4-pixel tiles dealt round-robin.  Up to 4 GPUs every rank's store kernel writes
+                                  its tiles straight into rank 0's frame (peer memory over NVLink, CUDA IPC; one tiny NCCL
+                                  all-reduce as completion barrier); beyond, compact float slabs are gathered to rank 0 over
+                                  NCCL and scattered into the frame (--tile-transport peer | gather forces one).  Strong
+                                  scaling: total work fixed.  Both frames are checked bit-equal to the single-GPU frame before
+                                  timing (tiles_check); the transport not used is timed as `tiles_other_transport`, the frames
+                                  partition as `frames_mode`.  e2e: every rank's store kernel writes its tiles into ONE pinned
+                                  host frame shared by the ranks (zero-copy over each GPU's own PCIe link).
   --parallelism frames            every rank renders one frame of the sequence per step, PPMColor bytes gathered to rank 0
                                   over NCCL overlapped with the next render.  Weak scaling: per-GPU work fixed.
   --animation F                   config 5's orbit: frame f on rank f % N, frames gathered to rank 0.
@@ -439,7 +441,9 @@ def ours_arm(args):
         gls = [[gflat[b][i] for i in range(world)] for b in range(2)] if rank == 0 else [None, None]
     host_frame = torch.empty((H, W, 3), dtype=torch.float32).pin_memory() if (world > 1 and rank == 0) else None
 
-    use_peer = args.tile_transport == "peer"
+    # auto: peer stores up to 4 GPUs, the NCCL gather beyond (run r2fs / r2bc, ms per 4K frame peer / gather: N = 2
+    # 1.77 / 1.81, N = 4 1.28 / 1.29, N = 8 1.03-1.05 / 0.95-1.02: eight writers into one GPU's frame lose to NCCL's transfer)
+    use_peer = args.tile_transport == "peer" or (args.tile_transport == "auto" and world <= 4)
 
     def step_tiles_gather(to_host=False):
         sharded.render(cam, max_depth=depth, traversal=args.traversal, frame=frame if rank == 0 else None,
@@ -553,13 +557,11 @@ def ours_arm(args):
     if tiles_mode:
         # the ranks' store kernels write straight into one pinned host frame shared by the ranks (each GPU over its own
         # PCIe link); falls back to "assemble on rank 0's GPU, then one device-to-host copy" when the registration fails
-        shared = None
-        if use_peer:
-            shared = mg.SharedHostFrame(torch, dist, W, H)  # (collective; never raises on one rank alone)
-            if not shared.usable:
-                log("[bench] shared pinned host frame unavailable; e2e copies the assembled frame from rank 0")
-                shared.close()
-                shared = None
+        shared = mg.SharedHostFrame(torch, dist, W, H)  # (collective; never raises on one rank alone)
+        if not shared.usable:
+            log("[bench] shared pinned host frame unavailable; e2e copies the assembled frame from rank 0")
+            shared.close()
+            shared = None
         if shared is not None:
             peer.render_to_host(cam, shared, max_depth=depth, traversal=args.traversal)
             torch.cuda.synchronize()
@@ -902,10 +904,10 @@ def main():
     ap.add_argument("--parallelism", default="auto", choices=["auto", "frames", "tiles"],
                     help="N > 1: tiles (default) = one frame split by 8x4 tiles (strong scaling, config 4); frames = one frame per GPU per step (weak)")
     ap.add_argument("--no-config5", action="store_true", help="skip the synthetic_10M sub-record (N = 1)")
-    ap.add_argument("--tile-transport", default="peer", choices=["gather", "peer"],
-                    help="tiles, N > 1: peer (default) = every rank's store kernel writes its tiles into rank 0's frame with 16-byte stores "
+    ap.add_argument("--tile-transport", default="auto", choices=["auto", "gather", "peer"],
+                    help="tiles, N > 1: peer = every rank's store kernel writes its tiles into rank 0's frame with 16-byte stores "
                          "(CUDA IPC over NVLink; one NCCL all-reduce as completion barrier); gather = compact slabs, one NCCL gather, "
-                         "crtb200_assemble_shards.  The other one is timed as an extra key")
+                         "crtb200_assemble_shards; auto (default) = peer up to 4 GPUs, gather beyond.  The other one is timed as an extra key")
     ap.add_argument("--concurrency", type=int, default=2, help="chunk streams of a host-bound frame (e2e); the library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--animation", type=int, default=0, help="F > 0: a step is the F-frame orbit animation (config 5), frames round-robin over GPUs")
