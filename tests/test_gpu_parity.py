@@ -477,3 +477,55 @@ def test_shards_written_in_place_make_the_same_frame(gpu, loaded, crt):
     torch.cuda.synchronize()
     assert same_f32(out.cpu().numpy(), full).all()
     assert np.array_equal(out8.cpu().numpy(), full8)
+
+
+def test_shards_stored_into_pinned_host_memory_make_the_same_frame(gpu, loaded, crt):
+    """The e2e leg of an N-GPU frame: every rank's store kernel writes its tiles straight into ONE pinned host frame
+    (multigpu.SharedHostFrame: mapped host memory, zero-copy over PCIe).  Here: three shards of one GPU into a pinned
+    host tensor == the unsharded frame."""
+    torch = pytest.importorskip("torch")
+    sf, flat, _, _ = loaded["hw14_small"]
+    gpu.upload(flat, keepalive=sf)
+    full, _, _, _ = gpu.render(sf.camera(), crt.make_options())
+    H, W = sf.info.height, sf.info.width
+    host = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory()
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(3):
+        # (pinned memory allocated by the CUDA runtime is mapped; under unified addressing its device address is its host address)
+        gpu.render_device(sf.camera(), crt.make_options(shard_index=r, shard_count=3, shard_full_frame=True),
+                          d_rgb=host.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert same_f32(host.numpy(), full).all()
+
+
+def test_shared_host_frame_single_rank(gpu, built, loaded, crt):
+    """multigpu.SharedHostFrame + PeerStoreRenderer.render_to_host with a one-rank process group (the collective plumbing,
+    the shared-memory segment, cudaHostRegister): the host frame equals the frame of a plain render."""
+    torch = pytest.importorskip("torch")
+    import socket
+    import torch.distributed as dist
+    mg = importlib.import_module(PKG + ".multigpu")
+    if dist.is_initialized():
+        pytest.skip("a process group already exists in this process")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        sf, flat, _, _ = loaded["hw11_room"]
+        gpu.upload(flat, keepalive=sf)
+        full, _, _, _ = gpu.render(sf.camera(), crt.make_options())
+        H, W = sf.info.height, sf.info.width
+        dev = torch.device("cuda", 0)
+        peer = mg.PeerStoreRenderer(crt, gpu, torch, dist, dev, W, H)
+        shared = mg.SharedHostFrame(torch, dist, W, H)
+        assert shared.usable
+        shared.array[:] = 0
+        peer.render_to_host(sf.camera(), shared)
+        torch.cuda.synchronize()
+        assert same_f32(np.array(shared.array), full).all()
+        shared.close()
+        peer.close()
+    finally:
+        dist.destroy_process_group()
